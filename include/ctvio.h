@@ -1,0 +1,216 @@
+/*
+ * ctvio.h — C-ABI of the B200-native sliding-window continuous-time bundle
+ * adjustment engine (libctvio_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of APRIL-ZJU/Ctrl-VIO:
+ * everything behind `TrajectoryEstimator::Solve()` /
+ * `TrajectoryEstimator::SaveMarginalizationInfo()`.  The reference has no FFI;
+ * its seam is the C++ class `ctrlvio::TrajectoryEstimator`
+ * (src/estimator/trajectory_estimator.h:61-206).  Each entry point below names
+ * the reference interface it replaces (paths relative to the reference's src/).
+ * Pointer identity of Ceres parameter blocks becomes INDEX identity: global
+ * knot index, bias-node index, landmark index.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types; all pointers are HOST pointers unless the
+ *     name ends in `_device`.
+ *   - quaternions are [x, y, z, w] (Eigen/Sophus coeff order, sophus_lib/so3.hpp:196).
+ *   - times are int64 nanoseconds relative to the trajectory start.
+ *   - every function returns CTVIO_OK (0) or a negative error code; the message
+ *     is available from ctvio_last_error().  There is NO CPU fallback: without
+ *     a usable CUDA device ctvio_create fails with CTVIO_ERR_NO_DEVICE.
+ */
+#ifndef CTVIO_H_
+#define CTVIO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTVIO_ABI_VERSION 1
+
+enum {
+  CTVIO_OK = 0,
+  CTVIO_ERR_INVALID = -1,    /* bad argument / index out of range            */
+  CTVIO_ERR_NO_DEVICE = -2,  /* no CUDA device / wrong architecture           */
+  CTVIO_ERR_CUDA = -3,       /* CUDA runtime error (see ctvio_last_error)     */
+  CTVIO_ERR_STATE = -4,      /* call sequence error (e.g. solve before state) */
+  CTVIO_ERR_NCCL = -5,
+  CTVIO_ERR_TIME_RANGE = -6  /* a factor time falls outside the spline (the reference asserts,
+                                spline_segment.h:80) */
+};
+
+/* parameter-block kinds used by the prior (marginalization_factor.h keep_block_*) */
+enum {
+  CTVIO_BLK_ROT = 0, /* knot rotation, 4 stored / 3 tangent (ceres_local_param.h:125-166) */
+  CTVIO_BLK_POS = 1, /* knot position, 3                                                   */
+  CTVIO_BLK_BG = 2,  /* gyro bias of a bias node, 3                                        */
+  CTVIO_BLK_BA = 3,  /* accel bias of a bias node, 3                                       */
+  CTVIO_BLK_LD = 4,  /* camera line delay, 1                                               */
+  CTVIO_BLK_RHO = 5  /* landmark inverse depth, 1                                          */
+};
+
+/* ceres::TerminationType / message analogue returned by ctvio_solve */
+enum {
+  CTVIO_TERM_NO_CONVERGENCE = 0, /* max_num_iterations reached */
+  CTVIO_TERM_GRADIENT = 1,
+  CTVIO_TERM_PARAMETER = 2,
+  CTVIO_TERM_FUNCTION = 3,
+  CTVIO_TERM_FAILURE = 4,
+  CTVIO_TERM_MIN_RADIUS = 5
+};
+
+typedef struct ctvio_engine* ctvio_handle;
+
+/* Static configuration of a trajectory + sensor rig.
+ *   replaces: Trajectory ctor (spline/trajectory.h:45-53), InitFactorInfo
+ *   (estimator/trajectory_manager.cpp:51-62: S_CtoI, p_CinI, sqrt_info),
+ *   OptWeight::imu_info_vec (utils/opt_weight.h:124-126), gravity_
+ *   (estimator/odometry_manager.cpp:423). */
+typedef struct ctvio_config {
+  int64_t t0_ns;          /* minTimeNs of knot 0                                  */
+  int64_t dt_ns;          /* knot spacing (config/ct_odometry_tumrs.yaml:13 -> 50 ms) */
+  double q_CtoI[4];       /* camera->IMU rotation, xyzw                           */
+  double p_CinI[3];       /* camera position in IMU frame                         */
+  double image_weight;    /* sqrt_info = image_weight * I2                        */
+  double gravity[3];
+  double imu_info[6];     /* 1/sigma_g x3, 1/sigma_a x3                           */
+  int64_t rs_padding_ns;  /* rolling-shutter time padding, 39 ms (estimator.cpp:299) */
+  double cauchy_solve;    /* CauchyLoss scale in Solve, 2 (estimator.cpp:321)     */
+  double cauchy_marg;     /* CauchyLoss scale for marginalized features, 1        */
+  int32_t device;         /* CUDA device ordinal                                  */
+  int32_t reserved;
+} ctvio_config;
+
+/* Per-problem options.
+ *   replaces: TrajectoryEstimatorOptions (estimator/trajectory_estimator_options.h:34-68),
+ *   TrajectoryEstimator::SetFixedIndex (trajectory_estimator.h:90),
+ *   Trajectory::SetLineDelay (spline/trajectory.h:55-62). */
+typedef struct ctvio_options {
+  int32_t fixed_knot_index; /* knots <= index are constant; -1 = none */
+  int32_t lock_traj;
+  int32_t lock_wb;          /* gyro biases constant  */
+  int32_t lock_ab;          /* accel biases constant */
+  int32_t fix_ld;           /* line delay constant   */
+  int32_t is_marg_state;
+  int32_t ctrl_to_be_opt_now;
+  int32_t ctrl_to_be_opt_later;
+  double ld_lower, ld_upper;
+} ctvio_options;
+
+/* ceres::Solver::Summary analogue (only what the caller logs / we measure). */
+typedef struct ctvio_summary {
+  int32_t iterations;             /* LM steps after iteration 0 (accepted + rejected + invalid) */
+  int32_t num_successful_steps;   /* includes iteration 0, like Ceres */
+  int32_t num_unsuccessful_steps;
+  int32_t termination;            /* CTVIO_TERM_* */
+  int32_t num_cost_evals;         /* cost-only passes over all residual blocks */
+  int32_t num_jacobian_evals;     /* residual+Jacobian passes over all residual blocks */
+  int32_t num_linear_solves;
+  int32_t num_line_search_steps;
+  double initial_cost, final_cost, final_radius;
+  double device_ms;               /* CUDA-event time of the whole solve on the engine stream */
+  int64_t kernel_launches;        /* kernels launched by this solve */
+} ctvio_summary;
+
+const char* ctvio_last_error(void);
+int ctvio_abi_version(void);
+
+/* lifecycle — replaces `new TrajectoryEstimator(trajectory, option)`
+ * (estimator/trajectory_estimator.cpp:97-112); one engine may be reused across windows. */
+int ctvio_create(const ctvio_config* cfg, ctvio_handle* out);
+int ctvio_destroy(ctvio_handle h);
+int ctvio_set_options(ctvio_handle h, const ctvio_options* opt);
+
+/* state in — replaces the raw `double*` parameter blocks handed to
+ * problem_->AddParameterBlock (estimator/trajectory_estimator.cpp:114-141,
+ * 230-247, 305-318): knots of Trajectory, all_imu_bias_, para_Feature,
+ * trajectory_->line_delay. Host -> HBM copies. */
+int ctvio_set_knots(ctvio_handle h, int32_t n_knots, const double* q_xyzw, const double* p_xyz);
+int ctvio_set_biases(ctvio_handle h, int32_t n_nodes, const double* bg_ba6);
+int ctvio_set_inv_depths(ctvio_handle h, int32_t n_landmarks, const double* inv_depth);
+int ctvio_set_line_delay(ctvio_handle h, double line_delay);
+
+/* state out — the solver updates the blocks in place in the reference; here
+ * the caller reads them back. HBM -> host copies. */
+int ctvio_get_knots(ctvio_handle h, double* q_xyzw, double* p_xyz);
+int ctvio_get_biases(ctvio_handle h, double* bg_ba6);
+int ctvio_get_inv_depths(ctvio_handle h, double* inv_depth);
+int ctvio_get_line_delay(ctvio_handle h, double* line_delay);
+
+/* factors.  `marg` arrays may be NULL (all zero). */
+int ctvio_clear_factors(ctvio_handle h);
+/* replaces TrajectoryEstimator::AddImageFeatureDelayAnalytic (estimator/trajectory_estimator.cpp:293-332),
+ * batched: observation k links anchor (ti,rowi,pi) to (tj,rowj,pj) of landmark lm[k]. */
+int ctvio_add_image_features(ctvio_handle h, int32_t n, const int64_t* ti, const int32_t* rowi,
+                             const double* pi_xy, const int64_t* tj, const int32_t* rowj,
+                             const double* pj_xy, const int32_t* landmark, const int32_t* marg);
+/* replaces TrajectoryEstimator::AddIMUMeasurementAnalytic (:219-263), batched. */
+int ctvio_add_imu_measurements(ctvio_handle h, int32_t n, const int64_t* t, const double* gyro_xyz,
+                               const double* accel_xyz, const int32_t* bias_node, const int32_t* marg);
+/* replaces TrajectoryEstimator::AddBiasFactor (:265-291); sqrt_info is already divided by sqrt(dt). */
+int ctvio_add_bias_factors(ctvio_handle h, int32_t n, const int32_t* node_i, const int32_t* node_j,
+                           const double* sqrt_info6, const int32_t* marg);
+/* replaces TrajectoryEstimator::AddMarginalizationFactor (:334-348) +
+ * MarginalizationInfo::{linearized_jacobians, linearized_residuals, keep_block_*}
+ * (factor/analytic_diff/marginalization_factor.h:96-131).  n == 0 clears the prior. */
+int ctvio_set_prior(ctvio_handle h, int32_t n, const double* J_lin_rowmajor, const double* r_lin,
+                    int32_t n_blocks, const int32_t* blk_type, const int32_t* blk_index,
+                    const int32_t* blk_col, const double* blk_x0_4);
+
+/* replaces TrajectoryEstimator::Solve -> ceres::Solve (estimator/trajectory_estimator.cpp:367-408):
+ * LM trust region, Jacobi scaling, Cauchy loss, bounds on the line delay; state is updated in HBM. */
+int ctvio_solve(ctvio_handle h, int32_t max_iterations, ctvio_summary* summary);
+
+/* replaces TrajectoryManager::double2vector (estimator/trajectory_manager.cpp:485-516):
+ * 4-DoF (yaw + translation) re-alignment of knots >= min_idx to the pre-solve pose (R0 row-major, t0). */
+int ctvio_gauge_realign(ctvio_handle h, int32_t min_idx, const double* R0_rowmajor9, const double* t0_xyz);
+
+/* replaces TrajectoryEstimator::SaveMarginalizationInfo (:184-204) =
+ * MarginalizationInfo::preMarginalize + marginalize over every factor added with marg != 0 and
+ * the current prior (PrepareMarginalizationInfo, :143-182).  Returns CTVIO_OK and n_out == 0
+ * when nothing can be kept (the reference hands back nullptr). */
+int ctvio_marginalize(ctvio_handle h, int32_t* n_out, int32_t* n_blocks_out);
+int ctvio_get_prior(ctvio_handle h, double* J_lin_rowmajor, double* r_lin, int32_t* blk_type,
+                    int32_t* blk_index, int32_t* blk_col, double* blk_x0_4);
+/* make the prior produced by ctvio_marginalize the active one (device-to-device, no host trip) */
+int ctvio_adopt_prior(ctvio_handle h);
+
+/* state snapshot in HBM (bench: re-run the same window without a host round trip) */
+int ctvio_save_state(ctvio_handle h);
+int ctvio_restore_state(ctvio_handle h);
+
+/* ---- probes used by the parity tests (the reference's CostFunction::Evaluate seam) ---- */
+/* Evaluate every image factor at the current state.
+ *   replaces ImageFeatureDelayFactor::Evaluate (factor/analytic_diff/image_feature_factor.h:63-269)
+ *   + the loss corrector.  Outputs (any may be NULL): r[2n], s[2n] global start knots (i-side, j-side),
+ *   J[n][100]: [side][knot k][rot 2x3 row-major | pos 2x3 row-major] (96) + d/d rho (2) + d/d ld (2). */
+int ctvio_eval_image_factors(ctvio_handle h, int32_t want_jacobians, double cauchy_scale, double* r,
+                             int32_t* s, double* J, double* cost);
+/* replaces IMUFactor::Evaluate (factor/analytic_diff/trajectory_value_factor.h:141-248).
+ *   r[6n], s[n], J[n][156]: [knot k][rot 6x3 | pos 6x3] (144) + diag d/d bg (6) + diag d/d ba (6). */
+int ctvio_eval_imu_factors(ctvio_handle h, int32_t want_jacobians, double* r, int32_t* s, double* J,
+                           double* cost);
+/* total cost 0.5*sum rho(|r|^2) of all factors incl. bias + prior at the current state */
+int ctvio_eval_cost(ctvio_handle h, double* cost);
+/* Schur-form normal equations at the current state: camera block H_cc (np x np, row-major, symmetric),
+ * g_c (np), per-landmark h_l, g_l (n_landmarks each).  np = 6*n_knots + 6*n_bias + 1. */
+int ctvio_normal_equations(ctvio_handle h, double* Hcc, double* gc, double* hl, double* gl, double* cost);
+
+/* ---- spline query service (Trajectory::poseNs / GetIMUState, spline/trajectory.cpp:27-55) ----
+ * batch R(t), p(t), body angular velocity, world linear velocity and acceleration. Any output may be NULL. */
+int ctvio_query_trajectory(ctvio_handle h, int32_t n, const int64_t* t, double* q_xyzw, double* p_xyz,
+                           double* omega_body, double* vel_world, double* acc_world);
+
+/* ---- multi-GPU: landmark-sharded residuals, one allreduce of the reduced system per LM step ----
+ * Every rank holds the full (replicated) state and its own shard of image factors; rank 0 also holds
+ * IMU / bias / prior factors. unique_id is the 128-byte ncclUniqueId from ctvio_nccl_unique_id on rank 0. */
+int ctvio_nccl_unique_id(uint8_t* id128);
+int ctvio_comm_init(ctvio_handle h, int32_t rank, int32_t world_size, const uint8_t* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTVIO_H_ */
