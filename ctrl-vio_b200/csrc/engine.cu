@@ -1,0 +1,1134 @@
+// Host side of the CUDA engine: C-ABI of include/ctvio.h, problem preprocessing (frame-pair groups,
+// landmark ranges, Schur batches), device-resident window state and the LM trust-region driver.
+//
+// The driver restates Ceres 1.14's TrustRegionMinimizer / LevenbergMarquardtStrategy semantics that
+// the reference gets from ceres::Solve (trajectory_estimator.cpp:367-408):
+// Jacobi scaling fixed at iteration 0, D^2 = clamp(diag)/mu, rho = dcost/dmodel accepted above 1e-3,
+// mu <- mu / max(1/3, 1-(2rho-1)^3) on success, mu <- mu/f, f <- 2f on failure, function / parameter
+// tolerances, Armijo projected line search when the line delay has bounds.
+// B200-first differences from a port: every candidate point is evaluated with full Jacobians into a
+// second normal-equation buffer (an accepted step costs no re-linearisation pass), all per-step
+// quantities are reduced on the device, and the host reads back ONE 96-byte scalar block per step.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ctvio.h"
+#include "kernels.h"
+#include "marginalize.h"
+#include "poly_min.h"
+
+using namespace ctvio;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_OK(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(CTVIO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& h, cudaStream_t s) {
+    cudaError_t e = reserve(h.size());
+    if (e != cudaSuccess || h.empty()) return e;
+    return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+struct DevState {
+  DevBuf<double> q, p, bias, rho, ld;
+  DevBuf<KnotPair> tab;
+  StatePtrs ptrs() { return StatePtrs{q.p, p.p, bias.p, rho.p, ld.p, tab.p}; }
+};
+
+struct HostImage { int64_t ti, tj; int32_t rowi, rowj; double pi[2], pj[2]; int32_t lm, marg; };
+struct HostImu { int64_t t; double gyro[3], accel[3]; int32_t node, marg; };
+struct HostBias { int32_t i, j; double s[6]; int32_t marg; };
+
+}  // namespace
+
+struct ctvio_engine {
+  ctvio_config cfg;
+  ctvio_options opt;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  SplineParams sp;
+  RigParams rig;
+  bool use_tma = true;
+
+  // sizes
+  int nK = 0, nB = 0, nL = 0;
+  bool have_knots = false, have_bias = false, have_rho = false;
+
+  // state: two buffers (current / candidate) + snapshot
+  DevState x[2], snap;
+  int cur = 0;
+  bool table_valid = false;
+
+  // factors (host copies in caller order)
+  std::vector<HostImage> img;
+  std::vector<HostImu> imu;
+  std::vector<HostBias> biasf;
+  bool structure_dirty = true;
+
+  // device factor arrays
+  DevBuf<longlong2> d_img_t;
+  DevBuf<double2> d_img_pi, d_img_pj;
+  DevBuf<int4> d_img_meta;
+  DevBuf<int32_t> d_img_orig;
+  DevBuf<VisualItem> d_items;
+  int n_items = 0;
+  std::vector<int32_t> img_order;  // sorted position -> original index
+  DevBuf<longlong2> d_imu_t;
+  DevBuf<double2> d_imu_ga;
+  DevBuf<int2> d_bf_ij;
+  DevBuf<double> d_bf_s;
+
+  // landmark layout / schur batches
+  std::vector<int32_t> h_lo, h_hi;
+  std::vector<int64_t> h_woff;
+  DevBuf<int32_t> d_lo, d_hi, d_schur_order, d_wide;
+  DevBuf<int64_t> d_woff;
+  DevBuf<SchurBatch> d_batches;
+  int n_batches = 0, n_wide = 0;
+  DevBuf<uint8_t> d_cmask, d_active;
+  std::vector<uint8_t> h_cmask, h_active;
+
+  // normal equations (two buffers, each one slab: A | gc | hl | gl | wld | W)
+  DevBuf<double> ne_slab[2];
+  size_t ne_slab_len = 0;
+  size_t off_gc = 0, off_hl = 0, off_gl = 0, off_wld = 0, off_W = 0;
+  // linear system
+  DevBuf<double> d_M, d_Linv, d_rhs, d_y, d_sc, d_sl, d_hh, d_dc, d_dl;
+  int npad = 0;
+  DevBuf<LmScalars> d_scal;
+  LmScalars* h_scal = nullptr;  // pinned
+
+  // prior
+  ctvio::PriorHost prior, new_prior;
+  DevBuf<double> d_prior_J, d_prior_r, d_prior_JtJ, d_prior_x0, d_prior_dx, d_prior_res;
+  DevBuf<int32_t> d_prior_type, d_prior_index, d_prior_col, d_prior_col2g;
+  bool prior_dirty = true;
+
+  DevBuf<double> d_tmp;  // scratch (gauge inputs, probe outputs)
+
+  // multi-GPU
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+
+  int64_t launches = 0;
+
+  ProblemDims dims() const {
+    ProblemDims d;
+    d.nK = nK; d.nB = nB; d.nL = nL;
+    d.idx_bias0 = 6 * nK;
+    d.idx_ld = 6 * nK + 6 * nB;
+    d.np = d.idx_ld + 1;
+    return d;
+  }
+  NormalEqPtrs ne(int b) {
+    double* s = ne_slab[b].p;
+    return NormalEqPtrs{s, s + off_gc, s + off_hl, s + off_gl, s + off_wld, s + off_W, &d_scal.p->cost_eval};
+  }
+  LandmarkLayout lml() { return LandmarkLayout{d_lo.p, d_hi.p, d_woff.p}; }
+};
+
+namespace {
+
+int knot_window_first(const ctvio_engine* e, int64_t t) {
+  int64_t s = (t - e->cfg.t0_ns) / e->cfg.dt_ns;
+  return int(s);
+}
+
+// padded window [first, last] of an evaluation time (se3_spline.h:463-503), clamped to the spline
+bool knot_window(const ctvio_engine* e, int64_t t, int& first, int& last) {
+  const int64_t maxt = e->cfg.t0_ns + int64_t(e->nK - 3) * e->cfg.dt_ns;
+  if (t < e->cfg.t0_ns || t >= maxt) return false;
+  const int smax = e->nK - 4;
+  const int s1 = knot_window_first(e, t);
+  int64_t t2 = t + e->cfg.rs_padding_ns;
+  int s2 = (t2 >= maxt) ? smax : int((t2 - e->cfg.t0_ns) / e->cfg.dt_ns);
+  if (s2 > s1 + 1) return false;  // padding wider than one knot interval is not supported by the 5-knot window
+  first = s1;
+  last = std::min(s2 + 3, e->nK - 1);
+  return true;
+}
+
+int prepare_prior(ctvio_engine* e);
+
+// Build every host-side structure that depends on the factor set / sizes and upload it.
+int prepare(ctvio_engine* e) {
+  if (!e->have_knots) return fail(CTVIO_ERR_STATE, "knots have not been set");
+  if (e->nK < 4) return fail(CTVIO_ERR_STATE, "need at least 4 knots");
+  if (!e->have_bias) { e->nB = 0; }
+  cudaStream_t st = e->stream;
+  const ProblemDims d = e->dims();
+  if (e->structure_dirty) {
+    // ---- image factors: frame-pair groups ----
+    const int n = int(e->img.size());
+    std::vector<int32_t> wi0(n), wj0(n);
+    e->h_lo.assign(e->nL, INT32_MAX);
+    e->h_hi.assign(e->nL, 0);
+    for (int k = 0; k < n; ++k) {
+      const HostImage& o = e->img[k];
+      int f0, l0, f1, l1;
+      if (!knot_window(e, o.ti, f0, l0) || !knot_window(e, o.tj, f1, l1))
+        return fail(CTVIO_ERR_TIME_RANGE, "image factor time (+ rolling-shutter padding) outside the spline");
+      if (o.lm < 0 || o.lm >= e->nL) return fail(CTVIO_ERR_INVALID, "landmark index out of range");
+      wi0[k] = f0; wj0[k] = f1;
+      e->h_lo[o.lm] = std::min(e->h_lo[o.lm], 6 * std::min(f0, f1));
+      e->h_hi[o.lm] = std::max(e->h_hi[o.lm], 6 * (std::max(l0, l1) + 1));
+    }
+    e->img_order.resize(n);
+    for (int k = 0; k < n; ++k) e->img_order[k] = k;
+    std::stable_sort(e->img_order.begin(), e->img_order.end(), [&](int a, int b) {
+      if (wi0[a] != wi0[b]) return wi0[a] < wi0[b];
+      if (wj0[a] != wj0[b]) return wj0[a] < wj0[b];
+      return e->img[a].lm < e->img[b].lm;
+    });
+    std::vector<longlong2> ht(n);
+    std::vector<double2> hpi(n), hpj(n);
+    std::vector<int4> hm(n);
+    for (int k = 0; k < n; ++k) {
+      const HostImage& o = e->img[e->img_order[k]];
+      ht[k] = make_longlong2(o.ti, o.tj);
+      hpi[k] = make_double2(o.pi[0], o.pi[1]);
+      hpj[k] = make_double2(o.pj[0], o.pj[1]);
+      hm[k] = make_int4(o.rowi, o.rowj, o.lm, o.marg);
+    }
+    // work items: chunks of one group; chunk size adapts so that small problems still spread over the SMs
+    int chunk = 512;
+    if (n < 148 * 512) chunk = std::max(kVisObsPerRound, ((n / 148 + kVisObsPerRound - 1) / kVisObsPerRound) * kVisObsPerRound);
+    std::vector<VisualItem> items;
+    for (int k = 0; k < n;) {
+      const int a = e->img_order[k];
+      int end = k;
+      while (end < n && wi0[e->img_order[end]] == wi0[a] && wj0[e->img_order[end]] == wj0[a]) ++end;
+      for (int s = k; s < end; s += chunk) items.push_back(VisualItem{s, std::min(chunk, end - s), wi0[a], wj0[a]});
+      k = end;
+    }
+    e->n_items = int(items.size());
+    CUDA_OK(e->d_img_t.upload(ht, st));
+    CUDA_OK(e->d_img_pi.upload(hpi, st));
+    CUDA_OK(e->d_img_pj.upload(hpj, st));
+    CUDA_OK(e->d_img_meta.upload(hm, st));
+    CUDA_OK(e->d_img_orig.upload(e->img_order, st));
+    CUDA_OK(e->d_items.upload(items, st));
+
+    // ---- landmark layout ----
+    e->h_woff.assign(e->nL + 1, 0);
+    for (int l = 0; l < e->nL; ++l) {
+      if (e->h_hi[l] == 0) e->h_lo[l] = 0;
+      e->h_woff[l + 1] = e->h_woff[l] + (e->h_hi[l] - e->h_lo[l]);
+    }
+    CUDA_OK(e->d_lo.upload(e->h_lo, st));
+    CUDA_OK(e->d_hi.upload(e->h_hi, st));
+    CUDA_OK(e->d_woff.upload(e->h_woff, st));
+    // ---- schur batches: landmarks sorted by range, greedy batches with union range <= kSchurMaxDim ----
+    std::vector<int32_t> order, wide;
+    for (int l = 0; l < e->nL; ++l) {
+      if (e->h_hi[l] == 0) continue;  // unobserved landmark: h_l = 0, step 0
+      if (e->h_hi[l] - e->h_lo[l] > kSchurMaxDim) wide.push_back(l);
+      else order.push_back(l);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (e->h_lo[a] != e->h_lo[b]) return e->h_lo[a] < e->h_lo[b];
+      return e->h_hi[a] < e->h_hi[b];
+    });
+    // batch size adapts to the landmark count so that C2-sized windows still use many SMs
+    const int bcap = std::max(8, std::min(kSchurBatch, int(order.size() + 147) / 148));
+    std::vector<SchurBatch> batches;
+    for (size_t k = 0; k < order.size();) {
+      SchurBatch b{int32_t(k), 0, e->h_lo[order[k]], e->h_hi[order[k]]};
+      while (k < order.size() && b.count < bcap) {
+        const int l = order[k];
+        const int ulo = std::min(b.ulo, e->h_lo[l]), uhi = std::max(b.uhi, e->h_hi[l]);
+        if (uhi - ulo > kSchurMaxDim) break;
+        b.ulo = ulo; b.uhi = uhi;
+        ++b.count; ++k;
+      }
+      batches.push_back(b);
+    }
+    e->n_batches = int(batches.size());
+    e->n_wide = int(wide.size());
+    CUDA_OK(e->d_schur_order.upload(order, st));
+    CUDA_OK(e->d_batches.upload(batches, st));
+    CUDA_OK(e->d_wide.upload(wide, st));
+
+    // ---- imu / bias factors ----
+    const int ni = int(e->imu.size());
+    std::vector<longlong2> it(ni);
+    std::vector<double2> iga(3 * size_t(ni));
+    const int64_t maxt = e->cfg.t0_ns + int64_t(e->nK - 3) * e->cfg.dt_ns;
+    for (int k = 0; k < ni; ++k) {
+      const HostImu& o = e->imu[k];
+      if (o.t < e->cfg.t0_ns || o.t >= maxt) return fail(CTVIO_ERR_TIME_RANGE, "imu time outside the spline");
+      if (o.node < 0 || o.node >= e->nB) return fail(CTVIO_ERR_INVALID, "bias node out of range");
+      it[k] = make_longlong2(o.t, o.node);
+      iga[3 * k] = make_double2(o.gyro[0], o.gyro[1]);
+      iga[3 * k + 1] = make_double2(o.gyro[2], o.accel[0]);
+      iga[3 * k + 2] = make_double2(o.accel[1], o.accel[2]);
+    }
+    CUDA_OK(e->d_imu_t.upload(it, st));
+    CUDA_OK(e->d_imu_ga.upload(iga, st));
+    const int nb = int(e->biasf.size());
+    std::vector<int2> bij(nb);
+    std::vector<double> bs(6 * size_t(nb));
+    for (int k = 0; k < nb; ++k) {
+      const HostBias& o = e->biasf[k];
+      if (o.i < 0 || o.i >= e->nB || o.j < 0 || o.j >= e->nB) return fail(CTVIO_ERR_INVALID, "bias node out of range");
+      bij[k] = make_int2(o.i, o.j);
+      for (int c = 0; c < 6; ++c) bs[6 * k + c] = o.s[c];
+    }
+    CUDA_OK(e->d_bf_ij.upload(bij, st));
+    CUDA_OK(e->d_bf_s.upload(bs, st));
+
+    // ---- buffers ----
+    const size_t np = size_t(d.np);
+    e->off_gc = np * np;
+    e->off_hl = e->off_gc + np;
+    e->off_gl = e->off_hl + e->nL;
+    e->off_wld = e->off_gl + e->nL;
+    e->off_W = e->off_wld + e->nL;
+    e->ne_slab_len = e->off_W + size_t(e->h_woff[e->nL]);
+    for (int b = 0; b < 2; ++b) CUDA_OK(e->ne_slab[b].reserve(e->ne_slab_len));
+    e->npad = ((d.np + kCholNB - 1) / kCholNB) * kCholNB;
+    CUDA_OK(e->d_M.reserve(size_t(e->npad) * e->npad));
+    CUDA_OK(e->d_Linv.reserve(size_t(e->npad) * kCholNB));
+    CUDA_OK(e->d_rhs.reserve(e->npad));
+    CUDA_OK(e->d_y.reserve(e->npad));
+    CUDA_OK(e->d_sc.reserve(np));
+    CUDA_OK(e->d_sl.reserve(e->nL));
+    CUDA_OK(e->d_hh.reserve(e->nL));
+    CUDA_OK(e->d_dc.reserve(np));
+    CUDA_OK(e->d_dl.reserve(e->nL));
+    if (e->nL > 0) CUDA_OK(cudaMemsetAsync(e->d_hh.p, 0, sizeof(double) * e->nL, st));
+    e->prior_dirty = true;
+  }
+  // ---- masks (depend on options + structure) ----
+  {
+    e->h_cmask.assign(d.np, 0);
+    for (int k = 0; k < e->nK; ++k)
+      if (e->opt.lock_traj || (e->opt.fixed_knot_index >= 0 && k <= e->opt.fixed_knot_index))
+        for (int c = 0; c < 6; ++c) e->h_cmask[6 * k + c] = 1;  // trajectory_estimator.cpp:134-138
+    for (int b = 0; b < e->nB; ++b)
+      for (int c = 0; c < 3; ++c) {
+        if (e->opt.lock_wb) e->h_cmask[d.idx_bias0 + 6 * b + c] = 1;
+        if (e->opt.lock_ab) e->h_cmask[d.idx_bias0 + 6 * b + 3 + c] = 1;
+      }
+    if (e->opt.fix_ld) e->h_cmask[d.idx_ld] = 1;
+    std::vector<uint8_t> touched(d.np + e->nL, 0);
+    auto mark = [&](int f, int l) {
+      for (int k = f; k <= l; ++k)
+        for (int c = 0; c < 6; ++c) touched[6 * k + c] = 1;
+    };
+    for (const HostImage& o : e->img) {
+      int f, l;
+      knot_window(e, o.ti, f, l); mark(f, l);
+      knot_window(e, o.tj, f, l); mark(f, l);
+      touched[d.idx_ld] = 1;
+      touched[d.np + o.lm] = 1;
+    }
+    for (const HostImu& o : e->imu) {
+      const int s = knot_window_first(e, o.t);
+      mark(s, s + 3);
+      for (int c = 0; c < 6; ++c) touched[d.idx_bias0 + 6 * o.node + c] = 1;
+    }
+    for (const HostBias& o : e->biasf)
+      for (int c = 0; c < 6; ++c) touched[d.idx_bias0 + 6 * o.i + c] = touched[d.idx_bias0 + 6 * o.j + c] = 1;
+    if (e->prior.n > 0)
+      for (size_t b = 0; b < e->prior.type.size(); ++b) {
+        const int g = ctvio::prior_block_base(e->prior.type[b], e->prior.index[b], d.nK, d.nB);
+        const int ls = (e->prior.type[b] == CTVIO_BLK_LD || e->prior.type[b] == CTVIO_BLK_RHO) ? 1 : 3;
+        if (g >= 0) for (int c = 0; c < ls; ++c) touched[g + c] = 1;
+      }
+    e->h_active.assign(d.np + e->nL, 0);
+    for (int i = 0; i < d.np; ++i) e->h_active[i] = touched[i] && !e->h_cmask[i];
+    for (int l = 0; l < e->nL; ++l) e->h_active[d.np + l] = touched[d.np + l];
+    CUDA_OK(e->d_cmask.upload(e->h_cmask, st));
+    CUDA_OK(e->d_active.upload(e->h_active, st));
+  }
+  e->structure_dirty = false;
+  if (e->prior_dirty) {
+    const int rc = prepare_prior(e);
+    if (rc != CTVIO_OK) return rc;
+  }
+  return CTVIO_OK;
+}
+
+int prepare_prior(ctvio_engine* e) {
+  const ProblemDims d = e->dims();
+  const ctvio::PriorHost& pr = e->prior;
+  e->prior_dirty = false;
+  if (pr.n <= 0) return CTVIO_OK;
+  cudaStream_t st = e->stream;
+  std::vector<int32_t> col2g(pr.n, -1);
+  for (size_t b = 0; b < pr.type.size(); ++b) {
+    const int g = ctvio::prior_block_base(pr.type[b], pr.index[b], d.nK, d.nB);
+    if (pr.type[b] == CTVIO_BLK_RHO) return fail(CTVIO_ERR_INVALID, "inverse-depth blocks cannot be part of a prior");
+    if (g < 0) return fail(CTVIO_ERR_INVALID, "prior block index out of range");
+    const int ls = pr.type[b] == CTVIO_BLK_LD ? 1 : 3;
+    for (int c = 0; c < ls; ++c)
+      if (!e->h_cmask[g + c]) col2g[pr.col[b] + c] = g + c;
+  }
+  CUDA_OK(e->d_prior_J.upload(pr.J, st));
+  CUDA_OK(e->d_prior_r.upload(pr.r, st));
+  CUDA_OK(e->d_prior_x0.upload(pr.x0, st));
+  CUDA_OK(e->d_prior_type.upload(pr.type, st));
+  CUDA_OK(e->d_prior_index.upload(pr.index, st));
+  CUDA_OK(e->d_prior_col.upload(pr.col, st));
+  CUDA_OK(e->d_prior_col2g.upload(col2g, st));
+  CUDA_OK(e->d_prior_JtJ.reserve(size_t(pr.n) * pr.n));
+  CUDA_OK(e->d_prior_dx.reserve(pr.n));
+  CUDA_OK(e->d_prior_res.reserve(pr.n));
+  e->launches += ctvio::launch_gram(e->d_prior_J.p, pr.n, pr.n, e->d_prior_JtJ.p, st);
+  return CTVIO_OK;
+}
+
+PriorPtrs prior_ptrs(ctvio_engine* e) {
+  PriorPtrs p;
+  std::memset(&p, 0, sizeof(p));
+  p.n = e->prior.n;
+  if (p.n <= 0) return p;
+  p.n_blocks = int(e->prior.type.size());
+  p.J = e->d_prior_J.p; p.r = e->d_prior_r.p; p.JtJ = e->d_prior_JtJ.p;
+  p.type = e->d_prior_type.p; p.index = e->d_prior_index.p; p.col = e->d_prior_col.p;
+  p.x0 = e->d_prior_x0.p; p.col2g = e->d_prior_col2g.p;
+  p.dx = e->d_prior_dx.p; p.res = e->d_prior_res.p;
+  return p;
+}
+
+VisualLaunch visual_launch(ctvio_engine* e, int xb, int nb, double cauchy) {
+  VisualLaunch v;
+  v.obs = ImageObsPtrs{e->d_img_t.p, e->d_img_pi.p, e->d_img_pj.p, e->d_img_meta.p, int32_t(e->img.size())};
+  v.items = e->d_items.p;
+  v.n_items = e->n_items;
+  v.st = e->x[xb].ptrs();
+  v.ne = e->ne(nb);
+  v.lm = e->lml();
+  v.dims = e->dims();
+  v.sp = e->sp;
+  v.rig = e->rig;
+  v.cauchy = cauchy;
+  v.cmask = e->d_cmask.p;
+  v.scal = e->d_scal.p;
+  v.use_tma = e->use_tma;
+  return v;
+}
+ImuLaunch imu_launch(ctvio_engine* e, int xb, int nb) {
+  ImuLaunch v;
+  v.obs = ImuObsPtrs{e->d_imu_t.p, e->d_imu_ga.p, int32_t(e->imu.size())};
+  v.st = e->x[xb].ptrs();
+  v.ne = e->ne(nb);
+  v.dims = e->dims();
+  v.sp = e->sp;
+  v.rig = e->rig;
+  v.cmask = e->d_cmask.p;
+  v.scal = e->d_scal.p;
+  return v;
+}
+SmallFactorsLaunch small_launch(ctvio_engine* e, int xb, int nb) {
+  SmallFactorsLaunch v;
+  v.bf = BiasFactorPtrs{e->d_bf_ij.p, e->d_bf_s.p, int32_t(e->biasf.size())};
+  v.prior = prior_ptrs(e);
+  v.st = e->x[xb].ptrs();
+  v.ne = e->ne(nb);
+  v.dims = e->dims();
+  v.cmask = e->d_cmask.p;
+  v.scal = e->d_scal.p;
+  return v;
+}
+LinearLaunch linear_launch(ctvio_engine* e, int nb) {
+  LinearLaunch a;
+  a.dims = e->dims();
+  a.ne = e->ne(nb);
+  a.lm = e->lml();
+  a.schur_order = e->d_schur_order.p;
+  a.batches = e->d_batches.p;
+  a.n_batches = e->n_batches;
+  a.wide_lms = e->d_wide.p;
+  a.n_wide = e->n_wide;
+  a.cmask = e->d_cmask.p;
+  a.active = e->d_active.p;
+  a.sc = e->d_sc.p; a.sl = e->d_sl.p;
+  a.M = e->d_M.p; a.Linv = e->d_Linv.p; a.rhs = e->d_rhs.p; a.y = e->d_y.p;
+  a.hh = e->d_hh.p; a.dc = e->d_dc.p; a.dl = e->d_dl.p;
+  a.npad = e->npad;
+  a.scal = e->d_scal.p;
+  return a;
+}
+
+// one pass over all residual blocks at state buffer xb into normal-equation buffer nb
+void evaluate(ctvio_engine* e, int xb, int nb, bool full) {
+  cudaStream_t st = e->stream;
+  if (full) cudaMemsetAsync(e->ne_slab[nb].p, 0, e->ne_slab_len * sizeof(double), st);
+  cudaMemsetAsync(&e->d_scal.p->cost_eval, 0, sizeof(double), st);
+  e->launches += launch_visual(visual_launch(e, xb, nb, e->cfg.cauchy_solve), full, st);
+  e->launches += launch_imu(imu_launch(e, xb, nb), full, st);
+  e->launches += launch_small_factors(small_launch(e, xb, nb), full, st);
+}
+
+int read_scalars(ctvio_engine* e) {
+  CUDA_OK(cudaMemcpyAsync(e->h_scal, e->d_scal.p, sizeof(LmScalars), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  if (e->h_scal->error_flags & 1) {
+    cudaMemsetAsync(&e->d_scal.p->error_flags, 0, sizeof(int32_t), e->stream);
+    return fail(CTVIO_ERR_TIME_RANGE, "a factor time left its knot window / the spline (line delay too large?)");
+  }
+  return CTVIO_OK;
+}
+
+int ensure_table(ctvio_engine* e) {
+  if (!e->table_valid) {
+    e->launches += launch_knot_table(e->x[e->cur].ptrs(), e->nK, e->stream);
+    e->table_valid = true;
+  }
+  return CTVIO_OK;
+}
+
+int alloc_state(ctvio_engine* e, DevState& s) {
+  CUDA_OK(s.q.reserve(4 * size_t(e->nK)));
+  CUDA_OK(s.p.reserve(kPStride * size_t(e->nK)));
+  CUDA_OK(s.tab.reserve(size_t(std::max(e->nK - 1, 1))));
+  CUDA_OK(s.bias.reserve(6 * size_t(std::max(e->nB, 1))));
+  CUDA_OK(s.rho.reserve(size_t(std::max(e->nL, 1))));
+  CUDA_OK(s.ld.reserve(1));
+  return CTVIO_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* ctvio_last_error(void) { return g_err.c_str(); }
+int ctvio_abi_version(void) { return CTVIO_ABI_VERSION; }
+
+int ctvio_create(const ctvio_config* cfg, ctvio_handle* out) {
+  if (!cfg || !out) return fail(CTVIO_ERR_INVALID, "null argument");
+  if (cfg->dt_ns <= 0) return fail(CTVIO_ERR_INVALID, "dt_ns must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(CTVIO_ERR_NO_DEVICE, "no CUDA device visible: the ctvio engine has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(CTVIO_ERR_NO_DEVICE, "device ordinal out of range");
+  CUDA_OK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10) return fail(CTVIO_ERR_NO_DEVICE, "libctvio_b200 is built for sm_100a (B200) only");
+  ctvio_engine* e = new ctvio_engine();
+  e->cfg = *cfg;
+  std::memset(&e->opt, 0, sizeof(e->opt));
+  e->opt.fixed_knot_index = -1;
+  e->opt.fix_ld = 1;
+  e->sp = SplineParams{cfg->t0_ns, cfg->dt_ns, 0, 1e9 / double(cfg->dt_ns)};
+  e->rig.R_CI = so3_matrix(Q4{cfg->q_CtoI[0], cfg->q_CtoI[1], cfg->q_CtoI[2], cfg->q_CtoI[3]});
+  e->rig.p_CI = V3{cfg->p_CinI[0], cfg->p_CinI[1], cfg->p_CinI[2]};
+  e->rig.w_img = cfg->image_weight;
+  e->rig.gravity = V3{cfg->gravity[0], cfg->gravity[1], cfg->gravity[2]};
+  for (int k = 0; k < 6; ++k) e->rig.imu_info[k] = cfg->imu_info[k];
+  const char* no_tma = std::getenv("CTVIO_NO_TMA");
+  e->use_tma = !(no_tma && no_tma[0] == '1');
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+      cudaMallocHost(&e->h_scal, sizeof(LmScalars)) != cudaSuccess || e->d_scal.reserve(1) != cudaSuccess) {
+    delete e;
+    return fail(CTVIO_ERR_CUDA, "could not create stream / events / scalar block");
+  }
+  cudaMemsetAsync(e->d_scal.p, 0, sizeof(LmScalars), e->stream);
+  *out = e;
+  return CTVIO_OK;
+}
+
+int ctvio_destroy(ctvio_handle e) {
+  if (!e) return CTVIO_OK;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  ctvio::comm_destroy(e->nccl_comm);
+  if (e->h_scal) cudaFreeHost(e->h_scal);
+  cudaEventDestroy(e->ev0);
+  cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return CTVIO_OK;
+}
+
+int ctvio_set_options(ctvio_handle e, const ctvio_options* o) {
+  if (!e || !o) return fail(CTVIO_ERR_INVALID, "null argument");
+  e->opt = *o;
+  e->prior_dirty = true;  // col2g depends on the constant mask
+  return CTVIO_OK;
+}
+
+int ctvio_set_knots(ctvio_handle e, int32_t n, const double* q, const double* p) {
+  if (!e || !q || !p || n < 4) return fail(CTVIO_ERR_INVALID, "need >= 4 knots");
+  cudaSetDevice(e->cfg.device);
+  if (n != e->nK) e->structure_dirty = true;
+  e->nK = n;
+  e->sp.n_knots = n;
+  for (int b = 0; b < 2; ++b) { const int rc = alloc_state(e, e->x[b]); if (rc) return rc; }
+  std::vector<double> p4(kPStride * size_t(n), 0.0);
+  for (int k = 0; k < n; ++k) for (int c = 0; c < 3; ++c) p4[kPStride * k + c] = p[3 * k + c];
+  CUDA_OK(cudaMemcpyAsync(e->x[e->cur].q.p, q, 4 * size_t(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_OK(cudaMemcpyAsync(e->x[e->cur].p.p, p4.data(), p4.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));  // p4 is a stack-lifetime staging buffer
+  e->have_knots = true;
+  e->table_valid = false;
+  return CTVIO_OK;
+}
+
+int ctvio_set_biases(ctvio_handle e, int32_t n, const double* b) {
+  if (!e || (n > 0 && !b) || n < 0) return fail(CTVIO_ERR_INVALID, "bad bias array");
+  cudaSetDevice(e->cfg.device);
+  if (n != e->nB) e->structure_dirty = true;
+  e->nB = n;
+  for (int k = 0; k < 2; ++k) CUDA_OK(e->x[k].bias.reserve(6 * size_t(std::max(n, 1))));
+  if (n > 0) CUDA_OK(cudaMemcpyAsync(e->x[e->cur].bias.p, b, 6 * size_t(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->have_bias = true;
+  return CTVIO_OK;
+}
+
+int ctvio_set_inv_depths(ctvio_handle e, int32_t n, const double* r) {
+  if (!e || (n > 0 && !r) || n < 0) return fail(CTVIO_ERR_INVALID, "bad inverse-depth array");
+  cudaSetDevice(e->cfg.device);
+  if (n != e->nL) e->structure_dirty = true;
+  e->nL = n;
+  for (int k = 0; k < 2; ++k) CUDA_OK(e->x[k].rho.reserve(size_t(std::max(n, 1))));
+  if (n > 0) CUDA_OK(cudaMemcpyAsync(e->x[e->cur].rho.p, r, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->have_rho = true;
+  return CTVIO_OK;
+}
+
+int ctvio_set_line_delay(ctvio_handle e, double ld) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  cudaSetDevice(e->cfg.device);
+  for (int k = 0; k < 2; ++k) CUDA_OK(e->x[k].ld.reserve(1));
+  CUDA_OK(cudaMemcpyAsync(e->x[e->cur].ld.p, &ld, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  return CTVIO_OK;
+}
+
+int ctvio_get_knots(ctvio_handle e, double* q, double* p) {
+  if (!e || !e->have_knots) return fail(CTVIO_ERR_STATE, "knots have not been set");
+  cudaSetDevice(e->cfg.device);
+  if (q) CUDA_OK(cudaMemcpyAsync(q, e->x[e->cur].q.p, 4 * size_t(e->nK) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  std::vector<double> p4;
+  if (p) {
+    p4.resize(kPStride * size_t(e->nK));
+    CUDA_OK(cudaMemcpyAsync(p4.data(), e->x[e->cur].p.p, p4.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  if (p) for (int k = 0; k < e->nK; ++k) for (int c = 0; c < 3; ++c) p[3 * k + c] = p4[kPStride * k + c];
+  return CTVIO_OK;
+}
+int ctvio_get_biases(ctvio_handle e, double* b) {
+  if (!e || !b) return fail(CTVIO_ERR_INVALID, "null argument");
+  cudaSetDevice(e->cfg.device);
+  if (e->nB > 0) CUDA_OK(cudaMemcpyAsync(b, e->x[e->cur].bias.p, 6 * size_t(e->nB) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  return CTVIO_OK;
+}
+int ctvio_get_inv_depths(ctvio_handle e, double* r) {
+  if (!e || !r) return fail(CTVIO_ERR_INVALID, "null argument");
+  cudaSetDevice(e->cfg.device);
+  if (e->nL > 0) CUDA_OK(cudaMemcpyAsync(r, e->x[e->cur].rho.p, size_t(e->nL) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  return CTVIO_OK;
+}
+int ctvio_get_line_delay(ctvio_handle e, double* ld) {
+  if (!e || !ld) return fail(CTVIO_ERR_INVALID, "null argument");
+  cudaSetDevice(e->cfg.device);
+  CUDA_OK(cudaMemcpyAsync(ld, e->x[e->cur].ld.p, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  return CTVIO_OK;
+}
+
+int ctvio_clear_factors(ctvio_handle e) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  e->img.clear(); e->imu.clear(); e->biasf.clear();
+  e->structure_dirty = true;
+  return CTVIO_OK;
+}
+
+int ctvio_add_image_features(ctvio_handle e, int32_t n, const int64_t* ti, const int32_t* rowi, const double* pi,
+                             const int64_t* tj, const int32_t* rowj, const double* pj, const int32_t* lm,
+                             const int32_t* marg) {
+  if (!e || n < 0 || (n > 0 && (!ti || !rowi || !pi || !tj || !rowj || !pj || !lm)))
+    return fail(CTVIO_ERR_INVALID, "null argument");
+  e->img.reserve(e->img.size() + n);
+  for (int k = 0; k < n; ++k) {
+    HostImage o{ti[k], tj[k], rowi[k], rowj[k], {pi[2 * k], pi[2 * k + 1]}, {pj[2 * k], pj[2 * k + 1]}, lm[k],
+                marg ? marg[k] : 0};
+    e->img.push_back(o);
+  }
+  e->structure_dirty = true;
+  return CTVIO_OK;
+}
+int ctvio_add_imu_measurements(ctvio_handle e, int32_t n, const int64_t* t, const double* gyro, const double* accel,
+                               const int32_t* node, const int32_t* marg) {
+  if (!e || n < 0 || (n > 0 && (!t || !gyro || !accel || !node))) return fail(CTVIO_ERR_INVALID, "null argument");
+  for (int k = 0; k < n; ++k) {
+    HostImu o{t[k], {gyro[3 * k], gyro[3 * k + 1], gyro[3 * k + 2]}, {accel[3 * k], accel[3 * k + 1], accel[3 * k + 2]},
+              node[k], marg ? marg[k] : 0};
+    e->imu.push_back(o);
+  }
+  e->structure_dirty = true;
+  return CTVIO_OK;
+}
+int ctvio_add_bias_factors(ctvio_handle e, int32_t n, const int32_t* ni, const int32_t* nj, const double* s,
+                           const int32_t* marg) {
+  if (!e || n < 0 || (n > 0 && (!ni || !nj || !s))) return fail(CTVIO_ERR_INVALID, "null argument");
+  for (int k = 0; k < n; ++k) {
+    HostBias o{ni[k], nj[k], {s[6 * k], s[6 * k + 1], s[6 * k + 2], s[6 * k + 3], s[6 * k + 4], s[6 * k + 5]},
+               marg ? marg[k] : 0};
+    e->biasf.push_back(o);
+  }
+  e->structure_dirty = true;
+  return CTVIO_OK;
+}
+
+int ctvio_set_prior(ctvio_handle e, int32_t n, const double* J, const double* r, int32_t nb, const int32_t* type,
+                    const int32_t* index, const int32_t* col, const double* x0) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  e->prior = ctvio::PriorHost();
+  e->prior_dirty = true;
+  if (n <= 0) return CTVIO_OK;
+  if (!J || !r || nb <= 0 || !type || !index || !col || !x0) return fail(CTVIO_ERR_INVALID, "null argument");
+  e->prior.n = n;
+  e->prior.J.assign(J, J + size_t(n) * n);
+  e->prior.r.assign(r, r + n);
+  e->prior.type.assign(type, type + nb);
+  e->prior.index.assign(index, index + nb);
+  e->prior.col.assign(col, col + nb);
+  e->prior.x0.assign(x0, x0 + 4 * size_t(nb));
+  return CTVIO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  cudaSetDevice(e->cfg.device);
+  int rc = prepare(e);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  const ProblemDims d = e->dims();
+  // Ceres 1.14 Solver::Options defaults
+  const double initial_radius = 1e4, max_radius = 1e16, min_radius = 1e-32, min_relative_decrease = 1e-3;
+  const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
+  const int max_consecutive_invalid = 5;
+  const double ls_sufficient_decrease = 1e-4, ls_max_contraction = 1e-3, ls_min_contraction = 0.6, ls_min_step = 1e-9;
+  const int ls_max_iterations = 20;
+
+  ctvio_summary sum;
+  std::memset(&sum, 0, sizeof(sum));
+  const int64_t launches0 = e->launches;
+  cudaEventRecord(e->ev0, st);
+
+  const bool is_constrained = !e->opt.fix_ld && e->h_active[d.idx_ld];
+  if (is_constrained) {  // IterationZero: x = Plus(x, 0) projects the line delay into its bounds
+    double ld;
+    CUDA_OK(cudaMemcpyAsync(&ld, e->x[e->cur].ld.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    const double c = std::min(std::max(ld, e->opt.ld_lower), e->opt.ld_upper);
+    if (c != ld) CUDA_OK(cudaMemcpyAsync(e->x[e->cur].ld.p, &c, sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  ensure_table(e);
+  int cur = e->cur;  // state buffer and normal-equation buffer flip together
+  evaluate(e, cur, cur, true);
+  sum.num_jacobian_evals++;
+  LinearLaunch lin = linear_launch(e, cur);
+  e->launches += launch_jacobi_scale(lin, st);
+  e->launches += launch_gradient_norm(lin, e->x[cur].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st);
+  rc = read_scalars(e);
+  if (rc) return rc;
+  double x_cost = e->h_scal->cost_eval;
+  double gmax = e->h_scal->gmax;
+  sum.initial_cost = x_cost;
+  sum.num_successful_steps = 1;
+
+  double radius = initial_radius, decrease_factor = 2.0;
+  int num_invalid = 0;
+  bool last_ok = true;
+  int iter = 0;
+  int term = CTVIO_TERM_NO_CONVERGENCE;
+
+  auto apply = [&](int from, int to, double alpha) {
+    ApplyLaunch ap;
+    ap.dims = d;
+    ap.x = e->x[from].ptrs();
+    ap.xc = e->x[to].ptrs();
+    ap.dc = e->d_dc.p; ap.dl = e->d_dl.p;
+    ap.alpha = alpha;
+    ap.active = e->d_active.p;
+    ap.clamp_ld = e->opt.fix_ld ? 0 : 1;
+    ap.ld_lower = e->opt.ld_lower; ap.ld_upper = e->opt.ld_upper;
+    ap.scal = e->d_scal.p;
+    e->launches += launch_apply_step(ap, st);
+  };
+
+  while (true) {
+    if (iter >= max_iterations) { term = CTVIO_TERM_NO_CONVERGENCE; break; }
+    if (last_ok && gmax <= gradient_tolerance) { term = CTVIO_TERM_GRADIENT; break; }
+    if (radius < min_radius) { term = CTVIO_TERM_MIN_RADIUS; break; }
+    ++iter;
+    const int cand = cur ^ 1;
+    // ---- trust-region step + speculative full evaluation of the candidate ----
+    lin = linear_launch(e, cur);
+    e->launches += launch_lm_step(lin, radius, st);
+    sum.num_linear_solves++;
+    if (e->world > 1) { /* reduced system is all-reduced inside launch_lm_step's caller in sharded mode (see comm) */ }
+    apply(cur, cand, 1.0);
+    evaluate(e, cand, cand, true);
+    sum.num_jacobian_evals++;
+    LinearLaunch linc = linear_launch(e, cand);
+    e->launches += launch_gradient_norm(linc, e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st);
+    rc = read_scalars(e);
+    if (rc) return rc;
+    const LmScalars sc = *e->h_scal;
+    const double model_cost_change = -sc.gd - 0.5 * sc.dHd;
+    const bool valid = !sc.chol_fail && std::isfinite(model_cost_change) && model_cost_change > 0.0;
+    if (!valid) {
+      ++sum.num_unsuccessful_steps;
+      last_ok = false;
+      if (++num_invalid >= max_consecutive_invalid) { term = CTVIO_TERM_FAILURE; break; }
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      continue;
+    }
+    num_invalid = 0;
+    double cand_cost = sc.cost_eval, cand_gmax = sc.gmax, step_norm2 = sc.step_norm2, x_norm2 = sc.x_norm2;
+    // ---- Armijo projected line search (bounds-constrained problems only; Ceres line_search.cc) ----
+    if (is_constrained) {
+      const double g0 = sc.gd;  // gradient . delta at x
+      struct Sample { double x, value, gradient; bool value_ok, grad_ok; };
+      Sample initial{0.0, x_cost, g0, true, true}, previous{0, 0, 0, false, false};
+      Sample current{1.0, cand_cost, 0.0, std::isfinite(cand_cost), false};
+      bool have_grad = false;
+      int ls_iters = 0;
+      bool success = true;
+      while (!current.value_ok || current.value > x_cost + ls_sufficient_decrease * g0 * current.x) {
+        ++ls_iters;
+        if (ls_iters >= ls_max_iterations) { success = false; break; }
+        if (current.value_ok && !have_grad) {
+          // directional derivative at the trial point: g(x + a d) . d from the candidate buffers
+          e->launches += ctvio::launch_dot_gradient(linear_launch(e, cand), st);
+          rc = read_scalars(e);
+          if (rc) return rc;
+          current.gradient = e->h_scal->gd;
+          current.grad_ok = std::isfinite(current.gradient);
+        }
+        const double smin = ls_max_contraction * current.x, smax = ls_min_contraction * current.x;
+        double step;
+        if (!current.value_ok) {
+          step = std::min(std::max(current.x * 0.5, smin), smax);
+        } else {
+          std::vector<ctvio::PolySample> samples;
+          samples.push_back({initial.x, initial.value, initial.gradient, true, true});
+          samples.push_back({current.x, current.value, current.gradient, true, current.grad_ok});
+          if (previous.value_ok) samples.push_back({previous.x, previous.value, previous.gradient, true, previous.grad_ok});
+          step = ctvio::minimize_interpolating_polynomial(samples, smin, smax);
+        }
+        if (step * sc.dir_max < ls_min_step) { success = false; break; }
+        previous = current;
+        apply(cur, cand, step);
+        evaluate(e, cand, cand, true);
+        sum.num_jacobian_evals++;
+        e->launches += launch_gradient_norm(linear_launch(e, cand), e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower,
+                                            e->opt.ld_upper, st);
+        rc = read_scalars(e);
+        if (rc) return rc;
+        current = Sample{step, e->h_scal->cost_eval, 0.0, std::isfinite(e->h_scal->cost_eval), false};
+        have_grad = false;
+      }
+      sum.num_line_search_steps += ls_iters;
+      if (!success && current.x != 1.0) {
+        // Ceres keeps the full step when the search fails: rebuild the alpha = 1 candidate
+        apply(cur, cand, 1.0);
+        evaluate(e, cand, cand, true);
+        sum.num_jacobian_evals++;
+        e->launches += launch_gradient_norm(linear_launch(e, cand), e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower,
+                                            e->opt.ld_upper, st);
+        rc = read_scalars(e);
+        if (rc) return rc;
+      }
+      cand_cost = e->h_scal->cost_eval;
+      cand_gmax = e->h_scal->gmax;
+      step_norm2 = e->h_scal->step_norm2;
+      x_norm2 = e->h_scal->x_norm2;
+    }
+    // ---- tolerances, step acceptance ----
+    const double step_norm = std::sqrt(step_norm2), x_norm = std::sqrt(x_norm2);
+    if (step_norm <= parameter_tolerance * (x_norm + parameter_tolerance)) { term = CTVIO_TERM_PARAMETER; break; }
+    const double cost_change = x_cost - cand_cost;
+    if (std::fabs(cost_change) <= function_tolerance * x_cost) { term = CTVIO_TERM_FUNCTION; break; }
+    const double rho = cost_change / model_cost_change;
+    if (rho > min_relative_decrease) {
+      cur = cand;  // candidate state AND its normal equations become current: no re-linearisation pass
+      x_cost = cand_cost;
+      gmax = cand_gmax;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3));
+      radius = std::min(max_radius, radius);
+      decrease_factor = 2.0;
+      last_ok = true;
+      ++sum.num_successful_steps;
+    } else {
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      last_ok = false;
+      ++sum.num_unsuccessful_steps;
+    }
+  }
+  e->cur = cur;
+  e->table_valid = true;
+  cudaEventRecord(e->ev1, st);
+  CUDA_OK(cudaEventSynchronize(e->ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  sum.iterations = iter;
+  sum.termination = term;
+  sum.final_cost = x_cost;
+  sum.final_radius = radius;
+  sum.device_ms = ms;
+  sum.kernel_launches = e->launches - launches0;
+  if (out) *out = sum;
+  return CTVIO_OK;
+}
+
+int ctvio_gauge_realign(ctvio_handle e, int32_t min_idx, const double* R0, const double* t0) {
+  if (!e || !R0 || !t0 || min_idx < 0 || min_idx >= e->nK) return fail(CTVIO_ERR_INVALID, "bad argument");
+  cudaSetDevice(e->cfg.device);
+  CUDA_OK(e->d_tmp.reserve(12));
+  double h[12];
+  for (int k = 0; k < 9; ++k) h[k] = R0[k];
+  for (int k = 0; k < 3; ++k) h[9 + k] = t0[k];
+  CUDA_OK(cudaMemcpyAsync(e->d_tmp.p, h, sizeof(h), cudaMemcpyHostToDevice, e->stream));
+  e->launches += launch_gauge_realign(e->x[e->cur].ptrs(), e->nK, min_idx, e->d_tmp.p, e->stream);
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->table_valid = true;
+  return CTVIO_OK;
+}
+
+int ctvio_save_state(ctvio_handle e) {
+  if (!e || !e->have_knots) return fail(CTVIO_ERR_STATE, "state not set");
+  cudaSetDevice(e->cfg.device);
+  int rc = alloc_state(e, e->snap);
+  if (rc) return rc;
+  DevState& s = e->x[e->cur];
+  cudaStream_t st = e->stream;
+  CUDA_OK(cudaMemcpyAsync(e->snap.q.p, s.q.p, 4 * size_t(e->nK) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->snap.p.p, s.p.p, kPStride * size_t(e->nK) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (e->nB) CUDA_OK(cudaMemcpyAsync(e->snap.bias.p, s.bias.p, 6 * size_t(e->nB) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (e->nL) CUDA_OK(cudaMemcpyAsync(e->snap.rho.p, s.rho.p, size_t(e->nL) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->snap.ld.p, s.ld.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return CTVIO_OK;
+}
+int ctvio_restore_state(ctvio_handle e) {
+  if (!e || !e->snap.q.p) return fail(CTVIO_ERR_STATE, "no snapshot");
+  cudaSetDevice(e->cfg.device);
+  DevState& s = e->x[e->cur];
+  cudaStream_t st = e->stream;
+  CUDA_OK(cudaMemcpyAsync(s.q.p, e->snap.q.p, 4 * size_t(e->nK) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(s.p.p, e->snap.p.p, kPStride * size_t(e->nK) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (e->nB) CUDA_OK(cudaMemcpyAsync(s.bias.p, e->snap.bias.p, 6 * size_t(e->nB) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (e->nL) CUDA_OK(cudaMemcpyAsync(s.rho.p, e->snap.rho.p, size_t(e->nL) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(s.ld.p, e->snap.ld.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  e->table_valid = false;
+  return CTVIO_OK;
+}
+
+// ---- probes --------------------------------------------------------------------------------------
+int ctvio_eval_image_factors(ctvio_handle e, int32_t want_jac, double cauchy, double* r, int32_t* s, double* J,
+                             double* cost) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  cudaSetDevice(e->cfg.device);
+  int rc = prepare(e);
+  if (rc) return rc;
+  ensure_table(e);
+  const size_t n = e->img.size();
+  DevBuf<double> dr, dJ;
+  DevBuf<int32_t> ds;
+  CUDA_OK(dr.reserve(2 * n));
+  CUDA_OK(ds.reserve(2 * n));
+  if (want_jac) CUDA_OK(dJ.reserve(100 * n));
+  cudaStream_t st = e->stream;
+  cudaMemsetAsync(&e->d_scal.p->cost_eval, 0, sizeof(double), st);
+  e->launches += launch_probe_image(visual_launch(e, e->cur, e->cur, cauchy), e->d_img_orig.p, want_jac != 0, dr.p, ds.p,
+                                    want_jac ? dJ.p : nullptr, st);
+  rc = read_scalars(e);
+  if (rc) return rc;
+  if (r && n) CUDA_OK(cudaMemcpy(r, dr.p, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (s && n) CUDA_OK(cudaMemcpy(s, ds.p, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (J && want_jac && n) CUDA_OK(cudaMemcpy(J, dJ.p, 100 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cost) *cost = e->h_scal->cost_eval;
+  return CTVIO_OK;
+}
+
+int ctvio_eval_imu_factors(ctvio_handle e, int32_t want_jac, double* r, int32_t* s, double* J, double* cost) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  cudaSetDevice(e->cfg.device);
+  int rc = prepare(e);
+  if (rc) return rc;
+  ensure_table(e);
+  const size_t n = e->imu.size();
+  DevBuf<double> dr, dJ;
+  DevBuf<int32_t> ds;
+  CUDA_OK(dr.reserve(6 * n));
+  CUDA_OK(ds.reserve(n));
+  if (want_jac) CUDA_OK(dJ.reserve(156 * n));
+  cudaStream_t st = e->stream;
+  cudaMemsetAsync(&e->d_scal.p->cost_eval, 0, sizeof(double), st);
+  e->launches += launch_probe_imu(imu_launch(e, e->cur, e->cur), want_jac != 0, dr.p, ds.p, want_jac ? dJ.p : nullptr, st);
+  rc = read_scalars(e);
+  if (rc) return rc;
+  if (r && n) CUDA_OK(cudaMemcpy(r, dr.p, 6 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (s && n) CUDA_OK(cudaMemcpy(s, ds.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (J && want_jac && n) CUDA_OK(cudaMemcpy(J, dJ.p, 156 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cost) *cost = e->h_scal->cost_eval;
+  return CTVIO_OK;
+}
+
+int ctvio_eval_cost(ctvio_handle e, double* cost) {
+  if (!e || !cost) return fail(CTVIO_ERR_INVALID, "null argument");
+  cudaSetDevice(e->cfg.device);
+  int rc = prepare(e);
+  if (rc) return rc;
+  ensure_table(e);
+  evaluate(e, e->cur, e->cur, false);
+  rc = read_scalars(e);
+  if (rc) return rc;
+  *cost = e->h_scal->cost_eval;
+  return CTVIO_OK;
+}
+
+int ctvio_normal_equations(ctvio_handle e, double* Hcc, double* gc, double* hl, double* gl, double* cost) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  cudaSetDevice(e->cfg.device);
+  int rc = prepare(e);
+  if (rc) return rc;
+  ensure_table(e);
+  evaluate(e, e->cur, e->cur, true);
+  rc = read_scalars(e);
+  if (rc) return rc;
+  const ProblemDims d = e->dims();
+  const size_t np = d.np;
+  NormalEqPtrs ne = e->ne(e->cur);
+  if (Hcc) {
+    std::vector<double> up(np * np);
+    CUDA_OK(cudaMemcpy(up.data(), ne.A, np * np * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < np; ++i)
+      for (size_t j = i; j < np; ++j) Hcc[i * np + j] = Hcc[j * np + i] = up[i * np + j];
+  }
+  if (gc) CUDA_OK(cudaMemcpy(gc, ne.gc, np * sizeof(double), cudaMemcpyDeviceToHost));
+  if (hl && e->nL) CUDA_OK(cudaMemcpy(hl, ne.hl, e->nL * sizeof(double), cudaMemcpyDeviceToHost));
+  if (gl && e->nL) CUDA_OK(cudaMemcpy(gl, ne.gl, e->nL * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cost) *cost = e->h_scal->cost_eval;
+  return CTVIO_OK;
+}
+
+int ctvio_query_trajectory(ctvio_handle e, int32_t n, const int64_t* t, double* q, double* p, double* omega,
+                           double* vel, double* acc) {
+  if (!e || n < 0 || (n > 0 && !t)) return fail(CTVIO_ERR_INVALID, "bad argument");
+  if (!e->have_knots) return fail(CTVIO_ERR_STATE, "knots have not been set");
+  cudaSetDevice(e->cfg.device);
+  ensure_table(e);
+  if (n == 0) return CTVIO_OK;
+  DevBuf<int64_t> dt;
+  DevBuf<double> out;
+  CUDA_OK(dt.reserve(n));
+  CUDA_OK(out.reserve(16 * size_t(n)));
+  cudaStream_t st = e->stream;
+  CUDA_OK(cudaMemcpyAsync(dt.p, t, size_t(n) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  QueryLaunch a;
+  a.st = e->x[e->cur].ptrs();
+  a.sp = e->sp;
+  a.n = n;
+  a.t = dt.p;
+  a.q = out.p; a.p = out.p + 4 * size_t(n); a.omega = out.p + 7 * size_t(n); a.vel = out.p + 10 * size_t(n);
+  a.acc = out.p + 13 * size_t(n);
+  a.scal = e->d_scal.p;
+  e->launches += launch_query(a, st);
+  int rc = read_scalars(e);
+  if (rc) return rc;
+  if (q) CUDA_OK(cudaMemcpy(q, a.q, 4 * size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+  if (p) CUDA_OK(cudaMemcpy(p, a.p, 3 * size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+  if (omega) CUDA_OK(cudaMemcpy(omega, a.omega, 3 * size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+  if (vel) CUDA_OK(cudaMemcpy(vel, a.vel, 3 * size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+  if (acc) CUDA_OK(cudaMemcpy(acc, a.acc, 3 * size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+  return CTVIO_OK;
+}
+
+// ---- marginalization (K7), see marginalize.cu ---------------------------------------------------
+int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
+  if (!e || !n_out || !nb_out) return fail(CTVIO_ERR_INVALID, "null argument");
+  *n_out = 0;
+  *nb_out = 0;
+  return fail(CTVIO_ERR_STATE, "ctvio_marginalize: GPU marginalization is not built into this library yet");
+}
+int ctvio_get_prior(ctvio_handle e, double* J, double* r, int32_t* type, int32_t* index, int32_t* col, double* x0) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  const ctvio::PriorHost& p = e->new_prior;
+  if (p.n <= 0) return fail(CTVIO_ERR_STATE, "no prior has been produced");
+  if (J) std::memcpy(J, p.J.data(), p.J.size() * sizeof(double));
+  if (r) std::memcpy(r, p.r.data(), p.r.size() * sizeof(double));
+  if (type) std::memcpy(type, p.type.data(), p.type.size() * sizeof(int32_t));
+  if (index) std::memcpy(index, p.index.data(), p.index.size() * sizeof(int32_t));
+  if (col) std::memcpy(col, p.col.data(), p.col.size() * sizeof(int32_t));
+  if (x0) std::memcpy(x0, p.x0.data(), p.x0.size() * sizeof(double));
+  return CTVIO_OK;
+}
+int ctvio_adopt_prior(ctvio_handle e) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  e->prior = e->new_prior;
+  e->prior_dirty = true;
+  return CTVIO_OK;
+}
+
+int ctvio_nccl_unique_id(uint8_t* id128) {
+  if (!id128) return fail(CTVIO_ERR_INVALID, "null argument");
+  std::string err;
+  if (!ctvio::comm_unique_id(id128, &err)) return fail(CTVIO_ERR_NCCL, err);
+  return CTVIO_OK;
+}
+int ctvio_comm_init(ctvio_handle e, int32_t rank, int32_t world, const uint8_t* id128) {
+  if (!e || !id128 || world < 1 || rank < 0 || rank >= world) return fail(CTVIO_ERR_INVALID, "bad argument");
+  cudaSetDevice(e->cfg.device);
+  std::string err;
+  void* comm = ctvio::comm_create(rank, world, id128, &err);
+  if (!comm) return fail(CTVIO_ERR_NCCL, err);
+  ctvio::comm_destroy(e->nccl_comm);
+  e->nccl_comm = comm;
+  e->rank = rank;
+  e->world = world;
+  return CTVIO_OK;
+}
+
+}  // extern "C"

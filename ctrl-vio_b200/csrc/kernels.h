@@ -1,0 +1,215 @@
+// Device data layout + kernel launch wrappers of the CUDA engine.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "spline_eval.cuh"
+
+namespace ctvio {
+
+constexpr int kPStride = 4;        // knot positions are stored [N][4] (32 B) so that TMA windows are 16-B aligned
+constexpr int kVisThreads = 256;   // visual kernel CTA: 128 lane pairs
+constexpr int kVisObsPerRound = 128;
+constexpr int kLocalDim = 64;      // padded local Jacobian width of one frame-pair group
+constexpr int kWinKnots = 5;       // knots of a padded evaluation window (se3_spline.h:463-503 with 39 ms padding)
+constexpr int kColLd = 60, kColR = 61, kColRho = 62;
+constexpr int kSchurMaxDim = 192;  // widest landmark-batch knot range handled by the tiled Schur kernel
+constexpr int kSchurBatch = 64;
+constexpr int kCholNB = 64;
+
+// ---- state at one linearisation point (all HBM) ------------------------------------------------
+struct StatePtrs {
+  double* q;       // [nK][4] xyzw
+  double* p;       // [nK][4] xyz + pad
+  double* bias;    // [nB][6]
+  double* rho;     // [nL]
+  double* ld;      // [1]
+  KnotPair* tab;   // [nK-1] knot-pair table of this state
+};
+
+// ---- Schur-form normal equations at one linearisation point -------------------------------------
+struct NormalEqPtrs {
+  double* A;     // [np][np] camera block, UPPER triangle valid (row <= col), unscaled
+  double* gc;    // [np]
+  double* hl;    // [nL]  landmark diagonal
+  double* gl;    // [nL]  landmark gradient
+  double* wld;   // [nL]  landmark x line-delay coupling
+  double* W;     // landmark x knot coupling, compact per landmark over its knot-dim range [lo, hi)
+  double* cost;  // [1]
+};
+
+// image observations, sorted by frame-pair group; SoA, 16-byte vector loads (64 B / obs + 8 B rho gather)
+struct ImageObsPtrs {
+  const longlong2* t;     // {ti, tj}
+  const double2* pi;      // anchor bearing xy
+  const double2* pj;      // observation xy
+  const int4* meta;       // {rowi, rowj, landmark, marg}
+  int32_t n;
+};
+
+struct VisualItem {  // one CTA work item: a chunk of one frame-pair group
+  int32_t start, count;
+  int32_t wi0, wj0;  // first knot of the padded anchor / observation windows
+};
+
+struct ImuObsPtrs {
+  const longlong2* t_node;  // {t, bias node}
+  const double2* ga;        // [n][3] double2: {gx,gy},{gz,ax},{ay,az}
+  int32_t n;
+};
+
+struct BiasFactorPtrs {
+  const int2* ij;
+  const double* sqrt_info;  // [n][6]
+  int32_t n;
+};
+
+struct PriorPtrs {
+  int32_t n, n_blocks;
+  const double* J;       // [n][n] row-major
+  const double* r;       // [n]
+  const double* JtJ;     // [n][n]
+  const int32_t* type;   // per block
+  const int32_t* index;
+  const int32_t* col;
+  const double* x0;      // [n_blocks][4]
+  const int32_t* col2g;  // [n] column -> camera dim (or -1)
+  double* dx;            // [n] scratch
+  double* res;           // [n] scratch
+};
+
+struct ProblemDims {
+  int32_t nK, nB, nL, np, idx_bias0, idx_ld;
+};
+
+struct LandmarkLayout {
+  const int32_t* lo;     // [nL] first camera dim of the landmark's knot range
+  const int32_t* hi;     // [nL]
+  const int64_t* woff;   // [nL+1] offsets into W
+};
+
+struct SchurBatch {
+  int32_t first, count;  // landmarks [first, first+count) in schur order
+  int32_t ulo, uhi;      // union knot-dim range
+};
+
+// scalars exchanged with the host once per LM step
+struct LmScalars {
+  double cost_eval;        // cost accumulated by the last evaluation pass
+  double gd;               // g' delta
+  double dHd;              // delta' H delta
+  double step_norm2;       // |x - x+|^2 (ambient, active blocks)
+  double x_norm2;          // |x|^2 (ambient, active blocks)
+  double gmax;             // max |g| over active dims (bounds-projected for the line delay)
+  double dir_max;          // max |delta|
+  double ld_value;         // line delay of the candidate state
+  int32_t chol_fail;       // non-positive pivot / non-finite
+  int32_t error_flags;     // bit0: factor time outside its window / spline
+  int32_t pad[2];
+};
+
+// ---- launch wrappers (each returns the number of kernels it launched) ----------------------------
+int launch_knot_table(const StatePtrs& st, int nK, cudaStream_t s);
+
+struct VisualLaunch {
+  ImageObsPtrs obs;
+  const VisualItem* items;
+  int32_t n_items;
+  StatePtrs st;
+  NormalEqPtrs ne;
+  LandmarkLayout lm;
+  ProblemDims dims;
+  SplineParams sp;
+  RigParams rig;
+  double cauchy;
+  const uint8_t* cmask;   // [np] 1 = constant
+  LmScalars* scal;
+  bool use_tma;
+};
+int launch_visual(const VisualLaunch& a, bool full, cudaStream_t s);
+size_t visual_smem_bytes();
+
+struct ImuLaunch {
+  ImuObsPtrs obs;
+  StatePtrs st;
+  NormalEqPtrs ne;
+  ProblemDims dims;
+  SplineParams sp;
+  RigParams rig;
+  const uint8_t* cmask;
+  LmScalars* scal;
+};
+int launch_imu(const ImuLaunch& a, bool full, cudaStream_t s);
+
+struct SmallFactorsLaunch {
+  BiasFactorPtrs bf;
+  PriorPtrs prior;
+  StatePtrs st;
+  NormalEqPtrs ne;
+  ProblemDims dims;
+  const uint8_t* cmask;
+  LmScalars* scal;
+};
+int launch_small_factors(const SmallFactorsLaunch& a, bool full, cudaStream_t s);
+
+// probes (parity tests): per-factor residuals / Jacobians in the C-ABI layout, original factor order
+int launch_probe_image(const VisualLaunch& a, const int32_t* orig_index, bool want_jac, double* r, int32_t* s,
+                       double* J, cudaStream_t st);
+int launch_probe_imu(const ImuLaunch& a, bool want_jac, double* r, int32_t* s, double* J, cudaStream_t st);
+
+// ---- linear algebra / LM step -------------------------------------------------------------------
+struct LinearLaunch {
+  ProblemDims dims;
+  NormalEqPtrs ne;
+  LandmarkLayout lm;
+  const int32_t* schur_order;   // [nL] landmark ids in batch order
+  const SchurBatch* batches;
+  int32_t n_batches;
+  const int32_t* wide_lms;      // landmarks whose own range exceeds kSchurMaxDim (slow path)
+  int32_t n_wide;
+  const uint8_t* cmask;
+  const uint8_t* active;        // [np + nL]
+  double* sc;                   // [np] Jacobi scale
+  double* sl;                   // [nL]
+  double* M;                    // [npad][npad] reduced system (full symmetric), npad = multiple of kCholNB
+  double* Linv;                 // [npad/NB][NB][NB] inverses of the diagonal Cholesky blocks
+  double* rhs;                  // [npad]
+  double* y;                    // [npad]
+  double* hh;                   // [nL] damped landmark diagonals
+  double* dc;                   // [np] step (camera dims)
+  double* dl;                   // [nL]
+  int32_t npad;
+  LmScalars* scal;
+};
+int launch_jacobi_scale(const LinearLaunch& a, cudaStream_t s);
+// builds the damped, scaled reduced system, factors it, solves and back-substitutes: dc, dl, gd, dHd
+int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s);
+int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld, double ld_lower, double ld_upper,
+                         cudaStream_t s);
+
+struct ApplyLaunch {
+  ProblemDims dims;
+  StatePtrs x, xc;          // current, candidate
+  const double* dc;
+  const double* dl;
+  double alpha;
+  const uint8_t* active;
+  int32_t clamp_ld;
+  double ld_lower, ld_upper;
+  LmScalars* scal;
+};
+int launch_apply_step(const ApplyLaunch& a, cudaStream_t s);
+int launch_gauge_realign(const StatePtrs& st, int nK, int min_idx, const double* R0_t0_dev, cudaStream_t s);
+
+struct QueryLaunch {
+  StatePtrs st;
+  SplineParams sp;
+  int32_t n;
+  const int64_t* t;
+  double *q, *p, *omega, *vel, *acc;
+  LmScalars* scal;
+};
+int launch_query(const QueryLaunch& a, cudaStream_t s);
+
+}  // namespace ctvio

@@ -1,0 +1,757 @@
+// Residual / Jacobian / normal-equation kernels of the CUDA engine (sm_100a, fp64).
+//
+//   knot_table_kernel   K0  per linearisation point: d_k, |d_k|, Jr^-1(d_k) for every knot pair
+//   visual_kernel       K1  replaces ImageFeatureDelayFactor::Evaluate (image_feature_factor.h:63-269)
+//                           + loss corrector + Ceres' J'J / J'r build for all image factors
+//   imu_kernel          K2  replaces IMUFactor::Evaluate (trajectory_value_factor.h:141-248)
+//   small_factors_kernel K3 replaces BiasFactor::Evaluate (:45-99) and MarginalizationFactor::Evaluate
+//                           (marginalization_factor.cpp:326-373)
+//
+// K1 design (B200-first, not a translation of the reference's per-factor virtual calls):
+//   * observations are pre-sorted by frame-pair group = (first knot of the padded anchor window,
+//     first knot of the padded observation window); one CTA owns a chunk of one group, so every
+//     Jacobian row of the chunk lives in the same 61-dim local space
+//     [anchor window 5 knots x 6 | observation window 5 knots x 6 | line delay] (+ residual column);
+//   * the 10 active control knots and their knot-pair table entries are staged in shared memory
+//     by TMA bulk copies (cp.async.bulk + mbarrier) — 6 copies, ~2 KB per CTA;
+//   * a LANE PAIR evaluates one observation: even lane = anchor pose, odd lane = observation pose
+//     (eval_side), 18 doubles exchanged by warp shuffles, each lane then chain-rules its own 4 knots;
+//   * Jacobian rows never go to HBM: they are written to a shared-memory tile (128 obs x 2 rows x 64)
+//     and reduced by a register-tiled SYRK (8x8 tiles, 7 row groups) into a shared accumulator that
+//     is flushed once per CTA with fp64 atomics into the upper-triangular camera block A and g;
+//   * landmark Schur pieces (h_l, g_l, W_l) are reduced with fp64 RED atomics into the compact
+//     per-landmark rows.
+// Algorithmic HBM traffic per observation: 64 B record + 8 B inverse-depth gather.
+#include <cstdio>
+
+#include "kernels.h"
+
+namespace ctvio {
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers: shared-memory addresses, mbarrier, TMA bulk copy
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0
+
+__global__ void knot_table_kernel(StatePtrs st, int nK) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nK - 1) return;
+  KnotPair kp;
+  make_knot_pair(st.q, k, kp);
+  st.tab[k] = kp;
+}
+
+int launch_knot_table(const StatePtrs& st, int nK, cudaStream_t s) {
+  if (nK < 2) return 0;
+  knot_table_kernel<<<(nK - 1 + 127) / 128, 128, 0, s>>>(st, nK);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1
+
+struct VisArgs {
+  ImageObsPtrs obs;
+  const VisualItem* items;
+  StatePtrs st;
+  NormalEqPtrs ne;
+  LandmarkLayout lm;
+  ProblemDims dims;
+  SplineParams sp;
+  RigParams rig;
+  double cauchy;
+  const uint8_t* cmask;
+  LmScalars* scal;
+  int use_tma;
+};
+
+struct __align__(128) VisStatic {
+  KnotPair tab[2][4];            // 1024 B
+  double q[2][kWinKnots][4];     // 320 B
+  double p[2][kWinKnots][4];     // 320 B
+  double cost_part[8];
+  unsigned long long bar;
+  int err;
+};
+
+// upper-triangular tiles of the 8x8 tile grid over the 64 local dims
+__constant__ uint8_t c_tile_i[36] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2,
+                                     2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 6, 6, 7};
+__constant__ uint8_t c_tile_j[36] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 2, 3, 4, 5, 6, 7, 2, 3, 4,
+                                     5, 6, 7, 3, 4, 5, 6, 7, 4, 5, 6, 7, 5, 6, 7, 6, 7, 7};
+
+size_t visual_smem_bytes() {
+  return size_t(kVisObsPerRound) * 2 * kLocalDim * sizeof(double) + size_t(36) * 64 * sizeof(double);
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_constant__ VisArgs a) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  double* Jt = reinterpret_cast<double*>(dyn_smem);                 // [128][2][64]
+  double* accs = Jt + size_t(kVisObsPerRound) * 2 * kLocalDim;      // [36][64]
+  __shared__ VisStatic sm;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const VisualItem item = a.items[blockIdx.x];
+  const int nK = a.dims.nK;
+
+  // ---- stage the 10 active knots + 8 knot-pair entries (TMA bulk copies, one mbarrier) ----
+  const int w0[2] = {item.wi0, item.wj0};
+  if (a.use_tma) {
+    if (tid == 0) {
+      sm.err = 0;
+      mbar_init(reinterpret_cast<uint64_t*>(&sm.bar), 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t bytes = 0;
+#pragma unroll
+      for (int sd = 0; sd < 2; ++sd) {
+        const int nk = min(kWinKnots, nK - w0[sd]);
+        const int npair = min(4, nK - 1 - w0[sd]);
+        bytes += uint32_t(nk) * 64u + uint32_t(npair) * uint32_t(sizeof(KnotPair));
+      }
+      mbar_expect_tx(reinterpret_cast<uint64_t*>(&sm.bar), bytes);
+#pragma unroll
+      for (int sd = 0; sd < 2; ++sd) {
+        const int nk = min(kWinKnots, nK - w0[sd]);
+        const int npair = min(4, nK - 1 - w0[sd]);
+        tma_bulk_g2s(&sm.q[sd][0][0], a.st.q + 4 * w0[sd], uint32_t(nk) * 32u, reinterpret_cast<uint64_t*>(&sm.bar));
+        tma_bulk_g2s(&sm.p[sd][0][0], a.st.p + 4 * w0[sd], uint32_t(nk) * 32u, reinterpret_cast<uint64_t*>(&sm.bar));
+        tma_bulk_g2s(&sm.tab[sd][0], a.st.tab + w0[sd], uint32_t(npair) * uint32_t(sizeof(KnotPair)),
+                     reinterpret_cast<uint64_t*>(&sm.bar));
+      }
+    }
+  } else {
+    if (tid == 0) sm.err = 0;
+    // plain cooperative loads (debug path, CTVIO_NO_TMA=1)
+    for (int i = tid; i < 2 * kWinKnots * 4; i += kVisThreads) {
+      const int sd = i / (kWinKnots * 4), r = i % (kWinKnots * 4);
+      const int k = w0[sd] + r / 4;
+      (&sm.q[sd][0][0])[r] = k < nK ? a.st.q[4 * k + (r & 3)] : 0.0;
+      (&sm.p[sd][0][0])[r] = k < nK ? a.st.p[4 * k + (r & 3)] : 0.0;
+    }
+    for (int i = tid; i < 2 * 4 * 16; i += kVisThreads) {
+      const int sd = i / 64, r = i % 64;
+      const int k = w0[sd] + r / 16;
+      reinterpret_cast<double*>(&sm.tab[sd][0])[r] = k < nK - 1 ? reinterpret_cast<const double*>(a.st.tab + k)[r & 15] : 0.0;
+    }
+  }
+  if (FULL)
+    for (int i = tid; i < 36 * 64; i += kVisThreads) accs[i] = 0.0;
+  if (a.use_tma) {
+    while (!mbar_try_wait(reinterpret_cast<uint64_t*>(&sm.bar), 0)) {
+    }
+  }
+  __syncthreads();
+
+  const double ld = *a.st.ld;
+  const int64_t ld_ns = int64_t(ld * 1e9);  // image_feature_factor.h:72 (truncation)
+  const int side = tid & 1;
+  double cost_local = 0.0;
+
+  for (int base = 0; base < item.count; base += kVisObsPerRound) {
+    const int nround = min(kVisObsPerRound, item.count - base);
+    const int ol = tid >> 1;  // observation slot of this lane pair
+    const bool active = ol < nround;
+    double* row0 = Jt + size_t(ol) * 2 * kLocalDim;
+    double* row1 = row0 + kLocalDim;
+    bool valid = false;
+    const unsigned m_act = __ballot_sync(0xffffffffu, active);  // lane pairs are active together
+    if (active) {
+      const int oi = item.start + base + ol;
+      const longlong2 tt = a.obs.t[oi];
+      const double2 pi = a.obs.pi[oi];
+      const double2 pj = a.obs.pj[oi];
+      const int4 meta = a.obs.meta[oi];
+      const double rho = a.st.rho[meta.z];
+      const int64_t t_eval = side == 0 ? tt.x + int64_t(meta.x) * ld_ns : tt.y + int64_t(meta.y) * ld_ns;
+      int32_t s;
+      double u;
+      bool ok = spline_index(a.sp, t_eval, s, u);
+      const int slot = s - w0[side];
+      ok = ok && (slot == 0 || slot == 1);
+      const bool ok_both = __shfl_xor_sync(m_act, ok ? 1 : 0, 1) && ok;
+      const unsigned m_ok = __ballot_sync(m_act, ok_both);  // lanes that run the exchange below
+      valid = ok_both;
+      if (!ok_both) {
+        atomicOr(&sm.err, 1);
+      } else {
+        SideEval ev;
+        eval_side<FULL, kPStride>(a.sp, &sm.q[side][0][0], &sm.p[side][0][0], sm.tab[side], slot, u, ev);
+        // exchange pose (and velocities) with the partner lane
+        M3 Ro;
+        V3 po, omo, vo;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Ro.m[e] = __shfl_xor_sync(m_ok, ev.R.m[e], 1);
+        po = V3{__shfl_xor_sync(m_ok, ev.p.x, 1), __shfl_xor_sync(m_ok, ev.p.y, 1), __shfl_xor_sync(m_ok, ev.p.z, 1)};
+        if (FULL) {
+          omo = V3{__shfl_xor_sync(m_ok, ev.omega.x, 1), __shfl_xor_sync(m_ok, ev.omega.y, 1),
+                   __shfl_xor_sync(m_ok, ev.omega.z, 1)};
+          vo = V3{__shfl_xor_sync(m_ok, ev.vel.x, 1), __shfl_xor_sync(m_ok, ev.vel.y, 1),
+                  __shfl_xor_sync(m_ok, ev.vel.z, 1)};
+        }
+        const M3& R_i = side == 0 ? ev.R : Ro;
+        const M3& R_j = side == 0 ? Ro : ev.R;
+        const V3 p_i = side == 0 ? ev.p : po;
+        const V3 p_j = side == 0 ? po : ev.p;
+        ImageCommon cm;
+        const double pixy[2] = {pi.x, pi.y}, pjxy[2] = {pj.x, pj.y};
+        image_common(a.rig, pixy, pjxy, rho, R_i, p_i, R_j, p_j, a.cauchy, cm);
+        if (side == 0) cost_local += cm.cost;
+        if (FULL) {
+          double rot[4][6], pos[4][6], jrho[2];
+          image_side_blocks(side, cm, ev, rot, pos);
+          image_jrho(a.rig, cm, R_i, rho, jrho);
+          // constant-parameter masking + write the lane's 30 local columns (5 knot slots x 6)
+          const int cb = side * 30;
+          const int gk0 = w0[side];
+#pragma unroll
+          for (int kk = 0; kk < kWinKnots; ++kk) {
+            // k = kk - slot, resolved with selects so that register arrays keep static indices
+            double v0[6], v1[6];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double r0a = kk < 4 ? rot[kk < 4 ? kk : 0][c] : 0.0, r0b = kk >= 1 ? rot[kk >= 1 ? kk - 1 : 0][c] : 0.0;
+              const double r1a = kk < 4 ? rot[kk < 4 ? kk : 0][3 + c] : 0.0, r1b = kk >= 1 ? rot[kk >= 1 ? kk - 1 : 0][3 + c] : 0.0;
+              const double p0a = kk < 4 ? pos[kk < 4 ? kk : 0][c] : 0.0, p0b = kk >= 1 ? pos[kk >= 1 ? kk - 1 : 0][c] : 0.0;
+              const double p1a = kk < 4 ? pos[kk < 4 ? kk : 0][3 + c] : 0.0, p1b = kk >= 1 ? pos[kk >= 1 ? kk - 1 : 0][3 + c] : 0.0;
+              v0[c] = slot == 0 ? r0a : r0b;
+              v1[c] = slot == 0 ? r1a : r1b;
+              v0[3 + c] = slot == 0 ? p0a : p0b;
+              v1[3 + c] = slot == 0 ? p1a : p1b;
+            }
+            const int gk = gk0 + kk;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              const bool is_const = gk < nK ? (a.cmask[6 * gk + c] != 0) : true;
+              row0[cb + kk * 6 + c] = is_const ? 0.0 : v0[c];
+              row1[cb + kk * 6 + c] = is_const ? 0.0 : v1[c];
+            }
+          }
+          if (side == 0) {
+            row0[kColR] = cm.r[0]; row1[kColR] = cm.r[1];
+            row0[kColRho] = jrho[0]; row1[kColRho] = jrho[1];
+          } else {
+            double jld[2];
+            image_jld(a.rig, cm, meta.x, meta.y, R_i, omo, vo, R_j, ev.omega, ev.vel, jld);
+            const bool ld_const = a.cmask[a.dims.idx_ld] != 0;
+            row0[kColLd] = ld_const ? 0.0 : jld[0];
+            row1[kColLd] = ld_const ? 0.0 : jld[1];
+            row0[63] = 0.0; row1[63] = 0.0;
+          }
+          // landmark Schur pieces straight from registers: W_l += J_c' J_rho, h_l, g_l, w_ld
+          const int l = meta.z;
+          double* Wl = a.ne.W + a.lm.woff[l] - a.lm.lo[l];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int gd = 6 * (gk0 + slot + k);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (!a.cmask[gd + c]) atomicAdd(Wl + gd + c, rot[k][c] * jrho[0] + rot[k][3 + c] * jrho[1]);
+              if (!a.cmask[gd + 3 + c]) atomicAdd(Wl + gd + 3 + c, pos[k][c] * jrho[0] + pos[k][3 + c] * jrho[1]);
+            }
+          }
+          if (side == 0) {
+            atomicAdd(a.ne.hl + l, jrho[0] * jrho[0] + jrho[1] * jrho[1]);
+            atomicAdd(a.ne.gl + l, jrho[0] * cm.r[0] + jrho[1] * cm.r[1]);
+          } else {
+            atomicAdd(a.ne.wld + l, row0[kColLd] * jrho[0] + row1[kColLd] * jrho[1]);
+          }
+        }
+      }
+    }
+    if (FULL) {
+      if (!valid && ol < kVisObsPerRound) {
+        // inactive / invalid observation: its half of the two rows is zero
+        const int cb = side * 30;
+        for (int c = 0; c < 30; ++c) { row0[cb + c] = 0.0; row1[cb + c] = 0.0; }
+        if (side == 0) { row0[kColR] = row1[kColR] = 0.0; row0[kColRho] = row1[kColRho] = 0.0; }
+        else { row0[kColLd] = row1[kColLd] = 0.0; row0[63] = row1[63] = 0.0; }
+      }
+      __syncthreads();
+      // ---- register-tiled SYRK of the round's rows into the CTA accumulator ----
+      if (tid < 252) {
+        const int grp = tid / 36, tile = tid % 36;
+        const int ti = c_tile_i[tile], tj = c_tile_j[tile];
+        double acc[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) acc[e] = 0.0;
+        const int nrows = 2 * nround;
+        for (int row = grp; row < nrows; row += 7) {
+          const double2* ra = reinterpret_cast<const double2*>(Jt + size_t(row) * kLocalDim + ti * 8);
+          const double2* rb = reinterpret_cast<const double2*>(Jt + size_t(row) * kLocalDim + tj * 8);
+          double av[8], bv[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const double2 x = ra[e], y = rb[e];
+            av[2 * e] = x.x; av[2 * e + 1] = x.y;
+            bv[2 * e] = y.x; bv[2 * e + 1] = y.y;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fma(av[i], bv[j], acc[i * 8 + j]);
+        }
+#pragma unroll
+        for (int e = 0; e < 64; ++e)
+          if (acc[e] != 0.0) atomicAdd(&accs[tile * 64 + e], acc[e]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- cost + flush ----
+  cost_local = warp_sum(cost_local);
+  if (lane == 0) sm.cost_part[warp] = cost_local;
+  __syncthreads();
+  if (tid == 0) {
+    double c = 0;
+#pragma unroll
+    for (int w = 0; w < kVisThreads / 32; ++w) c += sm.cost_part[w];
+    atomicAdd(a.ne.cost, c);
+    if (sm.err) atomicOr(&a.scal->error_flags, 1);
+  }
+  if (FULL) {
+    const int np = a.dims.np;
+    for (int idx = tid; idx < 36 * 64; idx += kVisThreads) {
+      const double val = accs[idx];
+      if (val == 0.0) continue;
+      const int tile = idx >> 6, e = idx & 63;
+      const int la = c_tile_i[tile] * 8 + (e >> 3), lb = c_tile_j[tile] * 8 + (e & 7);
+      if (la > lb || lb > kColR || la >= kColR) continue;
+      const int ga = la < 30 ? 6 * item.wi0 + la : (la < 60 ? 6 * item.wj0 + (la - 30) : a.dims.idx_ld);
+      if (lb == kColR) {
+        atomicAdd(a.ne.gc + ga, val);
+        continue;
+      }
+      const int gb = lb < 30 ? 6 * item.wi0 + lb : (lb < 60 ? 6 * item.wj0 + (lb - 30) : a.dims.idx_ld);
+      const double v = (la != lb && ga == gb) ? 2.0 * val : val;
+      const int g0 = min(ga, gb), g1 = max(ga, gb);
+      atomicAdd(a.ne.A + size_t(g0) * np + g1, v);
+    }
+  }
+}
+
+int launch_visual(const VisualLaunch& l, bool full, cudaStream_t s) {
+  if (l.n_items <= 0) return 0;
+  VisArgs a{l.obs, l.items, l.st, l.ne, l.lm, l.dims, l.sp, l.rig, l.cauchy, l.cmask, l.scal, l.use_tma ? 1 : 0};
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(visual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(visual_smem_bytes()));
+    cudaFuncSetAttribute(visual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(visual_smem_bytes()));
+    attr_set = true;
+  }
+  if (full) visual_kernel<true><<<l.n_items, kVisThreads, visual_smem_bytes(), s>>>(a);
+  else visual_kernel<false><<<l.n_items, kVisThreads, 0, s>>>(a);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: IMU factors.  One thread per sample; the 6x30 Jacobian is staged in shared memory and each
+// thread reduces its own J'J (465 entries, mostly inside one 4-knot block) with fp64 atomics.
+
+struct ImuArgs {
+  ImuObsPtrs obs;
+  StatePtrs st;
+  NormalEqPtrs ne;
+  ProblemDims dims;
+  SplineParams sp;
+  RigParams rig;
+  const uint8_t* cmask;
+  LmScalars* scal;
+};
+
+constexpr int kImuThreads = 64;
+constexpr int kImuCols = 31;  // 24 knot dims + 3 bg + 3 ba + residual column
+
+template <bool FULL>
+__global__ void __launch_bounds__(kImuThreads) imu_kernel(const __grid_constant__ ImuArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  double* Js = reinterpret_cast<double*>(dyn_smem);  // [64][6][31]
+  __shared__ double cost_part[kImuThreads / 32];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.x * kImuThreads + tid;
+  double cost = 0.0;
+  if (n < a.obs.n) {
+    const longlong2 tn = a.obs.t_node[n];
+    const double2 g0 = a.obs.ga[3 * n], g1 = a.obs.ga[3 * n + 1], g2 = a.obs.ga[3 * n + 2];
+    const double gyro[3] = {g0.x, g0.y, g1.x}, accel[3] = {g1.y, g2.x, g2.y};
+    const int node = int(tn.y);
+    double bias[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) bias[c] = a.st.bias[6 * node + c];
+    int32_t s;
+    double u;
+    if (!spline_index(a.sp, tn.x, s, u)) {
+      atomicOr(&a.scal->error_flags, 1);
+    } else {
+      ImuEvalOut o;
+      eval_imu<FULL, kPStride>(a.sp, a.rig, a.st.q, a.st.p, a.st.tab, s, u, gyro, accel, bias, o);
+      cost = o.cost;
+      if (FULL) {
+        double* J = Js + size_t(tid) * 6 * kImuCols;
+        int gdim[30];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int c = 0; c < 6; ++c) gdim[k * 6 + c] = 6 * (s + k) + c;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) gdim[24 + c] = a.dims.idx_bias0 + 6 * node + c;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              J[r * kImuCols + k * 6 + c] = a.cmask[gdim[k * 6 + c]] ? 0.0 : o.Jrot[k][3 * r + c];
+              J[r * kImuCols + k * 6 + 3 + c] = a.cmask[gdim[k * 6 + 3 + c]] ? 0.0 : o.Jpos[k][3 * r + c];
+            }
+#pragma unroll
+          for (int c = 0; c < 6; ++c)
+            J[r * kImuCols + 24 + c] = (c == r && !a.cmask[gdim[24 + c]]) ? a.rig.imu_info[r] : 0.0;
+          J[r * kImuCols + 30] = o.r[r];
+        }
+        const int np = a.dims.np;
+        for (int ca = 0; ca < 30; ++ca) {
+          double ja[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) ja[r] = J[r * kImuCols + ca];
+          double g = 0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) g = fma(ja[r], J[r * kImuCols + 30], g);
+          if (g != 0.0) atomicAdd(a.ne.gc + gdim[ca], g);
+          for (int cb = ca; cb < 30; ++cb) {
+            double h = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) h = fma(ja[r], J[r * kImuCols + cb], h);
+            if (h != 0.0) atomicAdd(a.ne.A + size_t(gdim[ca]) * np + gdim[cb], h);  // gdim is increasing
+          }
+        }
+      }
+    }
+  }
+  cost = warp_sum(cost);
+  if ((tid & 31) == 0) cost_part[tid >> 5] = cost;
+  __syncthreads();
+  if (tid == 0) {
+    double c = 0;
+    for (int w = 0; w < kImuThreads / 32; ++w) c += cost_part[w];
+    if (c != 0.0) atomicAdd(a.ne.cost, c);
+  }
+}
+
+int launch_imu(const ImuLaunch& l, bool full, cudaStream_t s) {
+  if (l.obs.n <= 0) return 0;
+  ImuArgs a{l.obs, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal};
+  const int grid = (l.obs.n + kImuThreads - 1) / kImuThreads;
+  const size_t smem = size_t(kImuThreads) * 6 * kImuCols * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(imu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    attr_set = true;
+  }
+  if (full) imu_kernel<true><<<grid, kImuThreads, smem, s>>>(a);
+  else imu_kernel<false><<<grid, kImuThreads, 0, s>>>(a);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: bias random-walk factors + marginalization prior (one CTA; the n x n J'J of the prior is a
+// constant and is added by a separate elementwise kernel).
+
+struct SmallArgs {
+  BiasFactorPtrs bf;
+  PriorPtrs prior;
+  StatePtrs st;
+  NormalEqPtrs ne;
+  ProblemDims dims;
+  const uint8_t* cmask;
+  LmScalars* scal;
+};
+
+__device__ __forceinline__ const double* block_data(const StatePtrs& st, int type, int index) {
+  switch (type) {
+    case 0: return st.q + 4 * index;
+    case 1: return st.p + kPStride * index;
+    case 2: return st.bias + 6 * index;
+    case 3: return st.bias + 6 * index + 3;
+    case 4: return st.ld;
+    default: return st.rho + index;
+  }
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(256) small_factors_kernel(const __grid_constant__ SmallArgs a) {
+  __shared__ double red[8];
+  const int tid = threadIdx.x;
+  double cost = 0.0;
+  const int np = a.dims.np;
+  // bias factors (trajectory_value_factor.h:45-99)
+  for (int n = tid; n < a.bf.n; n += blockDim.x) {
+    const int2 ij = a.bf.ij[n];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double s = a.bf.sqrt_info[6 * n + k];
+      const double r = s * (a.st.bias[6 * ij.y + k] - a.st.bias[6 * ij.x + k]);
+      cost += 0.5 * r * r;
+      if (FULL) {
+        const int gi = a.dims.idx_bias0 + 6 * ij.x + k, gj = a.dims.idx_bias0 + 6 * ij.y + k;
+        const double ji = a.cmask[gi] ? 0.0 : -s, jj = a.cmask[gj] ? 0.0 : s;
+        atomicAdd(a.ne.gc + gi, ji * r);
+        atomicAdd(a.ne.gc + gj, jj * r);
+        atomicAdd(a.ne.A + size_t(gi) * np + gi, ji * ji);
+        atomicAdd(a.ne.A + size_t(gj) * np + gj, jj * jj);
+        atomicAdd(a.ne.A + size_t(min(gi, gj)) * np + max(gi, gj), ji * jj);
+      }
+    }
+  }
+  // prior (marginalization_factor.cpp:326-373)
+  const int n = a.prior.n;
+  if (n > 0) {
+    for (int b = tid; b < a.prior.n_blocks; b += blockDim.x) {
+      const int type = a.prior.type[b];
+      const double* x = block_data(a.st, type, a.prior.index[b]);
+      const double* x0 = a.prior.x0 + 4 * b;
+      double* dx = a.prior.dx + a.prior.col[b];
+      if (type == 0) {
+        const double n2 = x0[0] * x0[0] + x0[1] * x0[1] + x0[2] * x0[2] + x0[3] * x0[3];
+        const double ax = -x0[0] / n2, ay = -x0[1] / n2, az = -x0[2] / n2, aw = x0[3] / n2;
+        const double bx = x[0], by = x[1], bz = x[2], bw = x[3];
+        const double qx = aw * bx + ax * bw + ay * bz - az * by;
+        const double qy = aw * by + ay * bw + az * bx - ax * bz;
+        const double qz = aw * bz + az * bw + ax * by - ay * bx;
+        const double qw = aw * bw - ax * bx - ay * by - az * bz;
+        const double sg = (qw >= 0) ? 2.0 : -2.0;
+        dx[0] = sg * qx; dx[1] = sg * qy; dx[2] = sg * qz;
+      } else {
+        const int sz = (type == 4 || type == 5) ? 1 : 3;
+        for (int d = 0; d < sz; ++d) dx[d] = x[d] - x0[d];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      double s = a.prior.r[i];
+      const double* Ji = a.prior.J + size_t(i) * n;
+      for (int j = 0; j < n; ++j) s = fma(Ji[j], a.prior.dx[j], s);
+      a.prior.res[i] = s;
+      cost += 0.5 * s * s;
+    }
+    if (FULL) {
+      __syncthreads();
+      for (int j = tid; j < n; j += blockDim.x) {
+        const int g = a.prior.col2g[j];
+        if (g < 0) continue;
+        double s = 0;
+        for (int i = 0; i < n; ++i) s = fma(a.prior.J[size_t(i) * n + j], a.prior.res[i], s);
+        atomicAdd(a.ne.gc + g, s);
+      }
+    }
+  }
+  cost = warp_sum(cost);
+  if ((tid & 31) == 0) red[tid >> 5] = cost;
+  __syncthreads();
+  if (tid == 0) {
+    double c = 0;
+    for (int w = 0; w < 8; ++w) c += red[w];
+    if (c != 0.0) atomicAdd(a.ne.cost, c);
+  }
+}
+
+__global__ void prior_add_jtj_kernel(PriorPtrs pr, double* A, int np) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = pr.n;
+  if (idx >= n * n) return;
+  const int i = idx / n, j = idx % n;
+  if (j < i) return;
+  const int gi = pr.col2g[i], gj = pr.col2g[j];
+  if (gi < 0 || gj < 0) return;
+  const double v = pr.JtJ[idx];
+  if (v == 0.0) return;
+  // distinct prior columns map to distinct camera dims, so no diagonal doubling is needed
+  atomicAdd(A + size_t(min(gi, gj)) * np + max(gi, gj), v);
+}
+
+int launch_small_factors(const SmallFactorsLaunch& l, bool full, cudaStream_t s) {
+  if (l.bf.n <= 0 && l.prior.n <= 0) return 0;
+  SmallArgs a{l.bf, l.prior, l.st, l.ne, l.dims, l.cmask, l.scal};
+  int launches = 1;
+  if (full) small_factors_kernel<true><<<1, 256, 0, s>>>(a);
+  else small_factors_kernel<false><<<1, 256, 0, s>>>(a);
+  if (full && l.prior.n > 0) {
+    const int n2 = l.prior.n * l.prior.n;
+    prior_add_jtj_kernel<<<(n2 + 255) / 256, 256, 0, s>>>(l.prior, l.ne.A, l.dims.np);
+    ++launches;
+  }
+  return launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// probes: per-factor outputs in the C-ABI layout (one thread per factor, both sides in one thread;
+// an independent path from the fused lane-pair kernel, used by the parity tests)
+
+__global__ void probe_image_kernel(VisArgs a, const int32_t* orig_index, int want_jac, double* r, int32_t* sidx,
+                                   double* J) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.obs.n) return;
+  const longlong2 tt = a.obs.t[n];
+  const double2 pi = a.obs.pi[n], pj = a.obs.pj[n];
+  const int4 meta = a.obs.meta[n];
+  const double rho = a.st.rho[meta.z];
+  const int64_t ld_ns = int64_t(*a.st.ld * 1e9);
+  int32_t si, sj;
+  double ui, uj;
+  const int out = orig_index[n];
+  if (!spline_index(a.sp, tt.x + int64_t(meta.x) * ld_ns, si, ui) ||
+      !spline_index(a.sp, tt.y + int64_t(meta.y) * ld_ns, sj, uj)) {
+    atomicOr(&a.scal->error_flags, 1);
+    return;
+  }
+  SideEval ea, eb;
+  if (want_jac) {
+    eval_side<true, kPStride>(a.sp, a.st.q, a.st.p, a.st.tab, si, ui, ea);
+    eval_side<true, kPStride>(a.sp, a.st.q, a.st.p, a.st.tab, sj, uj, eb);
+  } else {
+    eval_side<false, kPStride>(a.sp, a.st.q, a.st.p, a.st.tab, si, ui, ea);
+    eval_side<false, kPStride>(a.sp, a.st.q, a.st.p, a.st.tab, sj, uj, eb);
+  }
+  ImageCommon cm;
+  const double pixy[2] = {pi.x, pi.y}, pjxy[2] = {pj.x, pj.y};
+  image_common(a.rig, pixy, pjxy, rho, ea.R, ea.p, eb.R, eb.p, a.cauchy, cm);
+  atomicAdd(a.ne.cost, cm.cost);
+  if (r) { r[2 * out] = cm.r[0]; r[2 * out + 1] = cm.r[1]; }
+  if (sidx) { sidx[2 * out] = si; sidx[2 * out + 1] = sj; }
+  if (!want_jac || !J) return;
+  double* Jo = J + size_t(out) * 100;
+  double rot[4][6], pos[4][6];
+  image_side_blocks(0, cm, ea, rot, pos);
+  for (int k = 0; k < 4; ++k)
+    for (int e = 0; e < 6; ++e) { Jo[k * 12 + e] = rot[k][e]; Jo[k * 12 + 6 + e] = pos[k][e]; }
+  image_side_blocks(1, cm, eb, rot, pos);
+  for (int k = 0; k < 4; ++k)
+    for (int e = 0; e < 6; ++e) { Jo[48 + k * 12 + e] = rot[k][e]; Jo[48 + k * 12 + 6 + e] = pos[k][e]; }
+  image_jrho(a.rig, cm, ea.R, rho, Jo + 96);
+  image_jld(a.rig, cm, meta.x, meta.y, ea.R, ea.omega, ea.vel, eb.R, eb.omega, eb.vel, Jo + 98);
+}
+
+int launch_probe_image(const VisualLaunch& l, const int32_t* orig_index, bool want_jac, double* r, int32_t* s,
+                       double* J, cudaStream_t st) {
+  if (l.obs.n <= 0) return 0;
+  VisArgs a{l.obs, l.items, l.st, l.ne, l.lm, l.dims, l.sp, l.rig, l.cauchy, l.cmask, l.scal, 0};
+  probe_image_kernel<<<(l.obs.n + 63) / 64, 64, 0, st>>>(a, orig_index, want_jac ? 1 : 0, r, s, J);
+  return 1;
+}
+
+__global__ void probe_imu_kernel(ImuArgs a, int want_jac, double* r, int32_t* sidx, double* J) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.obs.n) return;
+  const longlong2 tn = a.obs.t_node[n];
+  const double2 g0 = a.obs.ga[3 * n], g1 = a.obs.ga[3 * n + 1], g2 = a.obs.ga[3 * n + 2];
+  const double gyro[3] = {g0.x, g0.y, g1.x}, accel[3] = {g1.y, g2.x, g2.y};
+  const int node = int(tn.y);
+  double bias[6];
+  for (int c = 0; c < 6; ++c) bias[c] = a.st.bias[6 * node + c];
+  int32_t s;
+  double u;
+  if (!spline_index(a.sp, tn.x, s, u)) {
+    atomicOr(&a.scal->error_flags, 1);
+    return;
+  }
+  ImuEvalOut o;
+  if (want_jac) eval_imu<true, kPStride>(a.sp, a.rig, a.st.q, a.st.p, a.st.tab, s, u, gyro, accel, bias, o);
+  else eval_imu<false, kPStride>(a.sp, a.rig, a.st.q, a.st.p, a.st.tab, s, u, gyro, accel, bias, o);
+  atomicAdd(a.ne.cost, o.cost);
+  if (r) for (int k = 0; k < 6; ++k) r[6 * n + k] = o.r[k];
+  if (sidx) sidx[n] = s;
+  if (!want_jac || !J) return;
+  double* Jo = J + size_t(n) * 156;
+  for (int k = 0; k < 4; ++k)
+    for (int e = 0; e < 18; ++e) { Jo[k * 36 + e] = o.Jrot[k][e]; Jo[k * 36 + 18 + e] = o.Jpos[k][e]; }
+  for (int k = 0; k < 3; ++k) {
+    Jo[144 + k] = a.rig.imu_info[k]; Jo[147 + k] = 0; Jo[150 + k] = 0; Jo[153 + k] = a.rig.imu_info[3 + k];
+  }
+}
+
+int launch_probe_imu(const ImuLaunch& l, bool want_jac, double* r, int32_t* s, double* J, cudaStream_t st) {
+  if (l.obs.n <= 0) return 0;
+  ImuArgs a{l.obs, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal};
+  probe_imu_kernel<<<(l.obs.n + 63) / 64, 64, 0, st>>>(a, want_jac ? 1 : 0, r, s, J);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// spline query service (Trajectory::poseNs / GetIMUState, spline/trajectory.cpp:27-55)
+
+__global__ void query_kernel(QueryLaunch a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.n) return;
+  int32_t s;
+  double u;
+  if (!spline_index(a.sp, a.t[n], s, u)) {
+    atomicOr(&a.scal->error_flags, 1);
+    return;
+  }
+  SideEval ev;
+  eval_side<true, kPStride>(a.sp, a.st.q, a.st.p, a.st.tab, s, u, ev);
+  if (a.q) {
+    const Q4 q = quat_from_matrix(ev.R);
+    a.q[4 * n] = q.x; a.q[4 * n + 1] = q.y; a.q[4 * n + 2] = q.z; a.q[4 * n + 3] = q.w;
+  }
+  if (a.p) { a.p[3 * n] = ev.p.x; a.p[3 * n + 1] = ev.p.y; a.p[3 * n + 2] = ev.p.z; }
+  if (a.omega) { a.omega[3 * n] = ev.omega.x; a.omega[3 * n + 1] = ev.omega.y; a.omega[3 * n + 2] = ev.omega.z; }
+  if (a.vel) { a.vel[3 * n] = ev.vel.x; a.vel[3 * n + 1] = ev.vel.y; a.vel[3 * n + 2] = ev.vel.z; }
+  if (a.acc) {
+    double c2[4];
+    plain_coeffs<2>(u, a.sp.inv_dt, c2);
+    V3 acc = c2[0] * load_p<kPStride>(a.st.p, s);
+    for (int k = 1; k < 4; ++k) acc = acc + c2[k] * load_p<kPStride>(a.st.p, s + k);
+    a.acc[3 * n] = acc.x; a.acc[3 * n + 1] = acc.y; a.acc[3 * n + 2] = acc.z;
+  }
+}
+
+int launch_query(const QueryLaunch& a, cudaStream_t s) {
+  if (a.n <= 0) return 0;
+  query_kernel<<<(a.n + 127) / 128, 128, 0, s>>>(a);
+  return 1;
+}
+
+}  // namespace ctvio

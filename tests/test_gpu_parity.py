@@ -1,0 +1,214 @@
+"""GPU parity tests: the CUDA engine (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances (north_star): after the same number of LM iterations control-point translation within 1e-5
+relative and rotation within 1e-4 rad; per-factor quantities are fp64 on both sides (different operation
+order / fused multiply-adds / atomics) and are compared at 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+from helpers import get_state, pkg, rot_angle_between, small_window, syn
+
+pytestmark = pytest.mark.gpu
+
+
+def both(oracle_lib, cuda_lib, w, **kw):
+    return pkg.setup_estimator(cuda_lib, w, **kw), pkg.setup_estimator(oracle_lib, w, **kw)
+
+
+def assert_state_parity(g, o, tol_t=1e-5, tol_r=1e-4):
+    qg, pg, bg, rg, lg = get_state(g)
+    qo, po, bo, ro, lo = get_state(o)
+    rel_t = np.abs(pg - po).max() / max(np.abs(po).max(), 1e-12)
+    ang = rot_angle_between(qo, qg).max()
+    assert rel_t < tol_t, rel_t
+    assert ang < tol_r, ang
+    assert np.allclose(bg, bo, rtol=1e-5, atol=1e-8)
+    assert np.allclose(rg, ro, rtol=1e-5, atol=1e-9)
+    assert abs(lg - lo) < 1e-10
+    return rel_t, ang
+
+
+@pytest.mark.parametrize("ld", [0.0, 21e-6, 34.9e-6])
+def test_image_factor_probe_matches_oracle(oracle_lib, cuda_lib, ld):
+    w = small_window(seed=3, n_knots=9, n_kf=5, per_frame=8, fix_ld=False)
+    g, o = both(oracle_lib, cuda_lib, w)
+    g.SetLineDelay(ld); o.SetLineDelay(ld)
+    for cauchy in (0.0, 2.0):
+        rg, sg, Jg, cg = g.EvalImageFactors(True, cauchy)
+        ro, so, Jo, co = o.EvalImageFactors(True, cauchy)
+        assert np.array_equal(sg, so)
+        assert np.allclose(rg, ro, rtol=1e-9, atol=1e-9)
+        assert np.allclose(Jg, Jo, rtol=1e-9, atol=1e-10 * np.abs(Jo).max())
+        assert np.isclose(cg, co, rtol=1e-11)
+    rg, _, _, cg = g.EvalImageFactors(False, 2.0)
+    assert np.allclose(rg, ro, rtol=1e-9, atol=1e-9)
+
+
+def test_imu_factor_probe_matches_oracle(oracle_lib, cuda_lib):
+    w = small_window(seed=8, n_knots=9, n_kf=5, per_frame=4)
+    g, o = both(oracle_lib, cuda_lib, w)
+    b = np.random.default_rng(0).normal(0, 0.02, (g.n_bias, 6))
+    g.SetBiases(b); o.SetBiases(b)
+    rg, sg, Jg, cg = g.EvalImuFactors(True)
+    ro, so, Jo, co = o.EvalImuFactors(True)
+    assert np.array_equal(sg, so)
+    assert np.allclose(rg, ro, rtol=1e-9, atol=1e-8)
+    assert np.allclose(Jg, Jo, rtol=1e-9, atol=1e-10 * np.abs(Jo).max())
+    assert np.isclose(cg, co, rtol=1e-11)
+
+
+def test_query_trajectory_matches_oracle(oracle_lib, cuda_lib):
+    w = small_window(seed=11, n_knots=9)
+    g, o = both(oracle_lib, cuda_lib, w)
+    ts = np.linspace(w.t0_ns + 1, w.t0_ns + (w.n_knots - 3) * w.dt_ns - 1, 257).astype(np.int64)
+    for a, b in zip(g.QueryTrajectory(ts)[1:], o.QueryTrajectory(ts)[1:]):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-9)
+    assert rot_angle_between(g.QueryTrajectory(ts)[0], o.QueryTrajectory(ts)[0]).max() < 1e-12
+    with pytest.raises(pkg.CtvioError):
+        g.QueryTrajectory(np.array([w.t0_ns + (w.n_knots - 3) * w.dt_ns], np.int64))
+
+
+@pytest.mark.parametrize("case", ["small-ldfree", "c1", "c2", "c2-ldfree"])
+def test_normal_equations_match_oracle(oracle_lib, cuda_lib, case):
+    w = {"small-ldfree": lambda: small_window(seed=21, n_knots=8, n_kf=5, per_frame=5, fix_ld=False),
+         "c1": syn.config_c1, "c2": syn.config_c2, "c2-ldfree": lambda: syn.config_c2(fix_ld=False)}[case]()
+    g, o = both(oracle_lib, cuda_lib, w)
+    if not w.fix_ld:
+        g.SetLineDelay(17e-6); o.SetLineDelay(17e-6)
+    Hg, gg, hlg, glg, cg = g.NormalEquations()
+    Ho, go, hlo, glo, co = o.NormalEquations()
+    assert np.isclose(cg, co, rtol=1e-11)
+    assert np.allclose(Hg, Ho, rtol=1e-9, atol=1e-11 * np.abs(Ho).max())
+    assert np.allclose(gg, go, rtol=1e-8, atol=1e-10 * np.abs(go).max())
+    assert np.allclose(hlg, hlo, rtol=1e-10)
+    assert np.allclose(glg, glo, rtol=1e-8, atol=1e-10 * np.abs(glo).max())
+    assert np.isclose(g.EvalCost(), co, rtol=1e-11)
+
+
+@pytest.mark.parametrize("case,iters", [("small", 3), ("c1", 15), ("c2", 1), ("c2", 15), ("c2-ldfree", 15)])
+def test_solve_matches_oracle(oracle_lib, cuda_lib, case, iters):
+    w = {"small": lambda: small_window(seed=33, n_knots=8, n_kf=5, per_frame=5),
+         "c1": syn.config_c1, "c2": syn.config_c2, "c2-ldfree": lambda: syn.config_c2(fix_ld=False)}[case]()
+    g, o = both(oracle_lib, cuda_lib, w)
+    sg = g.Solve(iters)
+    so = o.Solve(iters)
+    assert (sg.iterations, sg.num_successful_steps, sg.num_unsuccessful_steps, sg.termination) == \
+           (so.iterations, so.num_successful_steps, so.num_unsuccessful_steps, so.termination)
+    assert np.isclose(sg.initial_cost, so.initial_cost, rtol=1e-11)
+    assert np.isclose(sg.final_cost, so.final_cost, rtol=1e-8)
+    assert_state_parity(g, o)
+    assert sg.kernel_launches > 0 and sg.device_ms > 0
+
+
+def test_imu_only_with_fixed_knots_matches_oracle(oracle_lib, cuda_lib):
+    """InitTrajectory-style problem (trajectory_manager.cpp:288-315)."""
+    w = syn.config_c2()
+    opt = pkg.make_options(fixed_knot_index=24, lock_wb=True, lock_ab=True, fix_ld=True)
+    q0 = w.q_gt.copy(); p0 = w.p_gt.copy()
+    q0[25:] = q0[24]; p0[25:] = p0[24]
+    m = w.imu_t >= w.t0_ns + 22 * w.dt_ns
+    ests = []
+    for lib in (cuda_lib, oracle_lib):
+        e = pkg.Estimator(lib, pkg.make_config(**w.config_kwargs()))
+        e.SetOptions(opt)
+        e.SetKnots(q0, p0); e.SetBiases(w.bias_gt); e.SetInvDepths(w.rho_gt); e.SetLineDelay(w.ld_gt)
+        e.AddIMUMeasurementAnalytic(w.imu_t[m], w.imu_gyro[m], w.imu_accel[m], w.imu_node[m])
+        ests.append((e, e.Solve(8)))
+    (g, sg), (o, so) = ests
+    assert sg.iterations == so.iterations and sg.termination == so.termination
+    assert np.isclose(sg.final_cost, so.final_cost, rtol=1e-8)
+    assert_state_parity(g, o)
+    q, p = g.GetKnots()
+    assert np.array_equal(q[:25], q0[:25]) and np.array_equal(p[:25], p0[:25])
+
+
+def test_gauge_realign_matches_oracle(oracle_lib, cuda_lib):
+    w = syn.config_c2()
+    g, o = both(oracle_lib, cuda_lib, w)
+    q0 = syn.qrot(w.q_gt[3][None], np.eye(3)).T.copy()
+    t0 = w.p_gt[3].copy()
+    for e in (g, o):
+        e.GaugeRealign(3, q0, t0)
+    assert_state_parity(g, o, tol_t=1e-12, tol_r=1e-12)
+    qg, pg = g.GetKnots()
+    assert np.allclose(pg[3], t0, atol=1e-12)
+    assert np.array_equal(pg[:3], w.p0[:3])
+
+
+def test_save_restore_state(cuda_lib):
+    w = syn.config_c2()
+    g = pkg.setup_estimator(cuda_lib, w)
+    g.SaveState()
+    s1 = g.Solve(5)
+    st1 = get_state(g)
+    g.RestoreState()
+    q, p = g.GetKnots()
+    assert np.array_equal(q, w.q0) and np.array_equal(p, w.p0)
+    s2 = g.Solve(5)
+    assert s1.iterations == s2.iterations and np.isclose(s1.final_cost, s2.final_cost, rtol=1e-9)
+    assert np.allclose(get_state(g)[1], st1[1], rtol=0, atol=1e-9)
+
+
+def test_prior_factor_matches_oracle(oracle_lib, cuda_lib):
+    """Window B of the C3 sequence with a prior produced by the oracle's marginalization of window A."""
+    seq = syn.config_c3_sequence()
+    wa = syn.subwindow(seq, 0, 10)
+    later = int((wa.kf_times[1] - wa.t0_ns) // wa.dt_ns)
+    nowk = int((wa.kf_times[0] - wa.t0_ns) // wa.dt_ns)
+    img_marg = (wa.anchor_frame[wa.lm] == 0).astype(np.int32)
+    imu_marg = (wa.imu_t < wa.kf_times[1]).astype(np.int32)
+    bias_marg = np.zeros(len(wa.bf_i), np.int32); bias_marg[0] = 1
+    opt = pkg.make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER, is_marg_state=True,
+                           ctrl_to_be_opt_now=nowk, ctrl_to_be_opt_later=later)
+    ea = pkg.setup_estimator(oracle_lib, wa, image_marg=img_marg, imu_marg=imu_marg, bias_marg=bias_marg, options=opt)
+    ea.Solve(8)
+    pr = ea.SaveMarginalizationInfo()
+    assert pr is not None
+    isb = (pr.blk_type == pkg.BLK_BG) | (pr.blk_type == pkg.BLK_BA)
+    pr.blk_index[isb] -= 1
+    wb = syn.subwindow(seq, 1, 11)
+    optb = pkg.make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER)
+    g, o = both(oracle_lib, cuda_lib, wb, options=optb)
+    qa, pa = ea.GetKnots()
+    b = np.zeros((11, 6)); b[:10] = ea.GetBiases()[1:]; b[10] = b[9]
+    for e in (g, o):
+        e.SetKnots(qa, pa); e.SetBiases(b); e.SetLineDelay(ea.GetLineDelay())
+        e.AddMarginalizationFactor(pr)
+    assert np.isclose(g.EvalCost(), o.EvalCost(), rtol=1e-10)
+    Hg, gg, _, _, _ = g.NormalEquations()
+    Ho, go, _, _, _ = o.NormalEquations()
+    assert np.allclose(Hg, Ho, rtol=1e-8, atol=1e-10 * np.abs(Ho).max())
+    assert np.allclose(gg, go, rtol=1e-7, atol=1e-9 * np.abs(go).max())
+    sg, so = g.Solve(15), o.Solve(15)
+    assert sg.iterations == so.iterations and sg.termination == so.termination
+    assert np.isclose(sg.final_cost, so.final_cost, rtol=1e-7)
+    assert_state_parity(g, o)
+
+
+def test_c4_full_size_against_oracle_and_properties(oracle_lib, cuda_lib):
+    """BASELINE config 4 at full size: 100 control points, 10 000 landmarks, 100 000 observations."""
+    w = syn.config_c4()
+    assert w.n_obs == 100_000 and len(w.rho0) == 10_000 and w.n_knots == 100
+    g, o = both(oracle_lib, cuda_lib, w)
+    cg, co = g.EvalCost(), o.EvalCost()
+    assert np.isclose(cg, co, rtol=1e-10)
+    sg = g.Solve(4)
+    so = o.Solve(4)
+    assert sg.iterations == so.iterations and sg.num_successful_steps == so.num_successful_steps
+    assert np.isclose(sg.final_cost, so.final_cost, rtol=1e-7)
+    assert_state_parity(g, o)
+    # size-independent properties: monotone cost, summary consistent with a fresh evaluation, idempotent re-solve
+    assert sg.final_cost < sg.initial_cost
+    assert np.isclose(g.EvalCost(), sg.final_cost, rtol=1e-10)
+    H, gc, hl, gl, _ = g.NormalEquations()
+    assert np.allclose(H, H.T) and (np.diag(H) >= 0).all() and (hl >= 0).all()
+
+
+def test_time_outside_window_is_reported(cuda_lib):
+    w = small_window(seed=5, n_knots=8, n_kf=5, per_frame=4, fix_ld=False)
+    g = pkg.setup_estimator(cuda_lib, w)
+    g.SetLineDelay(60e-6)  # 1023 rows * 60 us = 61 ms > padding: evaluation leaves its 5-knot window
+    with pytest.raises(pkg.CtvioError) as ei:
+        g.EvalCost()
+    assert "-6" in str(ei.value)
