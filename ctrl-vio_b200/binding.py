@@ -100,7 +100,7 @@ ABI_SYMBOLS = [
     "solve", "gauge_realign", "marginalize", "get_prior", "adopt_prior",
     "save_state", "restore_state",
     "eval_image_factors", "eval_imu_factors", "eval_cost", "normal_equations",
-    "query_trajectory", "nccl_unique_id", "comm_init",
+    "query_trajectory", "profile_kernels", "nccl_unique_id", "comm_init",
 ]
 
 
@@ -356,6 +356,12 @@ class Estimator:
         q = np.zeros((n, 4)); p = np.zeros((n, 3)); w = np.zeros((n, 3)); v = np.zeros((n, 3)); a = np.zeros((n, 3))
         self.lib.call("query_trajectory", self.h, C.c_int32(n), _lp(t), _dp(q), _dp(p), _dp(w), _dp(v), _dp(a))
         return q, p, w, v, a
+
+    def ProfileKernels(self, reps=20, flush_l2=True):
+        out = np.zeros(8)
+        self.lib.call("profile_kernels", self.h, C.c_int32(reps), C.c_int32(int(flush_l2)), _dp(out))
+        names = ["visual", "imu", "small", "reduced_schur", "cholesky_solve", "step_vectors", "apply_table", "visual_cost"]
+        return dict(zip(names, out.tolist()))
 
     # --- multi-GPU -----------------------------------------------------------------
     def NcclUniqueId(self) -> bytes:

@@ -78,8 +78,9 @@ struct HostBias { int32_t i, j; double s[6]; int32_t marg; };
 struct ctvio_engine {
   ctvio_config cfg;
   ctvio_options opt;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: IMU / bias / prior factors run beside the visual kernel
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  bool masks_dirty = true;
   SplineParams sp;
   RigParams rig;
   bool use_tma = true;
@@ -225,14 +226,19 @@ int prepare(ctvio_engine* e) {
       hm[k] = make_int4(o.rowi, o.rowj, o.lm, o.marg);
     }
     // work items: chunks of one group; chunk size adapts so that small problems still spread over the SMs
-    int chunk = 512;
-    if (n < 148 * 512) chunk = std::max(kVisObsPerRound, ((n / 148 + kVisObsPerRound - 1) / kVisObsPerRound) * kVisObsPerRound);
+    // (a group is split into equal chunks of at most `cap` observations, cap a multiple of the 128-observation round)
+    int cap = 512;
+    if (n < 148 * 512) cap = std::max(kVisObsPerRound, ((n / 148 + kVisObsPerRound - 1) / kVisObsPerRound) * kVisObsPerRound);
     std::vector<VisualItem> items;
     for (int k = 0; k < n;) {
       const int a = e->img_order[k];
       int end = k;
       while (end < n && wi0[e->img_order[end]] == wi0[a] && wj0[e->img_order[end]] == wj0[a]) ++end;
-      for (int s = k; s < end; s += chunk) items.push_back(VisualItem{s, std::min(chunk, end - s), wi0[a], wj0[a]});
+      const int cnt = end - k;
+      // a few stragglers beyond a full round are cheaper as their own small item than as an extra round
+      const int nchunks = (cnt + cap - 1) / cap;
+      const int per = (cnt + nchunks - 1) / nchunks;
+      for (int s = k; s < end; s += per) items.push_back(VisualItem{s, std::min(per, end - s), wi0[a], wj0[a]});
       k = end;
     }
     e->n_items = int(items.size());
@@ -323,7 +329,7 @@ int prepare(ctvio_engine* e) {
     e->npad = ((d.np + kCholNB - 1) / kCholNB) * kCholNB;
     CUDA_OK(e->d_M.reserve(size_t(e->npad) * e->npad));
     CUDA_OK(e->d_Linv.reserve(size_t(e->npad) * kCholNB));
-    CUDA_OK(e->d_rhs.reserve(e->npad));
+    CUDA_OK(e->d_rhs.reserve(2 * size_t(e->npad)));  // rhs | forward-solved vector
     CUDA_OK(e->d_y.reserve(e->npad));
     CUDA_OK(e->d_sc.reserve(np));
     CUDA_OK(e->d_sl.reserve(e->nL));
@@ -334,7 +340,7 @@ int prepare(ctvio_engine* e) {
     e->prior_dirty = true;
   }
   // ---- masks (depend on options + structure) ----
-  {
+  if (e->structure_dirty || e->masks_dirty) {
     e->h_cmask.assign(d.np, 0);
     for (int k = 0; k < e->nK; ++k)
       if (e->opt.lock_traj || (e->opt.fixed_knot_index >= 0 && k <= e->opt.fixed_knot_index))
@@ -375,6 +381,7 @@ int prepare(ctvio_engine* e) {
     for (int l = 0; l < e->nL; ++l) e->h_active[d.np + l] = touched[d.np + l];
     CUDA_OK(e->d_cmask.upload(e->h_cmask, st));
     CUDA_OK(e->d_active.upload(e->h_active, st));
+    e->masks_dirty = false;
   }
   e->structure_dirty = false;
   if (e->prior_dirty) {
@@ -491,9 +498,17 @@ void evaluate(ctvio_engine* e, int xb, int nb, bool full) {
   cudaStream_t st = e->stream;
   if (full) cudaMemsetAsync(e->ne_slab[nb].p, 0, e->ne_slab_len * sizeof(double), st);
   cudaMemsetAsync(&e->d_scal.p->cost_eval, 0, sizeof(double), st);
+  // fork: the (latency-bound) IMU + bias + prior kernels overlap the visual kernel on a second stream
+  const bool fork = !e->imu.empty() || !e->biasf.empty() || e->prior.n > 0;
+  if (fork) {
+    cudaEventRecord(e->ev_fork, st);
+    cudaStreamWaitEvent(e->stream2, e->ev_fork, 0);
+    e->launches += launch_imu(imu_launch(e, xb, nb), full, e->stream2);
+    e->launches += launch_small_factors(small_launch(e, xb, nb), full, e->stream2);
+    cudaEventRecord(e->ev_join, e->stream2);
+  }
   e->launches += launch_visual(visual_launch(e, xb, nb, e->cfg.cauchy_solve), full, st);
-  e->launches += launch_imu(imu_launch(e, xb, nb), full, st);
-  e->launches += launch_small_factors(small_launch(e, xb, nb), full, st);
+  if (fork) cudaStreamWaitEvent(st, e->ev_join, 0);
 }
 
 int read_scalars(ctvio_engine* e) {
@@ -557,7 +572,10 @@ int ctvio_create(const ctvio_config* cfg, ctvio_handle* out) {
   const char* no_tma = std::getenv("CTVIO_NO_TMA");
   e->use_tma = !(no_tma && no_tma[0] == '1');
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost(&e->h_scal, sizeof(LmScalars)) != cudaSuccess || e->d_scal.reserve(1) != cudaSuccess) {
     delete e;
     return fail(CTVIO_ERR_CUDA, "could not create stream / events / scalar block");
@@ -575,6 +593,9 @@ int ctvio_destroy(ctvio_handle e) {
   if (e->h_scal) cudaFreeHost(e->h_scal);
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
+  cudaEventDestroy(e->ev_fork);
+  cudaEventDestroy(e->ev_join);
+  cudaStreamDestroy(e->stream2);
   cudaStreamDestroy(e->stream);
   delete e;
   return CTVIO_OK;
@@ -583,6 +604,7 @@ int ctvio_destroy(ctvio_handle e) {
 int ctvio_set_options(ctvio_handle e, const ctvio_options* o) {
   if (!e || !o) return fail(CTVIO_ERR_INVALID, "null argument");
   e->opt = *o;
+  e->masks_dirty = true;
   e->prior_dirty = true;  // col2g depends on the constant mask
   return CTVIO_OK;
 }
@@ -721,6 +743,7 @@ int ctvio_set_prior(ctvio_handle e, int32_t n, const double* J, const double* r,
   if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
   e->prior = ctvio::PriorHost();
   e->prior_dirty = true;
+  e->masks_dirty = true;  // the prior's blocks count as touched parameters
   if (n <= 0) return CTVIO_OK;
   if (!J || !r || nb <= 0 || !type || !index || !col || !x0) return fail(CTVIO_ERR_INVALID, "null argument");
   e->prior.n = n;
@@ -1086,6 +1109,82 @@ int ctvio_query_trajectory(ctvio_handle e, int32_t n, const int64_t* t, double* 
   return CTVIO_OK;
 }
 
+int ctvio_profile_kernels(ctvio_handle e, int32_t reps, int32_t flush_l2, double* out) {
+  if (!e || !out || reps <= 0) return fail(CTVIO_ERR_INVALID, "bad argument");
+  cudaSetDevice(e->cfg.device);
+  int rc = prepare(e);
+  if (rc) return rc;
+  ensure_table(e);
+  cudaStream_t st = e->stream;
+  const int cur = e->cur, cand = cur ^ 1;
+  DevBuf<unsigned char> flush;
+  const size_t flush_bytes = size_t(256) << 20;
+  if (flush_l2) CUDA_OK(flush.reserve(flush_bytes));
+  // a valid linearisation + step so that every stage has meaningful inputs
+  evaluate(e, cur, cur, true);
+  LinearLaunch lin = linear_launch(e, cur);
+  launch_jacobi_scale(lin, st);
+  launch_lm_step(lin, 1e4, st);
+  rc = read_scalars(e);
+  if (rc) return rc;
+  ApplyLaunch ap;
+  ap.dims = e->dims();
+  ap.x = e->x[cur].ptrs(); ap.xc = e->x[cand].ptrs();
+  ap.dc = e->d_dc.p; ap.dl = e->d_dl.p; ap.alpha = 1.0; ap.active = e->d_active.p;
+  ap.clamp_ld = e->opt.fix_ld ? 0 : 1; ap.ld_lower = e->opt.ld_lower; ap.ld_upper = e->opt.ld_upper;
+  ap.scal = e->d_scal.p;
+  auto time_stage = [&](int stage, double* ms_out) -> int {
+    double total = 0;
+    for (int it = -3; it < reps; ++it) {
+      if (flush_l2) cudaMemsetAsync(flush.p, it & 0xff, flush_bytes, st);
+      if (stage == 0 || stage == 1 || stage == 2)
+        cudaMemsetAsync(e->ne_slab[cur].p, 0, e->ne_slab_len * sizeof(double), st);
+      cudaEventRecord(e->ev0, st);
+      switch (stage) {
+        case 0: launch_visual(visual_launch(e, cur, cur, e->cfg.cauchy_solve), true, st); break;
+        case 1: launch_imu(imu_launch(e, cur, cur), true, st); break;
+        case 2: launch_small_factors(small_launch(e, cur, cur), true, st); break;
+        case 3: launch_reduced_system(lin, 1e4, st); break;
+        case 4: launch_factor_solve(lin, st); break;
+        case 5: launch_step_vectors(lin, st); break;
+        case 6: launch_apply_step(ap, st); break;
+        default: launch_visual(visual_launch(e, cur, cur, e->cfg.cauchy_solve), false, st); break;
+      }
+      cudaEventRecord(e->ev1, st);
+      if (cudaEventSynchronize(e->ev1) != cudaSuccess) return fail(CTVIO_ERR_CUDA, "kernel failed while profiling");
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+      if (it >= 0) total += ms;
+    }
+    *ms_out = total / reps;
+    return CTVIO_OK;
+  };
+  // stage order keeps inputs valid: 3 (reduced system) must precede 4 (it is factored in place)
+  for (int stage : {0, 1, 2, 7}) { rc = time_stage(stage, &out[stage]); if (rc) return rc; }
+  evaluate(e, cur, cur, true);  // restore a complete set of normal equations
+  {
+    double total3 = 0, total4 = 0, total5 = 0;
+    for (int it = -3; it < reps; ++it) {
+      float ms;
+      if (flush_l2) cudaMemsetAsync(flush.p, it & 0xff, flush_bytes, st);
+      cudaEventRecord(e->ev0, st); launch_reduced_system(lin, 1e4, st); cudaEventRecord(e->ev1, st);
+      cudaEventSynchronize(e->ev1); cudaEventElapsedTime(&ms, e->ev0, e->ev1); if (it >= 0) total3 += ms;
+      if (flush_l2) cudaMemsetAsync(flush.p, it & 0xff, flush_bytes, st);
+      cudaEventRecord(e->ev0, st); launch_factor_solve(lin, st); cudaEventRecord(e->ev1, st);
+      cudaEventSynchronize(e->ev1); cudaEventElapsedTime(&ms, e->ev0, e->ev1); if (it >= 0) total4 += ms;
+      if (flush_l2) cudaMemsetAsync(flush.p, it & 0xff, flush_bytes, st);
+      cudaEventRecord(e->ev0, st); launch_step_vectors(lin, st); cudaEventRecord(e->ev1, st);
+      cudaEventSynchronize(e->ev1); cudaEventElapsedTime(&ms, e->ev0, e->ev1); if (it >= 0) total5 += ms;
+    }
+    out[3] = total3 / reps; out[4] = total4 / reps; out[5] = total5 / reps;
+  }
+  rc = time_stage(6, &out[6]);
+  if (rc) return rc;
+  cudaMemsetAsync(&e->d_scal.p->error_flags, 0, sizeof(int32_t), st);
+  CUDA_OK(cudaStreamSynchronize(st));
+  return CTVIO_OK;
+}
+
 // ---- marginalization (K7), see marginalize.cu ---------------------------------------------------
 int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
   if (!e || !n_out || !nb_out) return fail(CTVIO_ERR_INVALID, "null argument");
@@ -1109,6 +1208,7 @@ int ctvio_adopt_prior(ctvio_handle e) {
   if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
   e->prior = e->new_prior;
   e->prior_dirty = true;
+  e->masks_dirty = true;
   return CTVIO_OK;
 }
 

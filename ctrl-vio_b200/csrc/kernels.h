@@ -12,6 +12,8 @@ constexpr int kPStride = 4;        // knot positions are stored [N][4] (32 B) so
 constexpr int kVisThreads = 256;   // visual kernel CTA: 128 lane pairs
 constexpr int kVisObsPerRound = 128;
 constexpr int kLocalDim = 64;      // padded local Jacobian width of one frame-pair group
+constexpr int kRowStride = 66;     // shared-memory stride of one Jacobian row (doubles); 16-B aligned
+constexpr int kObsStride = 2 * kRowStride + 2;  // stride of one observation's 2 rows: 268 words -> 2-way store conflicts instead of 16-way
 constexpr int kWinKnots = 5;       // knots of a padded evaluation window (se3_spline.h:463-503 with 39 ms padding)
 constexpr int kColLd = 60, kColR = 61, kColRho = 62;
 constexpr int kSchurMaxDim = 192;  // widest landmark-batch knot range handled by the tiled Schur kernel
@@ -185,6 +187,10 @@ struct LinearLaunch {
 int launch_jacobi_scale(const LinearLaunch& a, cudaStream_t s);
 // builds the damped, scaled reduced system, factors it, solves and back-substitutes: dc, dl, gd, dHd
 int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s);
+// the three stages of launch_lm_step, separately launchable for measurement
+int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s);
+int launch_factor_solve(const LinearLaunch& a, cudaStream_t s);
+int launch_step_vectors(const LinearLaunch& a, cudaStream_t s);
 int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld, double ld_lower, double ld_upper,
                          cudaStream_t s);
 

@@ -177,166 +177,7 @@ __global__ void schur_wide_kernel(LinearLaunch a, double radius) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K5: blocked Cholesky, lower triangle of M, NB = 64
-constexpr size_t kCholSmem = 2 * size_t(kCholNB) * (kCholNB + 1) * sizeof(double);  // > 48 KB: dynamic
-
-__global__ void __launch_bounds__(256) chol_panel_kernel(double* M, int npad, int k, double* Linv, LmScalars* scal) {
-  extern __shared__ __align__(16) unsigned char chol_smem[];
-  double (*D)[kCholNB + 1] = reinterpret_cast<double (*)[kCholNB + 1]>(chol_smem);
-  double (*X)[kCholNB + 1] = D + kCholNB;
-  const int tid = threadIdx.x;
-  const int d0 = k * kCholNB;
-  for (int e = tid; e < kCholNB * kCholNB; e += 256) {
-    const int i = e / kCholNB, j = e % kCholNB;
-    D[i][j] = M[size_t(d0 + i) * npad + d0 + j];
-  }
-  __syncthreads();
-  // every CTA factors the diagonal block redundantly (64^3/3 flops) instead of waiting for another kernel
-  for (int j = 0; j < kCholNB; ++j) {
-    if (tid == 0) {
-      double d = D[j][j];
-      if (!(d > 0.0) || !isfinite(d)) {
-        if (blockIdx.x == 0) scal->chol_fail = 1;
-        d = 1.0;
-      }
-      D[j][j] = sqrt(d);
-    }
-    __syncthreads();
-    if (tid > j && tid < kCholNB) D[tid][j] /= D[j][j];
-    __syncthreads();
-    // trailing update of the block: rows i > j, cols j < c <= i
-    for (int e = tid; e < kCholNB * kCholNB; e += 256) {
-      const int i = e / kCholNB, c = e % kCholNB;
-      if (i > j && c > j && c <= i) D[i][c] -= D[i][j] * D[c][j];
-    }
-    __syncthreads();
-  }
-  if (blockIdx.x == 0) {
-    // The factored diagonal block is NOT written back into M: the other CTAs of this launch read the
-    // unfactored block from M concurrently, and every later consumer (block triangular solves) only
-    // needs its inverse.  Inverse of the lower-triangular block: column c by forward substitution
-    if (tid < kCholNB) {
-      const int c = tid;
-      for (int i = 0; i < kCholNB; ++i) {
-        double s = (i == c) ? 1.0 : 0.0;
-        for (int m = c; m < i; ++m) s -= D[i][m] * X[m][c];
-        X[i][c] = (i < c) ? 0.0 : s / D[i][i];
-      }
-    }
-    __syncthreads();
-    double* Li = Linv + size_t(k) * kCholNB * kCholNB;
-    for (int e = tid; e < kCholNB * kCholNB; e += 256) Li[e] = X[e / kCholNB][e % kCholNB];
-  } else {
-    // panel slab: X L^T = A  for the 64 rows of slab blockIdx.x below the diagonal block
-    const int r0 = (k + blockIdx.x) * kCholNB;
-    for (int e = tid; e < kCholNB * kCholNB; e += 256) {
-      const int i = e / kCholNB, j = e % kCholNB;
-      X[i][j] = M[size_t(r0 + i) * npad + d0 + j];
-    }
-    __syncthreads();
-    if (tid < kCholNB) {
-      const int i = tid;
-      for (int j = 0; j < kCholNB; ++j) {
-        double s = X[i][j];
-        for (int c = 0; c < j; ++c) s -= X[i][c] * D[j][c];
-        X[i][j] = s / D[j][j];
-      }
-    }
-    __syncthreads();
-    for (int e = tid; e < kCholNB * kCholNB; e += 256) {
-      const int i = e / kCholNB, j = e % kCholNB;
-      M[size_t(r0 + i) * npad + d0 + j] = X[i][j];
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) chol_update_kernel(double* M, int npad, int k) {
-  extern __shared__ __align__(16) unsigned char chol_smem[];
-  double (*Pi)[kCholNB + 1] = reinterpret_cast<double (*)[kCholNB + 1]>(chol_smem);
-  double (*Pj)[kCholNB + 1] = Pi + kCholNB;
-  // decode lower-triangular tile (bi >= bj) of the trailing matrix
-  int bi = 0, rem = blockIdx.x;
-  while (rem > bi) { rem -= bi + 1; ++bi; }
-  const int bj = rem;
-  const int tid = threadIdx.x;
-  const int ri = (k + 1 + bi) * kCholNB, rj = (k + 1 + bj) * kCholNB, c0 = k * kCholNB;
-  for (int e = tid; e < kCholNB * kCholNB; e += 256) {
-    const int i = e / kCholNB, j = e % kCholNB;
-    Pi[i][j] = M[size_t(ri + i) * npad + c0 + j];
-    Pj[i][j] = M[size_t(rj + i) * npad + c0 + j];
-  }
-  __syncthreads();
-  const int ty = tid / 16, tx = tid % 16;
-  double acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int c = 0; c < kCholNB; ++c) {
-    double av[4], bv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { av[i] = Pi[4 * ty + i][c]; bv[i] = Pj[4 * tx + i][c]; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) M[size_t(ri + 4 * ty + i) * npad + rj + 4 * tx + j] -= acc[i][j];
-}
-
-// block forward/backward substitution with the pre-inverted diagonal blocks; single CTA
-__global__ void __launch_bounds__(1024) tri_solve_kernel(const double* M, const double* Linv, const double* rhs,
-                                                         double* y, int npad) {
-  __shared__ double xk[kCholNB];
-  __shared__ double part[16][kCholNB];
-  const int tid = threadIdx.x;
-  const int nb = npad / kCholNB;
-  for (int i = tid; i < npad; i += 1024) y[i] = rhs[i];
-  __syncthreads();
-  for (int k = 0; k < nb; ++k) {
-    const double* Li = Linv + size_t(k) * kCholNB * kCholNB;
-    if (tid < kCholNB) {
-      double s = 0;
-      for (int c = 0; c <= tid; ++c) s = fma(Li[tid * kCholNB + c], y[k * kCholNB + c], s);
-      xk[tid] = s;
-    }
-    __syncthreads();
-    if (tid < kCholNB) y[k * kCholNB + tid] = xk[tid];
-    for (int r = (k + 1) * kCholNB + tid; r < npad; r += 1024) {
-      const double* Lr = M + size_t(r) * npad + k * kCholNB;
-      double s = 0;
-#pragma unroll 8
-      for (int c = 0; c < kCholNB; ++c) s = fma(Lr[c], xk[c], s);
-      y[r] -= s;
-    }
-    __syncthreads();
-  }
-  for (int k = nb - 1; k >= 0; --k) {
-    const int c = tid & 63, pt = tid >> 6;
-    double s = 0;
-    for (int r = (k + 1) * kCholNB + pt; r < npad; r += 16) s = fma(M[size_t(r) * npad + k * kCholNB + c], y[r], s);
-    part[pt][c] = s;
-    __syncthreads();
-    if (tid < kCholNB) {
-      double t = y[k * kCholNB + tid];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) t -= part[q][tid];
-      xk[tid] = t;
-    }
-    __syncthreads();
-    const double* Li = Linv + size_t(k) * kCholNB * kCholNB;
-    if (tid < kCholNB) {
-      double t = 0;
-      for (int r = tid; r < kCholNB; ++r) t = fma(Li[r * kCholNB + tid], xk[r], t);  // Linv^T
-      y[k * kCholNB + tid] = t;
-    }
-    __syncthreads();
-  }
-}
+// K5 (blocked Cholesky + triangular solves) lives in chol_coop.cu
 
 // ------------------------------------------------------------------------------------------------
 // K6
@@ -376,41 +217,44 @@ __global__ void __launch_bounds__(256) camera_step_kernel(LinearLaunch a) {
   }
 }
 
-// landmark back-substitution + landmark parts of gd / dHd.  Reads y (not dc) so that it can run
-// concurrently with camera_step_kernel.
+// landmark back-substitution + landmark parts of gd / dHd: one WARP per landmark (coalesced reads of
+// its coupling row), reads y (not dc) so that it can run concurrently with camera_step_kernel.
 __global__ void __launch_bounds__(256) landmark_step_kernel(LinearLaunch a) {
   __shared__ double red[3][8];
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = blockIdx.x * 8 + warp;
   double gd = 0, dHd = 0, dmax = 0;
   if (l < a.dims.nL) {
     const double sl = a.sl[l];
     const int lo = a.lm.lo[l], hi = a.lm.hi[l], ild = a.dims.idx_ld;
     const double* Wl = a.ne.W + a.lm.woff[l] - lo;
     double wy = 0;  // W_l . (sc o y)
-    for (int g = lo; g < hi; ++g) wy = fma(Wl[g], a.cmask[g] ? 0.0 : a.sc[g] * a.y[g], wy);
-    wy = fma(a.ne.wld[l], a.cmask[ild] ? 0.0 : a.sc[ild] * a.y[ild], wy);
-    const double hh = a.hh[l];
-    const double yl = hh > 0.0 ? (sl * a.ne.gl[l] - sl * wy) / hh : 0.0;
-    const double d = -sl * yl;
-    a.dl[l] = d;
-    gd = a.ne.gl[l] * d;
-    dHd = 2.0 * d * (-wy) + a.ne.hl[l] * d * d;  // W_l . dc = -wy
-    dmax = fabs(d);
-    if (!isfinite(d)) a.scal->chol_fail = 1;
+    for (int g = lo + lane; g < hi; g += 32) wy = fma(Wl[g], a.cmask[g] ? 0.0 : a.sc[g] * a.y[g], wy);
+    wy = warp_sum_d(wy);
+    if (lane == 0) {
+      wy = fma(a.ne.wld[l], a.cmask[ild] ? 0.0 : a.sc[ild] * a.y[ild], wy);
+      const double hh = a.hh[l];
+      const double yl = hh > 0.0 ? (sl * a.ne.gl[l] - sl * wy) / hh : 0.0;
+      const double d = -sl * yl;
+      a.dl[l] = d;
+      gd = a.ne.gl[l] * d;
+      dHd = 2.0 * d * (-wy) + a.ne.hl[l] * d * d;  // W_l . dc = -wy
+      dmax = fabs(d);
+      if (!isfinite(d)) a.scal->chol_fail = 1;
+    }
   }
-  gd = warp_sum_d(gd); dHd = warp_sum_d(dHd); dmax = warp_max_d(dmax);
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = gd; red[1][threadIdx.x >> 5] = dHd; red[2][threadIdx.x >> 5] = dmax; }
+  if (lane == 0) { red[0][warp] = gd; red[1][warp] = dHd; red[2][warp] = dmax; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double g = 0, h = 0, m = 0;
     for (int w = 0; w < 8; ++w) { g += red[0][w]; h += red[1][w]; m = fmax(m, red[2][w]); }
-    atomicAdd(&a.scal->gd, g);
-    atomicAdd(&a.scal->dHd, h);
-    atomic_max_pos(&a.scal->dir_max, m);
+    if (g != 0.0) atomicAdd(&a.scal->gd, g);
+    if (h != 0.0) atomicAdd(&a.scal->dHd, h);
+    if (m > 0.0) atomic_max_pos(&a.scal->dir_max, m);
   }
 }
 
-int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s) {
+int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s) {
   int launches = 0;
   const size_t total = size_t(a.npad) * a.npad;
   scale_copy_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(a, radius);
@@ -429,31 +273,22 @@ int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s) {
     schur_wide_kernel<<<(a.n_wide * 32 + 255) / 256, 256, 0, s>>>(a, radius);
     ++launches;
   }
-  const int nb = a.npad / kCholNB;
-  static bool chol_attr_set = false;
-  if (!chol_attr_set) {
-    cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCholSmem));
-    cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCholSmem));
-    chol_attr_set = true;
-  }
-  for (int k = 0; k < nb; ++k) {
-    chol_panel_kernel<<<nb - k, 256, kCholSmem, s>>>(a.M, a.npad, k, a.Linv, a.scal);
-    ++launches;
-    const int T = nb - k - 1;
-    if (T > 0) {
-      chol_update_kernel<<<T * (T + 1) / 2, 256, kCholSmem, s>>>(a.M, a.npad, k);
-      ++launches;
-    }
-  }
-  tri_solve_kernel<<<1, 1024, 0, s>>>(a.M, a.Linv, a.rhs, a.y, a.npad);
-  ++launches;
+  return launches;
+}
+
+int launch_step_vectors(const LinearLaunch& a, cudaStream_t s) {
+  int launches = 0;
   camera_step_kernel<<<(a.dims.np + 7) / 8, 256, 0, s>>>(a);
   ++launches;
   if (a.dims.nL > 0) {
-    landmark_step_kernel<<<(a.dims.nL + 255) / 256, 256, 0, s>>>(a);
+    landmark_step_kernel<<<(a.dims.nL + 7) / 8, 256, 0, s>>>(a);
     ++launches;
   }
   return launches;
+}
+
+int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s) {
+  return launch_reduced_system(a, radius, s) + launch_factor_solve(a, s) + launch_step_vectors(a, s);
 }
 
 // max-norm of the (bounds-projected) gradient over the active parameters

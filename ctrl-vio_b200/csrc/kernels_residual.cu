@@ -118,14 +118,52 @@ __constant__ uint8_t c_tile_j[36] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 2, 3, 4, 5, 6, 7
                                      5, 6, 7, 3, 4, 5, 6, 7, 4, 5, 6, 7, 5, 6, 7, 6, 7, 7};
 
 size_t visual_smem_bytes() {
-  return size_t(kVisObsPerRound) * 2 * kLocalDim * sizeof(double) + size_t(36) * 64 * sizeof(double);
+  return size_t(kVisObsPerRound) * kObsStride * sizeof(double) + size_t(36) * 64 * sizeof(double);
+}
+
+// Register-tiled SYRK of one round's Jacobian rows into the CTA accumulator (own register allocation:
+// kept out of line so its 64 accumulators do not spill the evaluation phase).
+// 252 threads = 7 row groups x 36 upper tiles (8x8).  The 7 partial tiles are added into the shared
+// accumulator one group at a time (shared-memory fp64 atomics are CAS loops on sm_100a).
+__device__ __noinline__ void syrk_round(const double* Jt, double* accs, int nround, int tid) {
+  const int grp = tid / 36, tile = tid % 36;
+  double acc[64];
+  if (tid < 252) {
+    const int ti = c_tile_i[tile], tj = c_tile_j[tile];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) acc[e] = 0.0;
+    const int nrows = 2 * nround;
+    for (int row = grp; row < nrows; row += 7) {
+      const double* rp = Jt + size_t(row >> 1) * kObsStride + (row & 1) * kRowStride;
+      const double2* ra = reinterpret_cast<const double2*>(rp + ti * 8);
+      const double2* rb = reinterpret_cast<const double2*>(rp + tj * 8);
+      double av[8], bv[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double2 x = ra[e], y = rb[e];
+        av[2 * e] = x.x; av[2 * e + 1] = x.y;
+        bv[2 * e] = y.x; bv[2 * e + 1] = y.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fma(av[i], bv[j], acc[i * 8 + j]);
+    }
+  }
+  for (int g = 0; g < 7; ++g) {
+    if (tid < 252 && grp == g) {
+#pragma unroll
+      for (int e = 0; e < 64; ++e) accs[tile * 64 + e] += acc[e];
+    }
+    __syncthreads();
+  }
 }
 
 template <bool FULL>
 __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_constant__ VisArgs a) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
-  double* Jt = reinterpret_cast<double*>(dyn_smem);                 // [128][2][64]
-  double* accs = Jt + size_t(kVisObsPerRound) * 2 * kLocalDim;      // [36][64]
+  double* Jt = reinterpret_cast<double*>(dyn_smem);                 // [128 obs][2 rows][64 cols], padded strides
+  double* accs = Jt + size_t(kVisObsPerRound) * kObsStride;         // [36][64]
   __shared__ VisStatic sm;
 
   const int tid = threadIdx.x;
@@ -193,8 +231,8 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
     const int nround = min(kVisObsPerRound, item.count - base);
     const int ol = tid >> 1;  // observation slot of this lane pair
     const bool active = ol < nround;
-    double* row0 = Jt + size_t(ol) * 2 * kLocalDim;
-    double* row1 = row0 + kLocalDim;
+    double* row0 = Jt + size_t(ol) * kObsStride;
+    double* row1 = row0 + kRowStride;
     bool valid = false;
     const unsigned m_act = __ballot_sync(0xffffffffu, active);  // lane pairs are active together
     if (active) {
@@ -216,8 +254,8 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
       if (!ok_both) {
         atomicOr(&sm.err, 1);
       } else {
-        SideEval ev;
-        eval_side<FULL, kPStride>(a.sp, &sm.q[side][0][0], &sm.p[side][0][0], sm.tab[side], slot, u, ev);
+        PoseStage ev;
+        pose_stage<FULL, kPStride>(a.sp, &sm.q[side][0][0], &sm.p[side][0][0], sm.tab[side], slot, u, ev);
         // exchange pose (and velocities) with the partner lane
         M3 Ro;
         V3 po, omo, vo;
@@ -239,35 +277,39 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
         image_common(a.rig, pixy, pjxy, rho, R_i, p_i, R_j, p_j, a.cauchy, cm);
         if (side == 0) cost_local += cm.cost;
         if (FULL) {
-          double rot[4][6], pos[4][6], jrho[2];
-          image_side_blocks(side, cm, ev, rot, pos);
+          double jrho[2], lhs[6];
           image_jrho(a.rig, cm, R_i, rho, jrho);
-          // constant-parameter masking + write the lane's 30 local columns (5 knot slots x 6)
+          image_side_lhs(side, cm, ev.R, lhs);
+          // one knot at a time: chain rule -> constant masking -> the lane's local columns of the shared tile
+          // (5 knot slots x 6 per side) -> landmark coupling W_l += J_c' J_rho (fp64 RED), so that no 2x24
+          // block array stays live in registers
           const int cb = side * 30;
           const int gk0 = w0[side];
+          const int l = meta.z;
+          double* Wl = a.ne.W + a.lm.woff[l] - a.lm.lo[l];
+          {
+            const int unused = cb + (slot == 0 ? 4 : 0) * 6;
 #pragma unroll
-          for (int kk = 0; kk < kWinKnots; ++kk) {
-            // k = kk - slot, resolved with selects so that register arrays keep static indices
-            double v0[6], v1[6];
+            for (int c = 0; c < 6; ++c) { row0[unused + c] = 0.0; row1[unused + c] = 0.0; }
+          }
+          const double sgn = side == 0 ? 1.0 : -1.0;
+          jacobian_stage(sm.tab[side], ev, [&](int k, const M3& Jk) {
+            double rk[6];
+            mul23_33(lhs, Jk, rk);
+            const int gd = 6 * (gk0 + slot + k);
+            const int col = cb + (slot + k) * 6;
+            const double ck = sgn * ev.c[k];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const double r0a = kk < 4 ? rot[kk < 4 ? kk : 0][c] : 0.0, r0b = kk >= 1 ? rot[kk >= 1 ? kk - 1 : 0][c] : 0.0;
-              const double r1a = kk < 4 ? rot[kk < 4 ? kk : 0][3 + c] : 0.0, r1b = kk >= 1 ? rot[kk >= 1 ? kk - 1 : 0][3 + c] : 0.0;
-              const double p0a = kk < 4 ? pos[kk < 4 ? kk : 0][c] : 0.0, p0b = kk >= 1 ? pos[kk >= 1 ? kk - 1 : 0][c] : 0.0;
-              const double p1a = kk < 4 ? pos[kk < 4 ? kk : 0][3 + c] : 0.0, p1b = kk >= 1 ? pos[kk >= 1 ? kk - 1 : 0][3 + c] : 0.0;
-              v0[c] = slot == 0 ? r0a : r0b;
-              v1[c] = slot == 0 ? r1a : r1b;
-              v0[3 + c] = slot == 0 ? p0a : p0b;
-              v1[3 + c] = slot == 0 ? p1a : p1b;
+              const bool mr = a.cmask[gd + c] != 0, mp = a.cmask[gd + 3 + c] != 0;
+              const double r0v = mr ? 0.0 : rk[c], r1v = mr ? 0.0 : rk[3 + c];
+              const double p0v = mp ? 0.0 : ck * cm.JvR[c], p1v = mp ? 0.0 : ck * cm.JvR[3 + c];
+              row0[col + c] = r0v; row1[col + c] = r1v;
+              row0[col + 3 + c] = p0v; row1[col + 3 + c] = p1v;
+              if (!mr) atomicAdd(Wl + gd + c, r0v * jrho[0] + r1v * jrho[1]);
+              if (!mp) atomicAdd(Wl + gd + 3 + c, p0v * jrho[0] + p1v * jrho[1]);
             }
-            const int gk = gk0 + kk;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-              const bool is_const = gk < nK ? (a.cmask[6 * gk + c] != 0) : true;
-              row0[cb + kk * 6 + c] = is_const ? 0.0 : v0[c];
-              row1[cb + kk * 6 + c] = is_const ? 0.0 : v1[c];
-            }
-          }
+          });
           if (side == 0) {
             row0[kColR] = cm.r[0]; row1[kColR] = cm.r[1];
             row0[kColRho] = jrho[0]; row1[kColRho] = jrho[1];
@@ -278,18 +320,6 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
             row0[kColLd] = ld_const ? 0.0 : jld[0];
             row1[kColLd] = ld_const ? 0.0 : jld[1];
             row0[63] = 0.0; row1[63] = 0.0;
-          }
-          // landmark Schur pieces straight from registers: W_l += J_c' J_rho, h_l, g_l, w_ld
-          const int l = meta.z;
-          double* Wl = a.ne.W + a.lm.woff[l] - a.lm.lo[l];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int gd = 6 * (gk0 + slot + k);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              if (!a.cmask[gd + c]) atomicAdd(Wl + gd + c, rot[k][c] * jrho[0] + rot[k][3 + c] * jrho[1]);
-              if (!a.cmask[gd + 3 + c]) atomicAdd(Wl + gd + 3 + c, pos[k][c] * jrho[0] + pos[k][3 + c] * jrho[1]);
-            }
           }
           if (side == 0) {
             atomicAdd(a.ne.hl + l, jrho[0] * jrho[0] + jrho[1] * jrho[1]);
@@ -309,34 +339,7 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
         else { row0[kColLd] = row1[kColLd] = 0.0; row0[63] = row1[63] = 0.0; }
       }
       __syncthreads();
-      // ---- register-tiled SYRK of the round's rows into the CTA accumulator ----
-      if (tid < 252) {
-        const int grp = tid / 36, tile = tid % 36;
-        const int ti = c_tile_i[tile], tj = c_tile_j[tile];
-        double acc[64];
-#pragma unroll
-        for (int e = 0; e < 64; ++e) acc[e] = 0.0;
-        const int nrows = 2 * nround;
-        for (int row = grp; row < nrows; row += 7) {
-          const double2* ra = reinterpret_cast<const double2*>(Jt + size_t(row) * kLocalDim + ti * 8);
-          const double2* rb = reinterpret_cast<const double2*>(Jt + size_t(row) * kLocalDim + tj * 8);
-          double av[8], bv[8];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const double2 x = ra[e], y = rb[e];
-            av[2 * e] = x.x; av[2 * e + 1] = x.y;
-            bv[2 * e] = y.x; bv[2 * e + 1] = y.y;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fma(av[i], bv[j], acc[i * 8 + j]);
-        }
-#pragma unroll
-        for (int e = 0; e < 64; ++e)
-          if (acc[e] != 0.0) atomicAdd(&accs[tile * 64 + e], acc[e]);
-      }
-      __syncthreads();
+      syrk_round(Jt, accs, nround, tid);
     }
   }
 
@@ -407,11 +410,13 @@ constexpr int kImuCols = 31;  // 24 knot dims + 3 bg + 3 ba + residual column
 template <bool FULL>
 __global__ void __launch_bounds__(kImuThreads) imu_kernel(const __grid_constant__ ImuArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  double* Js = reinterpret_cast<double*>(dyn_smem);  // [64][6][31]
+  double* Js = reinterpret_cast<double*>(dyn_smem);  // [64 samples][6 rows][31 cols]
   __shared__ double cost_part[kImuThreads / 32];
+  __shared__ int key_s[kImuThreads], key_node[kImuThreads];
   const int tid = threadIdx.x;
   const int n = blockIdx.x * kImuThreads + tid;
   double cost = 0.0;
+  if (FULL) { key_s[tid] = -1; key_node[tid] = 0; }
   if (n < a.obs.n) {
     const longlong2 tn = a.obs.t_node[n];
     const double2 g0 = a.obs.ga[3 * n], g1 = a.obs.ga[3 * n + 1], g2 = a.obs.ga[3 * n + 2];
@@ -429,43 +434,60 @@ __global__ void __launch_bounds__(kImuThreads) imu_kernel(const __grid_constant_
       eval_imu<FULL, kPStride>(a.sp, a.rig, a.st.q, a.st.p, a.st.tab, s, u, gyro, accel, bias, o);
       cost = o.cost;
       if (FULL) {
+        key_s[tid] = s;
+        key_node[tid] = node;
         double* J = Js + size_t(tid) * 6 * kImuCols;
-        int gdim[30];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int c = 0; c < 6; ++c) gdim[k * 6 + c] = 6 * (s + k) + c;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) gdim[24 + c] = a.dims.idx_bias0 + 6 * node + c;
+        const int gb0 = a.dims.idx_bias0 + 6 * node;
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              J[r * kImuCols + k * 6 + c] = a.cmask[gdim[k * 6 + c]] ? 0.0 : o.Jrot[k][3 * r + c];
-              J[r * kImuCols + k * 6 + 3 + c] = a.cmask[gdim[k * 6 + 3 + c]] ? 0.0 : o.Jpos[k][3 * r + c];
+              J[r * kImuCols + k * 6 + c] = a.cmask[6 * (s + k) + c] ? 0.0 : o.Jrot[k][3 * r + c];
+              J[r * kImuCols + k * 6 + 3 + c] = a.cmask[6 * (s + k) + 3 + c] ? 0.0 : o.Jpos[k][3 * r + c];
             }
 #pragma unroll
           for (int c = 0; c < 6; ++c)
-            J[r * kImuCols + 24 + c] = (c == r && !a.cmask[gdim[24 + c]]) ? a.rig.imu_info[r] : 0.0;
+            J[r * kImuCols + 24 + c] = (c == r && !a.cmask[gb0 + c]) ? a.rig.imu_info[r] : 0.0;
           J[r * kImuCols + 30] = o.r[r];
         }
-        const int np = a.dims.np;
-        for (int ca = 0; ca < 30; ++ca) {
-          double ja[6];
-#pragma unroll
-          for (int r = 0; r < 6; ++r) ja[r] = J[r * kImuCols + ca];
-          double g = 0;
-#pragma unroll
-          for (int r = 0; r < 6; ++r) g = fma(ja[r], J[r * kImuCols + 30], g);
-          if (g != 0.0) atomicAdd(a.ne.gc + gdim[ca], g);
-          for (int cb = ca; cb < 30; ++cb) {
-            double h = 0;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) h = fma(ja[r], J[r * kImuCols + cb], h);
-            if (h != 0.0) atomicAdd(a.ne.A + size_t(gdim[ca]) * np + gdim[cb], h);  // gdim is increasing
+      }
+    }
+  }
+  if (FULL) {
+    __syncthreads();
+    // cooperative J'J: each thread owns up to 8 of the 496 (a <= b) entries of the 31-column local system
+    // (column 30 = residual -> gradient) and sums them over runs of samples sharing (start knot, bias node),
+    // flushing one fp64 atomic per entry per run.
+    const int np = a.dims.np;
+    const int nloc = min(kImuThreads, a.obs.n - blockIdx.x * kImuThreads);
+    for (int e = tid; e < 496; e += kImuThreads) {
+      int ca = 0, rem = e;
+      while (rem >= 31 - ca) { rem -= 31 - ca; ++ca; }
+      const int cb = ca + rem;
+      if (ca == 30) continue;  // (r, r): cost, not needed
+      double acc = 0.0;
+      int ks = -1, kn = 0;
+      for (int m = 0; m <= nloc; ++m) {
+        const int s_m = m < nloc ? key_s[m] : -2, n_m = m < nloc ? key_node[m] : 0;
+        if (s_m != ks || n_m != kn) {
+          if (acc != 0.0 && ks >= 0) {
+            const int ga = ca < 24 ? 6 * ks + ca : a.dims.idx_bias0 + 6 * kn + (ca - 24);
+            if (cb == 30) {
+              atomicAdd(a.ne.gc + ga, acc);
+            } else {
+              const int gb = cb < 24 ? 6 * ks + cb : a.dims.idx_bias0 + 6 * kn + (cb - 24);
+              atomicAdd(a.ne.A + size_t(ga) * np + gb, acc);  // ga <= gb: knot dims precede bias dims
+            }
           }
+          acc = 0.0;
+          ks = s_m; kn = n_m;
+        }
+        if (m < nloc && s_m >= 0) {
+          const double* J = Js + size_t(m) * 6 * kImuCols;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) acc = fma(J[r * kImuCols + ca], J[r * kImuCols + cb], acc);
         }
       }
     }

@@ -167,6 +167,110 @@ CTVIO_HD void eval_side(const SplineParams& sp, const double* q, const double* p
   o.vel = vv;
 }
 
+// ---- two-stage form of eval_side for the fused visual kernel -------------------------------------------
+// Stage A (pose_stage) produces what the partner lane needs (R, p, omega, vel) and keeps only the three
+// incremental quaternions E_j = exp(-lam_j d_j); stage B (jacobian_stage) regenerates the Jacobian blocks one
+// knot at a time and hands each to `emit`, so that the 4 x 3x3 blocks never sit in registers together with
+// the exchanged pose.  Jr(phi) is rebuilt from the half-angle sine/cosine already inside E_j
+// (1 - cos t = 2 sin^2(t/2), sin t = 2 sin(t/2) cos(t/2)): no second sincos.
+struct PoseStage {
+  int32_t s;
+  double lam[4];
+  Q4 E[3];
+  M3 R;
+  V3 p;
+  double c[4];
+  V3 omega, vel;
+};
+
+template <bool WANT_JAC, int PS>
+CTVIO_HD void pose_stage(const SplineParams& sp, const double* q, const double* p, const KnotPair* tab, int32_t s,
+                         double u, PoseStage& o) {
+  o.s = s;
+  cum_coeffs(u, o.lam);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const KnotPair& kp = tab[s + j];
+    const double l = o.lam[j + 1];
+    const double th = fabs(l) * kp.theta;
+    o.E[j] = so3_exp_theta(V3{-l * kp.d[0], -l * kp.d[1], -l * kp.d[2]}, th * th, th);
+  }
+  const Q4 B321 = so3_mul(so3_mul(o.E[2], o.E[1]), o.E[0]);
+  o.R = so3_matrix(so3_mul(load_q(q, s), q_conj(B321)));
+  plain_coeffs<0>(u, sp.inv_dt, o.c);
+  V3 pp = o.c[0] * load_p<PS>(p, s);
+#pragma unroll
+  for (int k = 1; k < 4; ++k) pp = pp + o.c[k] * load_p<PS>(p, s + k);
+  o.p = pp;
+  if (!WANT_JAC) return;
+  double dl[4];
+  cum_dcoeffs(u, sp.inv_dt, dl);
+  V3 w = V3{dl[1] * tab[s].d[0], dl[1] * tab[s].d[1], dl[1] * tab[s].d[2]};
+#pragma unroll
+  for (int j = 1; j < 3; ++j) {
+    const KnotPair& kp = tab[s + j];
+    w = so3_rotate(o.E[j], w) + V3{dl[j + 1] * kp.d[0], dl[j + 1] * kp.d[1], dl[j + 1] * kp.d[2]};
+  }
+  o.omega = w;
+  double c1[4];
+  plain_coeffs<1>(u, sp.inv_dt, c1);
+  V3 vv = c1[0] * load_p<PS>(p, s);
+#pragma unroll
+  for (int k = 1; k < 4; ++k) vv = vv + c1[k] * load_p<PS>(p, s + k);
+  o.vel = vv;
+}
+
+// rightJacobianSO3(phi) with phi = lam * d and the half-angle values held by E = exp(-phi):
+// E.w = cos(|phi|/2), |E.xyz| = sin(|phi|/2)  (Taylor branch like utils/sophus_utils.hpp:165-199)
+CTVIO_HD M3 right_jacobian_from_half(V3 phi, const Q4& Eneg) {
+  const double n2 = dot(phi, phi);
+  if (n2 > kSo3Eps) {
+    const double n = sqrt(n2);
+    const double sh = sqrt(Eneg.x * Eneg.x + Eneg.y * Eneg.y + Eneg.z * Eneg.z), ch = Eneg.w;
+    const double one_minus_cos = 2.0 * sh * sh, sn = 2.0 * sh * ch;
+    return rodrigues_like(phi, n2, -one_minus_cos / n2, (n - sn) / (n2 * n));
+  }
+  return rodrigues_like(phi, n2, -0.5, 1.0 / 6.0);
+}
+
+template <class Emit>
+CTVIO_HD void jacobian_stage(const KnotPair* tab, const PoseStage& ps, Emit&& emit) {
+  const int s = ps.s;
+  M3 Hprev;  // H_{k-1} * JrInv_{k-1}
+  {
+    const Q4 B32 = so3_mul(ps.E[2], ps.E[1]);
+    const Q4 B321 = so3_mul(B32, ps.E[0]);
+    const KnotPair& kp = tab[s];
+    const V3 phi = V3{ps.lam[1] * kp.d[0], ps.lam[1] * kp.d[1], ps.lam[1] * kp.d[2]};
+    M3 JI;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) JI.m[e] = kp.jrinv[e];
+    const M3 H0 = m3_scale(ps.lam[1], m3_mul(so3_matrix(B32), right_jacobian_from_half(phi, ps.E[0])));
+    emit(0, m3_sub(so3_matrix(B321), m3_mul_bt(H0, JI)));
+    Hprev = m3_mul(H0, JI);
+  }
+  {
+    const KnotPair& kp = tab[s + 1];
+    const V3 phi = V3{ps.lam[2] * kp.d[0], ps.lam[2] * kp.d[1], ps.lam[2] * kp.d[2]};
+    M3 JI;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) JI.m[e] = kp.jrinv[e];
+    const M3 H1 = m3_scale(ps.lam[2], m3_mul(so3_matrix(ps.E[2]), right_jacobian_from_half(phi, ps.E[1])));
+    emit(1, m3_sub(Hprev, m3_mul_bt(H1, JI)));
+    Hprev = m3_mul(H1, JI);
+  }
+  {
+    const KnotPair& kp = tab[s + 2];
+    const V3 phi = V3{ps.lam[3] * kp.d[0], ps.lam[3] * kp.d[1], ps.lam[3] * kp.d[2]};
+    M3 JI;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) JI.m[e] = kp.jrinv[e];
+    const M3 H2 = m3_scale(ps.lam[3], right_jacobian_from_half(phi, ps.E[2]));
+    emit(2, m3_sub(Hprev, m3_mul_bt(H2, JI)));
+    emit(3, m3_mul(H2, JI));
+  }
+}
+
 struct RigParams {
   M3 R_CI;     // S_CtoI.matrix()
   V3 p_CI;     // p_CinI
@@ -244,22 +348,26 @@ CTVIO_HD void mul23_33(const double A[6], const M3& B, double out[6]) {
 // Knot Jacobian blocks of one side (image_feature_factor.h:188-236).
 //   side 0 (anchor):      rot_k = (-JvR R_i hat(p_Ii)) J_k ,  pos_k =  c_k JvR
 //   side 1 (observation): rot_k = ( JvR hat(dp) R_j)   J_k ,  pos_k = -c_k JvR
-// out: rot[4][6], pos[4][6] (2x3 row-major each)
-CTVIO_HD void image_side_blocks(int side, const ImageCommon& cm, const SideEval& me, double rot[4][6], double pos[4][6]) {
-  M3 jv;  // JvR as the top 2 rows of a 3x3 to reuse m3 helpers
+// image_side_lhs returns the 2x3 left factor of the rotation blocks.
+CTVIO_HD void image_side_lhs(int side, const ImageCommon& cm, const M3& R_me, double lhs[6]) {
+  M3 jv;  // JvR as the top 2 rows of a 3x3 to reuse the m3 helpers
 #pragma unroll
   for (int e = 0; e < 6; ++e) jv.m[e] = cm.JvR[e];
   jv.m[6] = jv.m[7] = jv.m[8] = 0.0;
-  double lhs[6];
   if (side == 0) {
-    const M3 t = m3_mul_hat(m3_mul(jv, me.R), cm.p_Ii);
+    const M3 t = m3_mul_hat(m3_mul(jv, R_me), cm.p_Ii);
 #pragma unroll
     for (int e = 0; e < 6; ++e) lhs[e] = -t.m[e];
   } else {
-    const M3 t = m3_mul(m3_mul_hat(jv, cm.dp), me.R);
+    const M3 t = m3_mul(m3_mul_hat(jv, cm.dp), R_me);
 #pragma unroll
     for (int e = 0; e < 6; ++e) lhs[e] = t.m[e];
   }
+}
+// out: rot[4][6], pos[4][6] (2x3 row-major each)
+CTVIO_HD void image_side_blocks(int side, const ImageCommon& cm, const SideEval& me, double rot[4][6], double pos[4][6]) {
+  double lhs[6];
+  image_side_lhs(side, cm, me.R, lhs);
   const double sgn = side == 0 ? 1.0 : -1.0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {

@@ -204,6 +204,16 @@ int ctvio_normal_equations(ctvio_handle h, double* Hcc, double* gc, double* hl, 
 int ctvio_query_trajectory(ctvio_handle h, int32_t n, const int64_t* t, double* q_xyzw, double* p_xyz,
                            double* omega_body, double* vel_world, double* acc_world);
 
+/* ---- measurement support (bench.py roofline) ----
+ * Average CUDA-event duration (ms, on the engine stream) of one launch of each stage of an LM step at the
+ * current state, over `reps` launches after 3 warm-up launches.  flush_l2 != 0 writes a 256 MiB scratch
+ * buffer (> the 126 MB L2) between timed launches.
+ *   out_ms[0] visual residual+Jacobian+accumulate kernel (K1)   out_ms[1] IMU kernel (K2)
+ *   out_ms[2] bias + prior kernels (K3)                          out_ms[3] reduced system + landmark Schur (K4)
+ *   out_ms[4] blocked Cholesky + triangular solves (K5)          out_ms[5] step vectors / back-substitution (K6)
+ *   out_ms[6] apply step + knot-pair table (K6/K0)               out_ms[7] cost-only visual kernel */
+int ctvio_profile_kernels(ctvio_handle h, int32_t reps, int32_t flush_l2, double* out_ms8);
+
 /* ---- multi-GPU: landmark-sharded residuals, one allreduce of the reduced system per LM step ----
  * Every rank holds the full (replicated) state and its own shard of image factors; rank 0 also holds
  * IMU / bias / prior factors. unique_id is the 128-byte ncclUniqueId from ctvio_nccl_unique_id on rank 0. */

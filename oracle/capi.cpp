@@ -354,6 +354,11 @@ int ctvo_query_trajectory(void* h, int32_t n, const int64_t* t, double* q, doubl
   return CTVIO_OK;
 }
 
+int ctvo_profile_kernels(void*, int32_t, int32_t, double* out) {
+  for (int k = 0; k < 8; ++k) out[k] = 0.0;  // not meaningful for the CPU oracle
+  return CTVIO_OK;
+}
+
 // ---- oracle-only probes for the self-validation tests ------------------------------------------
 // kind: 0 EvaluateRp, 1 EvaluateRTp, 2 VelocityBody, 3 EvaluateRotation.  out_val: quat(4) or vec3;
 // out_J: 4 x 9 row-major blocks, start index returned.

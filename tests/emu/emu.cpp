@@ -2,6 +2,8 @@
 // (ctrl-vio_b200/csrc/device_math.cuh, spline_eval.cuh) with plain g++ so the
 // lane-level arithmetic can be compared with the oracle on a machine without a
 // GPU.  Not linked into the product library; nothing in the product calls it.
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -86,6 +88,30 @@ int emu_eval_imu(int64_t t0_ns, int64_t dt_ns, int n_knots, const double* q, con
     J[144 + k] = imu_info[k]; J[147 + k] = 0; J[150 + k] = 0; J[153 + k] = imu_info[3 + k];
   }
   return 0;
+}
+
+// two-stage pose / Jacobian path used by the fused visual kernel vs the one-shot eval_side.
+// out: max abs difference over R, p, omega, vel, c and the four Jacobian blocks
+double emu_two_stage_maxdiff(int64_t t0_ns, int64_t dt_ns, int n_knots, const double* q, const double* p, int64_t t) {
+  SplineParams sp{t0_ns, dt_ns, n_knots, 1e9 / double(dt_ns)};
+  std::vector<KnotPair> tab(n_knots - 1);
+  for (int k = 0; k < n_knots - 1; ++k) make_knot_pair(q, k, tab[k]);
+  int32_t s;
+  double u;
+  if (!spline_index(sp, t, s, u)) return -1.0;
+  SideEval a;
+  eval_side<true, 3>(sp, q, p, tab.data(), s, u, a);
+  PoseStage b;
+  pose_stage<true, 3>(sp, q, p, tab.data(), s, u, b);
+  double m = 0;
+  auto upd = [&](double x, double y) { m = std::max(m, std::fabs(x - y)); };
+  for (int e = 0; e < 9; ++e) upd(a.R.m[e], b.R.m[e]);
+  upd(a.p.x, b.p.x); upd(a.p.y, b.p.y); upd(a.p.z, b.p.z);
+  upd(a.omega.x, b.omega.x); upd(a.omega.y, b.omega.y); upd(a.omega.z, b.omega.z);
+  upd(a.vel.x, b.vel.x); upd(a.vel.y, b.vel.y); upd(a.vel.z, b.vel.z);
+  for (int k = 0; k < 4; ++k) upd(a.c[k], b.c[k]);
+  jacobian_stage(tab.data(), b, [&](int k, const M3& Jk) { for (int e = 0; e < 9; ++e) upd(a.J[k].m[e], Jk.m[e]); });
+  return m;
 }
 
 void emu_quat_from_matrix(const double* m, double* q) {

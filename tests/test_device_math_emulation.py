@@ -89,3 +89,21 @@ def test_quat_from_matrix(emu):
         out = np.zeros(4)
         emu.emu_quat_from_matrix(dp(np.ascontiguousarray(R)), dp(out))
         assert min(np.abs(out - q).max(), np.abs(out + q).max()) < 1e-12
+
+
+def test_two_stage_evaluation_equals_one_shot(emu):
+    """pose_stage + jacobian_stage (fused visual kernel) == eval_side (probe / query path)."""
+    w = small_window(seed=14, n_knots=10, n_kf=5, per_frame=2)
+    q = np.ascontiguousarray(w.q0); p = np.ascontiguousarray(w.p0)
+    emu.emu_two_stage_maxdiff.restype = C.c_double
+    rng = np.random.default_rng(2)
+    for t in rng.integers(w.t0_ns, w.t0_ns + (w.n_knots - 3) * w.dt_ns - 1, 200):
+        d = emu.emu_two_stage_maxdiff(C.c_int64(w.t0_ns), C.c_int64(w.dt_ns), C.c_int(w.n_knots), dp(q), dp(p),
+                                      C.c_int64(int(t)))
+        assert 0 <= d < 1e-12, d
+    # identical consecutive knots (freshly extended trajectory, SURVEY C-16): Taylor branches
+    q2 = q.copy(); q2[5:] = q2[5]
+    for t in rng.integers(w.t0_ns + 3 * w.dt_ns, w.t0_ns + (w.n_knots - 3) * w.dt_ns - 1, 50):
+        d = emu.emu_two_stage_maxdiff(C.c_int64(w.t0_ns), C.c_int64(w.dt_ns), C.c_int(w.n_knots), dp(q2), dp(p),
+                                      C.c_int64(int(t)))
+        assert 0 <= d < 1e-12, d

@@ -208,7 +208,7 @@ def test_c4_full_size_against_oracle_and_properties(oracle_lib, cuda_lib):
 def test_time_outside_window_is_reported(cuda_lib):
     w = small_window(seed=5, n_knots=8, n_kf=5, per_frame=4, fix_ld=False)
     g = pkg.setup_estimator(cuda_lib, w)
-    g.SetLineDelay(60e-6)  # 1023 rows * 60 us = 61 ms > padding: evaluation leaves its 5-knot window
+    g.SetLineDelay(400e-6)  # row * 400 us exceeds one knot interval for every row > 125: leaves the 5-knot window
     with pytest.raises(pkg.CtvioError) as ei:
         g.EvalCost()
     assert "-6" in str(ei.value)
