@@ -23,7 +23,7 @@ else:
     print(os.path.join(list(s.submodule_search_locations)[0], 'lib') if s else '')
 PY
 )}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -Xptxas -v"
+FLAGS="${CTVIO_EXTRA_NVCC_FLAGS:-} -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -Xptxas -v"
 objs=""
 for f in $SRCS; do
   o="${f%.cu}.o"

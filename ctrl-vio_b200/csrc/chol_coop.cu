@@ -22,6 +22,22 @@ namespace ctvio {
 
 namespace cg = cooperative_groups;
 
+// optional phase timing of CTA 0 (debug): CTVIO_CHOL_TIMING=1 at build time; stamps go to g_chol_stamps
+#ifdef CTVIO_CHOL_TIMING
+__device__ unsigned long long g_chol_stamps[4096];
+__device__ __forceinline__ void stamp(int& n) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (n < 4096) g_chol_stamps[n] = t;
+  }
+  ++n;
+}
+#define STAMP() stamp(stamp_n)
+#else
+#define STAMP()
+#endif
+
 constexpr int kTS = kCholNB + 2;  // shared tile row stride (doubles): rows stay 16-B aligned
 constexpr size_t kCholCoopSmem = (4 * size_t(kCholNB) * kTS + 4 * kCholNB) * sizeof(double);
 
@@ -42,62 +58,152 @@ __device__ __forceinline__ void tile_gemm_abt(const double* As, const double* Bt
   }
 }
 
-// In-place lower Cholesky of the 64x64 block D (row stride kTS) by 256 threads, then Xi = D^-1 (lower
-// triangular, full tile written).  T is a scratch tile, rdiag[64] receives 1/L_jj.  Returns false
-// (uniformly) when a pivot is not positive / finite.
-__device__ bool factor_and_invert_64(double* D, double* Xi, double* T, double* rdiag, int* s_bad) {
-  const int tid = threadIdx.x;
-  const int i = tid >> 2, pt = tid & 3;
-  if (tid == 0) *s_bad = 0;
-  for (int j = 0; j < kCholNB; ++j) {
-    // left-looking column j: v_i = D[i][j] - sum_{k<j} D[i][k] D[j][k]; dot product split over 4 lanes
-    double s = 0.0;
-    if (i >= j)
-      for (int k = pt; k < j; k += 4) s = fma(D[i * kTS + k], D[j * kTS + k], s);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    double v = 0.0;
-    if (i >= j) v = D[i * kTS + j] - s;
-    if (i == j && pt == 0) {
-      if (!(v > 0.0) || !isfinite(v)) { *s_bad = 1; v = 1.0; }
-      const double r = rsqrt(v);
-      rdiag[j] = r;            // 1 / L_jj
-      D[j * kTS + j] = v * r;  // sqrt(v)
+// Register-tiled product for the triangular-inverse merge: for every pair of adjacent h-blocks on the
+// diagonal, C = alpha * A * B on h x h operands living in shared tiles (row stride kTS).  One thread per
+// 4x4 output tile, so every k-step feeds 16 independent FMAs.
+//   mode 0: C = T      <- L21 * X11       (A = D,  B = Xi)
+//   mode 1: C = Xi21   <- -(X22 * T)      (A = Xi, B = T)
+__device__ __forceinline__ void merge_gemm(int mode, int h, const double* D, double* Xi, double* T, int tid) {
+  const int npair = kCholNB / (2 * h), tpb = (h / 4) * (h / 4);
+  if (tid < npair * tpb) {
+    const int pb = tid / tpb, t = tid % tpb;
+    const int r0 = 4 * (t / (h / 4)), c0 = 4 * (t % (h / 4));
+    const int o = 2 * h * pb;
+    const double* A = mode == 0 ? D + (o + h) * kTS + o : Xi + (o + h) * kTS + o + h;
+    const double* B = mode == 0 ? Xi + o * kTS + o : T + (o + h) * kTS + o;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int m = 0; m < h; ++m) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = A[(r0 + i) * kTS + m];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = B[m * kTS + c0 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
     }
-    __syncthreads();
-    if (i > j && pt == 0) D[i * kTS + j] = v * rdiag[j];
-    __syncthreads();
+    double* C = mode == 0 ? T + (o + h) * kTS + o : Xi + (o + h) * kTS + o;
+    const double sg = mode == 0 ? 1.0 : -1.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) C[(r0 + i) * kTS + c0 + j] = sg * acc[i][j];
   }
-  // ---- inverse: 16x16 diagonal blocks by forward substitution (thread = column), then merge ----
+}
+
+// In-place lower Cholesky of the 64x64 block D (row stride kTS) by 256 threads, then Xi = D^-1 (lower
+// triangular, full tile written).  Right-looking on 4x4 register blocks: thread (ty, tx) owns block
+// (rows 4ty.., cols 4tx..); per block column jb: the diagonal owner factors + inverts its 4x4 block in
+// registers, the 4x4 panel blocks below are multiplied by that inverse, everybody to the right applies the
+// rank-4 update from shared memory.  The 64x64 inverse is then assembled from the 4x4 diagonal inverses by
+// recursive merges [[L11,0],[L21,L22]]^-1 = [[X11,0],[-X22 L21 X11, X22]].
+// T is a scratch tile.  Returns false (uniformly) when a pivot is not positive / finite.
+__device__ bool factor_and_invert_64(double* D, double* Xi, double* T, int* s_bad) {
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  if (tid == 0) *s_bad = 0;
+  double a[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[i][j] = D[(4 * ty + i) * kTS + 4 * tx + j];
   for (int e = tid; e < kCholNB * kCholNB; e += 256) Xi[(e >> 6) * kTS + (e & 63)] = 0.0;
   __syncthreads();
-  if (tid < kCholNB) {
-    const int o = 16 * (tid >> 4), c = tid & 15;
-    for (int r = c; r < 16; ++r) {
-      double t = (r == c) ? 1.0 : 0.0;
-      for (int m = c; m < r; ++m) t = fma(-D[(o + r) * kTS + o + m], Xi[(o + m) * kTS + o + c], t);
-      Xi[(o + r) * kTS + o + c] = t * rdiag[o + r];
-    }
-  }
-  __syncthreads();
-  // merge for block size h: [[L11,0],[L21,L22]]^-1 = [[X11,0],[-X22 L21 X11, X22]]
-  for (int h = 16; h < kCholNB; h *= 2) {
-    const int npair = kCholNB / (2 * h);
-    for (int e = tid; e < npair * h * h; e += 256) {  // T = L21 * X11
-      const int pb = e / (h * h), r = (e / h) % h, c = e % h;
-      const int o = 2 * h * pb;
-      double t = 0.0;
-      for (int m = c; m < h; ++m) t = fma(D[(o + h + r) * kTS + o + m], Xi[(o + m) * kTS + o + c], t);
-      T[(o + h + r) * kTS + o + c] = t;
+  for (int jb = 0; jb < 16; ++jb) {
+    if (ty == jb && tx == jb) {
+      // 4x4 Cholesky + inverse in registers
+      double l[4][4], li[4][4], rd[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double v = a[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) v = fma(-l[j][k], l[j][k], v);
+        if (!(v > 0.0) || !isfinite(v)) { *s_bad = 1; v = 1.0; }
+        rd[j] = rsqrt(v);
+        l[j][j] = v * rd[j];
+#pragma unroll
+        for (int i = j + 1; i < 4; ++i) {
+          double w = a[i][j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) w = fma(-l[i][k], l[j][k], w);
+          l[i][j] = w * rd[j];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (r < c) { li[r][c] = 0.0; continue; }
+          double t = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+          for (int m = c; m < r; ++m) t = fma(-l[r][m], li[m][c], t);
+          li[r][c] = t * rd[r];
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          D[(4 * jb + i) * kTS + 4 * jb + j] = j <= i ? l[i][j] : 0.0;
+          Xi[(4 * jb + i) * kTS + 4 * jb + j] = j <= i ? li[i][j] : 0.0;
+        }
     }
     __syncthreads();
-    for (int e = tid; e < npair * h * h; e += 256) {  // X21 = -X22 * T
-      const int pb = e / (h * h), r = (e / h) % h, c = e % h;
-      const int o = 2 * h * pb;
-      double t = 0.0;
-      for (int m = 0; m <= r; ++m) t = fma(Xi[(o + h + r) * kTS + o + h + m], T[(o + h + m) * kTS + o + c], t);
-      Xi[(o + h + r) * kTS + o + c] = -t;
+    if (tx == jb && ty > jb) {
+      // panel block: x = a * li^T   (li lower: x[r][c] = sum_{m<=c} a[r][m] li[c][m])
+      double li[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) li[i][j] = Xi[(4 * jb + i) * kTS + 4 * jb + j];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        double x[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double t = 0.0;
+#pragma unroll
+          for (int m = 0; m <= c; ++m) t = fma(a[r][m], li[c][m], t);
+          x[c] = t;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) D[(4 * ty + r) * kTS + 4 * jb + c] = x[c];
+      }
     }
+    __syncthreads();
+    if (tx > jb && ty >= tx) {
+      double lr[4][4], lc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          lr[i][m] = D[(4 * ty + i) * kTS + 4 * jb + m];
+          lc[i][m] = D[(4 * tx + i) * kTS + 4 * jb + m];
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int m = 0; m < 4; ++m) a[i][j] = fma(-lr[i][m], lc[j][m], a[i][j]);
+    }
+  }
+  // strictly-upper part of D is never read again by the callers' products except through Xi; zero it for safety
+  if (ty < tx) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) D[(4 * ty + i) * kTS + 4 * tx + j] = 0.0;
+  }
+  __syncthreads();
+  for (int h = 4; h < kCholNB; h *= 2) {
+    merge_gemm(0, h, D, Xi, T, tid);
+    __syncthreads();
+    merge_gemm(1, h, D, Xi, T, tid);
     __syncthreads();
   }
   return *s_bad == 0;
@@ -120,9 +226,14 @@ chol_coop_kernel(double* __restrict__ M, int npad, double* __restrict__ Linv, co
   const int G = gridDim.x, cta = blockIdx.x;
   const int nb = npad / kCholNB;
   cg::grid_group grid = cg::this_grid();
+#ifdef CTVIO_CHOL_TIMING
+  int stamp_n = 0;
+#endif
+  STAMP();
 
   for (int r = cta * 256 + tid; r < npad; r += G * 256) y[r] = rhs[r];
   grid.sync();
+  STAMP();
 
   for (int k = 0; k < nb; ++k) {
     const int nslab = nb - k - 1;
@@ -131,7 +242,9 @@ chol_coop_kernel(double* __restrict__ M, int npad, double* __restrict__ Linv, co
     if (cta == 0 || cta < nslab) {
       for (int e = tid; e < kCholNB * kCholNB; e += 256) D[(e >> 6) * kTS + (e & 63)] = M[size_t(d0 + (e >> 6)) * npad + d0 + (e & 63)];
       __syncthreads();
-      const bool ok = factor_and_invert_64(D, Xi, S2, rdiag, &s_bad);
+      STAMP();  // diag block loaded
+      const bool ok = factor_and_invert_64(D, Xi, S2, &s_bad);
+      STAMP();  // factored + inverted
       if (!ok && cta == 0 && tid == 0) scal->chol_fail = 1;
       // x_k = Xi * y_k  (4 lanes per row)
       {
@@ -182,8 +295,10 @@ chol_coop_kernel(double* __restrict__ M, int npad, double* __restrict__ Linv, co
         __syncthreads();
       }
     }
+    STAMP();  // phase P done
     if (nslab == 0) break;
     grid.sync();
+    STAMP();  // sync 1
     // ---------------- phase U: trailing update, tiles (bi >= bj) spread over the grid ----------------
     const int ntiles = nslab * (nslab + 1) / 2;
     for (int t = cta; t < ntiles; t += G) {
@@ -209,7 +324,9 @@ chol_coop_kernel(double* __restrict__ M, int npad, double* __restrict__ Linv, co
         for (int j = 0; j < 4; ++j) M[size_t(ri + 4 * ty + i) * npad + rj + 4 * tx + j] -= acc[i][j];
       __syncthreads();
     }
+    STAMP();  // phase U done
     grid.sync();
+    STAMP();  // sync 2
   }
   if (cta != 0) return;
   // ---------------- backward substitution  L^T x = yf  (CTA 0) ----------------
@@ -239,7 +356,14 @@ chol_coop_kernel(double* __restrict__ M, int npad, double* __restrict__ Linv, co
     if (tid < kCholNB) y[d0 + tid] = red[tid] + red[kCholNB + tid];
     __syncthreads();
   }
+  STAMP();  // backward substitution done
 }
+
+#ifdef CTVIO_CHOL_TIMING
+extern "C" int ctvio_debug_chol_stamps(unsigned long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, g_chol_stamps, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int launch_factor_solve(const LinearLaunch& a, cudaStream_t s) {
   static int n_sm = 0;

@@ -110,6 +110,9 @@ struct ctvio_engine {
   std::vector<int32_t> img_order;  // sorted position -> original index
   DevBuf<longlong2> d_imu_t;
   DevBuf<double2> d_imu_ga;
+  DevBuf<ImuItem> d_imu_items;
+  DevBuf<int32_t> d_imu_orig;
+  int n_imu_items = 0;
   DevBuf<int2> d_bf_ij;
   DevBuf<double> d_bf_s;
 
@@ -294,15 +297,35 @@ int prepare(ctvio_engine* e) {
     std::vector<longlong2> it(ni);
     std::vector<double2> iga(3 * size_t(ni));
     const int64_t maxt = e->cfg.t0_ns + int64_t(e->nK - 3) * e->cfg.dt_ns;
+    std::vector<int32_t> imu_order(ni), imu_s(ni);
     for (int k = 0; k < ni; ++k) {
       const HostImu& o = e->imu[k];
       if (o.t < e->cfg.t0_ns || o.t >= maxt) return fail(CTVIO_ERR_TIME_RANGE, "imu time outside the spline");
       if (o.node < 0 || o.node >= e->nB) return fail(CTVIO_ERR_INVALID, "bias node out of range");
+      imu_order[k] = k;
+      imu_s[k] = knot_window_first(e, o.t);
+    }
+    // runs of samples sharing (start knot, bias node) -> one CTA each
+    std::stable_sort(imu_order.begin(), imu_order.end(), [&](int a, int b) {
+      if (imu_s[a] != imu_s[b]) return imu_s[a] < imu_s[b];
+      return e->imu[a].node < e->imu[b].node;
+    });
+    std::vector<ImuItem> imu_items;
+    for (int k = 0; k < ni; ++k) {
+      const HostImu& o = e->imu[imu_order[k]];
       it[k] = make_longlong2(o.t, o.node);
       iga[3 * k] = make_double2(o.gyro[0], o.gyro[1]);
       iga[3 * k + 1] = make_double2(o.gyro[2], o.accel[0]);
       iga[3 * k + 2] = make_double2(o.accel[1], o.accel[2]);
+      const int s = imu_s[imu_order[k]];
+      if (imu_items.empty() || imu_items.back().s != s || imu_items.back().node != o.node ||
+          imu_items.back().count >= kImuMaxPerItem)
+        imu_items.push_back(ImuItem{k, 0, s, o.node});
+      imu_items.back().count++;
     }
+    e->n_imu_items = int(imu_items.size());
+    CUDA_OK(e->d_imu_items.upload(imu_items, st));
+    CUDA_OK(e->d_imu_orig.upload(imu_order, st));
     CUDA_OK(e->d_imu_t.upload(it, st));
     CUDA_OK(e->d_imu_ga.upload(iga, st));
     const int nb = int(e->biasf.size());
@@ -453,6 +476,8 @@ VisualLaunch visual_launch(ctvio_engine* e, int xb, int nb, double cauchy) {
 ImuLaunch imu_launch(ctvio_engine* e, int xb, int nb) {
   ImuLaunch v;
   v.obs = ImuObsPtrs{e->d_imu_t.p, e->d_imu_ga.p, int32_t(e->imu.size())};
+  v.items = e->d_imu_items.p;
+  v.n_items = e->n_imu_items;
   v.st = e->x[xb].ptrs();
   v.ne = e->ne(nb);
   v.dims = e->dims();
@@ -1029,7 +1054,8 @@ int ctvio_eval_imu_factors(ctvio_handle e, int32_t want_jac, double* r, int32_t*
   if (want_jac) CUDA_OK(dJ.reserve(156 * n));
   cudaStream_t st = e->stream;
   cudaMemsetAsync(&e->d_scal.p->cost_eval, 0, sizeof(double), st);
-  e->launches += launch_probe_imu(imu_launch(e, e->cur, e->cur), want_jac != 0, dr.p, ds.p, want_jac ? dJ.p : nullptr, st);
+  e->launches += launch_probe_imu(imu_launch(e, e->cur, e->cur), e->d_imu_orig.p, want_jac != 0, dr.p, ds.p,
+                                  want_jac ? dJ.p : nullptr, st);
   rc = read_scalars(e);
   if (rc) return rc;
   if (r && n) CUDA_OK(cudaMemcpy(r, dr.p, 6 * n * sizeof(double), cudaMemcpyDeviceToHost));

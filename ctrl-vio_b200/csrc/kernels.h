@@ -56,10 +56,16 @@ struct VisualItem {  // one CTA work item: a chunk of one frame-pair group
 };
 
 struct ImuObsPtrs {
-  const longlong2* t_node;  // {t, bias node}
+  const longlong2* t_node;  // {t, bias node}; sorted by (start knot, bias node)
   const double2* ga;        // [n][3] double2: {gx,gy},{gz,ax},{ay,az}
   int32_t n;
 };
+
+struct ImuItem {  // one CTA work item: samples sharing the start knot and the bias node
+  int32_t start, count;
+  int32_t s, node;
+};
+constexpr int kImuMaxPerItem = 32;
 
 struct BiasFactorPtrs {
   const int2* ij;
@@ -134,6 +140,8 @@ size_t visual_smem_bytes();
 
 struct ImuLaunch {
   ImuObsPtrs obs;
+  const ImuItem* items;
+  int32_t n_items;
   StatePtrs st;
   NormalEqPtrs ne;
   ProblemDims dims;
@@ -158,7 +166,8 @@ int launch_small_factors(const SmallFactorsLaunch& a, bool full, cudaStream_t s)
 // probes (parity tests): per-factor residuals / Jacobians in the C-ABI layout, original factor order
 int launch_probe_image(const VisualLaunch& a, const int32_t* orig_index, bool want_jac, double* r, int32_t* s,
                        double* J, cudaStream_t st);
-int launch_probe_imu(const ImuLaunch& a, bool want_jac, double* r, int32_t* s, double* J, cudaStream_t st);
+int launch_probe_imu(const ImuLaunch& a, const int32_t* orig_index, bool want_jac, double* r, int32_t* s, double* J,
+                     cudaStream_t st);
 
 // ---- linear algebra / LM step -------------------------------------------------------------------
 struct LinearLaunch {

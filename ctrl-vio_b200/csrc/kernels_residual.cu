@@ -390,11 +390,14 @@ int launch_visual(const VisualLaunch& l, bool full, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: IMU factors.  One thread per sample; the 6x30 Jacobian is staged in shared memory and each
-// thread reduces its own J'J (465 entries, mostly inside one 4-knot block) with fp64 atomics.
+// K2: IMU factors.  One CTA per (start knot, bias node) run of samples (<= 32): lanes of warp 0 evaluate
+// one sample each, the 6 x 31 Jacobian rows (24 knot dims | 6 bias dims | residual) go to shared memory and
+// all 64 threads reduce J'J with the same 8x8 register-tiled SYRK as K1 (10 upper tiles x 6 row groups),
+// flushing one fp64 atomic per non-zero entry per CTA.
 
 struct ImuArgs {
   ImuObsPtrs obs;
+  const ImuItem* items;
   StatePtrs st;
   NormalEqPtrs ne;
   ProblemDims dims;
@@ -405,115 +408,125 @@ struct ImuArgs {
 };
 
 constexpr int kImuThreads = 64;
-constexpr int kImuCols = 31;  // 24 knot dims + 3 bg + 3 ba + residual column
+constexpr int kImuCols = 32;      // 24 knot dims + 6 bias dims + residual + pad
+constexpr int kImuRowStride = 34; // doubles; 16-B aligned rows, fewer store conflicts
+__constant__ uint8_t c_imu_tile_i[10] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3};
+__constant__ uint8_t c_imu_tile_j[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
 
 template <bool FULL>
 __global__ void __launch_bounds__(kImuThreads) imu_kernel(const __grid_constant__ ImuArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  double* Js = reinterpret_cast<double*>(dyn_smem);  // [64 samples][6 rows][31 cols]
-  __shared__ double cost_part[kImuThreads / 32];
-  __shared__ int key_s[kImuThreads], key_node[kImuThreads];
+  double* Js = reinterpret_cast<double*>(dyn_smem);            // [32 samples x 6 rows][kImuRowStride]
+  double* accs = Js + kImuMaxPerItem * 6 * kImuRowStride;      // [10][64]
   const int tid = threadIdx.x;
-  const int n = blockIdx.x * kImuThreads + tid;
+  const ImuItem item = a.items[blockIdx.x];
   double cost = 0.0;
-  if (FULL) { key_s[tid] = -1; key_node[tid] = 0; }
-  if (n < a.obs.n) {
+  if (FULL)
+    for (int i = tid; i < 10 * 64; i += kImuThreads) accs[i] = 0.0;
+  if (tid < item.count) {
+    const int n = item.start + tid;
     const longlong2 tn = a.obs.t_node[n];
     const double2 g0 = a.obs.ga[3 * n], g1 = a.obs.ga[3 * n + 1], g2 = a.obs.ga[3 * n + 2];
     const double gyro[3] = {g0.x, g0.y, g1.x}, accel[3] = {g1.y, g2.x, g2.y};
-    const int node = int(tn.y);
+    const int node = item.node;
     double bias[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) bias[c] = a.st.bias[6 * node + c];
     int32_t s;
     double u;
-    if (!spline_index(a.sp, tn.x, s, u)) {
+    const bool ok = spline_index(a.sp, tn.x, s, u) && s == item.s;
+    double* J = Js + size_t(tid) * 6 * kImuRowStride;
+    if (!ok) {
       atomicOr(&a.scal->error_flags, 1);
+      if (FULL)
+        for (int e = 0; e < 6 * kImuRowStride; ++e) J[e] = 0.0;
     } else {
       ImuEvalOut o;
       eval_imu<FULL, kPStride>(a.sp, a.rig, a.st.q, a.st.p, a.st.tab, s, u, gyro, accel, bias, o);
       cost = o.cost;
       if (FULL) {
-        key_s[tid] = s;
-        key_node[tid] = node;
-        double* J = Js + size_t(tid) * 6 * kImuCols;
         const int gb0 = a.dims.idx_bias0 + 6 * node;
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
+          double* Jr = J + r * kImuRowStride;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              J[r * kImuCols + k * 6 + c] = a.cmask[6 * (s + k) + c] ? 0.0 : o.Jrot[k][3 * r + c];
-              J[r * kImuCols + k * 6 + 3 + c] = a.cmask[6 * (s + k) + 3 + c] ? 0.0 : o.Jpos[k][3 * r + c];
+              Jr[k * 6 + c] = a.cmask[6 * (s + k) + c] ? 0.0 : o.Jrot[k][3 * r + c];
+              Jr[k * 6 + 3 + c] = a.cmask[6 * (s + k) + 3 + c] ? 0.0 : o.Jpos[k][3 * r + c];
             }
 #pragma unroll
-          for (int c = 0; c < 6; ++c)
-            J[r * kImuCols + 24 + c] = (c == r && !a.cmask[gb0 + c]) ? a.rig.imu_info[r] : 0.0;
-          J[r * kImuCols + 30] = o.r[r];
+          for (int c = 0; c < 6; ++c) Jr[24 + c] = (c == r && !a.cmask[gb0 + c]) ? a.rig.imu_info[r] : 0.0;
+          Jr[30] = o.r[r];
+          Jr[31] = 0.0;
         }
       }
     }
   }
   if (FULL) {
     __syncthreads();
-    // cooperative J'J: each thread owns up to 8 of the 496 (a <= b) entries of the 31-column local system
-    // (column 30 = residual -> gradient) and sums them over runs of samples sharing (start knot, bias node),
-    // flushing one fp64 atomic per entry per run.
-    const int np = a.dims.np;
-    const int nloc = min(kImuThreads, a.obs.n - blockIdx.x * kImuThreads);
-    for (int e = tid; e < 496; e += kImuThreads) {
-      int ca = 0, rem = e;
-      while (rem >= 31 - ca) { rem -= 31 - ca; ++ca; }
-      const int cb = ca + rem;
-      if (ca == 30) continue;  // (r, r): cost, not needed
-      double acc = 0.0;
-      int ks = -1, kn = 0;
-      for (int m = 0; m <= nloc; ++m) {
-        const int s_m = m < nloc ? key_s[m] : -2, n_m = m < nloc ? key_node[m] : 0;
-        if (s_m != ks || n_m != kn) {
-          if (acc != 0.0 && ks >= 0) {
-            const int ga = ca < 24 ? 6 * ks + ca : a.dims.idx_bias0 + 6 * kn + (ca - 24);
-            if (cb == 30) {
-              atomicAdd(a.ne.gc + ga, acc);
-            } else {
-              const int gb = cb < 24 ? 6 * ks + cb : a.dims.idx_bias0 + 6 * kn + (cb - 24);
-              atomicAdd(a.ne.A + size_t(ga) * np + gb, acc);  // ga <= gb: knot dims precede bias dims
-            }
-          }
-          acc = 0.0;
-          ks = s_m; kn = n_m;
-        }
-        if (m < nloc && s_m >= 0) {
-          const double* J = Js + size_t(m) * 6 * kImuCols;
+    const int grp = tid / 10, tile = tid % 10;
+    double acc[64];
+    if (tid < 60) {
+      const int ti = c_imu_tile_i[tile], tj = c_imu_tile_j[tile];
 #pragma unroll
-          for (int r = 0; r < 6; ++r) acc = fma(J[r * kImuCols + ca], J[r * kImuCols + cb], acc);
+      for (int e = 0; e < 64; ++e) acc[e] = 0.0;
+      const int nrows = 6 * item.count;
+      for (int row = grp; row < nrows; row += 6) {
+        const double2* ra = reinterpret_cast<const double2*>(Js + size_t(row) * kImuRowStride + ti * 8);
+        const double2* rb = reinterpret_cast<const double2*>(Js + size_t(row) * kImuRowStride + tj * 8);
+        double av[8], bv[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double2 x = ra[e], y = rb[e];
+          av[2 * e] = x.x; av[2 * e + 1] = x.y;
+          bv[2 * e] = y.x; bv[2 * e + 1] = y.y;
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fma(av[i], bv[j], acc[i * 8 + j]);
       }
+    }
+    for (int g = 0; g < 6; ++g) {
+      if (tid < 60 && grp == g) {
+#pragma unroll
+        for (int e = 0; e < 64; ++e) accs[tile * 64 + e] += acc[e];
+      }
+      __syncthreads();
+    }
+    const int np = a.dims.np;
+    for (int idx = tid; idx < 10 * 64; idx += kImuThreads) {
+      const double val = accs[idx];
+      if (val == 0.0) continue;
+      const int tile2 = idx >> 6, e = idx & 63;
+      const int la = c_imu_tile_i[tile2] * 8 + (e >> 3), lb = c_imu_tile_j[tile2] * 8 + (e & 7);
+      if (la > lb || lb > 30 || la >= 30) continue;
+      const int ga = la < 24 ? 6 * item.s + la : a.dims.idx_bias0 + 6 * item.node + (la - 24);
+      if (lb == 30) {
+        atomicAdd(a.ne.gc + ga, val);
+        continue;
+      }
+      const int gb = lb < 24 ? 6 * item.s + lb : a.dims.idx_bias0 + 6 * item.node + (lb - 24);
+      atomicAdd(a.ne.A + size_t(ga) * np + gb, val);  // ga <= gb: knot dims precede bias dims
     }
   }
   cost = warp_sum(cost);
-  if ((tid & 31) == 0) cost_part[tid >> 5] = cost;
-  __syncthreads();
-  if (tid == 0) {
-    double c = 0;
-    for (int w = 0; w < kImuThreads / 32; ++w) c += cost_part[w];
-    if (c != 0.0) atomicAdd(a.ne.cost, c);
-  }
+  if (tid == 0 && cost != 0.0) atomicAdd(a.ne.cost, cost);  // only warp 0 evaluates (count <= 32)
 }
 
 int launch_imu(const ImuLaunch& l, bool full, cudaStream_t s) {
-  if (l.obs.n <= 0) return 0;
-  ImuArgs a{l.obs, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal};
-  const int grid = (l.obs.n + kImuThreads - 1) / kImuThreads;
-  const size_t smem = size_t(kImuThreads) * 6 * kImuCols * sizeof(double);
+  if (l.n_items <= 0) return 0;
+  ImuArgs a{l.obs, l.items, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal};
+  const size_t smem = (size_t(kImuMaxPerItem) * 6 * kImuRowStride + 10 * 64) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(imu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     attr_set = true;
   }
-  if (full) imu_kernel<true><<<grid, kImuThreads, smem, s>>>(a);
-  else imu_kernel<false><<<grid, kImuThreads, 0, s>>>(a);
+  if (full) imu_kernel<true><<<l.n_items, kImuThreads, smem, s>>>(a);
+  else imu_kernel<false><<<l.n_items, kImuThreads, 0, s>>>(a);
   return 1;
 }
 
@@ -703,9 +716,10 @@ int launch_probe_image(const VisualLaunch& l, const int32_t* orig_index, bool wa
   return 1;
 }
 
-__global__ void probe_imu_kernel(ImuArgs a, int want_jac, double* r, int32_t* sidx, double* J) {
+__global__ void probe_imu_kernel(ImuArgs a, const int32_t* orig_index, int want_jac, double* r, int32_t* sidx, double* J) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= a.obs.n) return;
+  const int out = orig_index[n];
   const longlong2 tn = a.obs.t_node[n];
   const double2 g0 = a.obs.ga[3 * n], g1 = a.obs.ga[3 * n + 1], g2 = a.obs.ga[3 * n + 2];
   const double gyro[3] = {g0.x, g0.y, g1.x}, accel[3] = {g1.y, g2.x, g2.y};
@@ -722,10 +736,10 @@ __global__ void probe_imu_kernel(ImuArgs a, int want_jac, double* r, int32_t* si
   if (want_jac) eval_imu<true, kPStride>(a.sp, a.rig, a.st.q, a.st.p, a.st.tab, s, u, gyro, accel, bias, o);
   else eval_imu<false, kPStride>(a.sp, a.rig, a.st.q, a.st.p, a.st.tab, s, u, gyro, accel, bias, o);
   atomicAdd(a.ne.cost, o.cost);
-  if (r) for (int k = 0; k < 6; ++k) r[6 * n + k] = o.r[k];
-  if (sidx) sidx[n] = s;
+  if (r) for (int k = 0; k < 6; ++k) r[6 * out + k] = o.r[k];
+  if (sidx) sidx[out] = s;
   if (!want_jac || !J) return;
-  double* Jo = J + size_t(n) * 156;
+  double* Jo = J + size_t(out) * 156;
   for (int k = 0; k < 4; ++k)
     for (int e = 0; e < 18; ++e) { Jo[k * 36 + e] = o.Jrot[k][e]; Jo[k * 36 + 18 + e] = o.Jpos[k][e]; }
   for (int k = 0; k < 3; ++k) {
@@ -733,10 +747,11 @@ __global__ void probe_imu_kernel(ImuArgs a, int want_jac, double* r, int32_t* si
   }
 }
 
-int launch_probe_imu(const ImuLaunch& l, bool want_jac, double* r, int32_t* s, double* J, cudaStream_t st) {
+int launch_probe_imu(const ImuLaunch& l, const int32_t* orig_index, bool want_jac, double* r, int32_t* s, double* J,
+                     cudaStream_t st) {
   if (l.obs.n <= 0) return 0;
-  ImuArgs a{l.obs, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal};
-  probe_imu_kernel<<<(l.obs.n + 63) / 64, 64, 0, st>>>(a, want_jac ? 1 : 0, r, s, J);
+  ImuArgs a{l.obs, l.items, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal};
+  probe_imu_kernel<<<(l.obs.n + 63) / 64, 64, 0, st>>>(a, orig_index, want_jac ? 1 : 0, r, s, J);
   return 1;
 }
 

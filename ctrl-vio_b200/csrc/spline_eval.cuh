@@ -461,7 +461,7 @@ CTVIO_HD void eval_imu(const SplineParams& sp, const RigParams& rig, const doubl
   M3 JrN[3], JI[3];  // Jr(-k delta), JrInv(d)
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    JrN[j] = right_jacobian(neg(phi[j]));
+    JrN[j] = right_jacobian_from_half(neg(phi[j]), E[j]);  // Jr(-k delta) from the half-angle values in E_j
 #pragma unroll
     for (int e = 0; e < 9; ++e) JI[j].m[e] = tab[s + j].jrinv[e];
   }

@@ -1,0 +1,24 @@
+"""debug: phase timing of CTA 0 inside chol_coop_kernel (needs a CTVIO_CHOL_TIMING build)."""
+import ctypes as C, importlib, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pkg = importlib.import_module("ctrl-vio_b200"); syn = pkg.synthetic
+for name in ("c2", "c4"):
+    w = syn.config_c2() if name == "c2" else syn.config_c4()
+    est = pkg.setup_estimator(pkg.load(), w)
+    est.Solve(2)
+    buf = (C.c_ulonglong * 512)()
+    pkg.load().lib.ctvio_debug_chol_stamps(buf, 512)
+    t = np.array(buf[:], dtype=np.float64)
+    nb = (6 * w.n_knots + 6 * len(w.kf_times) + 1 + 63) // 64
+    print(name, "nb", nb)
+    i = 0
+    print(" init+sync %.1f us" % ((t[1] - t[0]) / 1e3)); i = 1
+    for k in range(nb):
+        load = t[i + 1] - t[i]; fact = t[i + 2] - t[i + 1]; slab = t[i + 3] - t[i + 2]
+        if k == nb - 1:
+            print(f" step {k}: load {load/1e3:.1f} factor+inv {fact/1e3:.1f} slab/xk {slab/1e3:.1f}"); i += 3; break
+        s1 = t[i + 4] - t[i + 3]; upd = t[i + 5] - t[i + 4]; s2 = t[i + 6] - t[i + 5]
+        print(f" step {k}: load {load/1e3:.1f} factor+inv {fact/1e3:.1f} slab {slab/1e3:.1f} sync1 {s1/1e3:.1f} update {upd/1e3:.1f} sync2 {s2/1e3:.1f}")
+        i += 6
+    print(" backward %.1f us, total %.1f us" % ((t[i + 1] - t[i]) / 1e3, (t[i + 1] - t[0]) / 1e3))
