@@ -100,7 +100,7 @@ ABI_SYMBOLS = [
     "solve", "gauge_realign", "marginalize", "get_prior", "adopt_prior",
     "save_state", "restore_state",
     "eval_image_factors", "eval_imu_factors", "eval_cost", "normal_equations",
-    "query_trajectory", "profile_kernels", "nccl_unique_id", "comm_init",
+    "query_trajectory", "profile_kernels", "measure_fp64_tflops", "nccl_unique_id", "comm_init",
 ]
 
 
@@ -362,6 +362,11 @@ class Estimator:
         self.lib.call("profile_kernels", self.h, C.c_int32(reps), C.c_int32(int(flush_l2)), _dp(out))
         names = ["visual", "imu", "small", "reduced_schur", "cholesky_solve", "step_vectors", "apply_table", "visual_cost"]
         return dict(zip(names, out.tolist()))
+
+    def MeasureFp64Tflops(self):
+        v = C.c_double()
+        self.lib.call("measure_fp64_tflops", self.h, C.byref(v))
+        return v.value
 
     # --- multi-GPU -----------------------------------------------------------------
     def NcclUniqueId(self) -> bytes:

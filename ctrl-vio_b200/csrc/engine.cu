@@ -1211,6 +1211,15 @@ int ctvio_profile_kernels(ctvio_handle e, int32_t reps, int32_t flush_l2, double
   return CTVIO_OK;
 }
 
+int ctvio_measure_fp64_tflops(ctvio_handle e, double* tflops) {
+  if (!e || !tflops) return fail(CTVIO_ERR_INVALID, "null argument");
+  cudaSetDevice(e->cfg.device);
+  const double v = ctvio::measure_fp64_tflops(e->stream);
+  if (v < 0) return fail(CTVIO_ERR_CUDA, "fp64 micro-benchmark failed");
+  *tflops = v;
+  return CTVIO_OK;
+}
+
 // ---- marginalization (K7), see marginalize.cu ---------------------------------------------------
 int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
   if (!e || !n_out || !nb_out) return fail(CTVIO_ERR_INVALID, "null argument");

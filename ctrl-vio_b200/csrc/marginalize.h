@@ -35,6 +35,9 @@ int launch_gram(const double* J, int rows, int cols, double* G, cudaStream_t s);
 // scal->gd = gc . dc + gl . dl  (directional derivative of the cost along the step, candidate buffers)
 int launch_dot_gradient(const LinearLaunch& a, cudaStream_t s);
 
+// measured fp64 FMA throughput of the current device (TFLOP/s); < 0 on error
+double measure_fp64_tflops(cudaStream_t s);
+
 bool comm_unique_id(uint8_t* id128, std::string* err);
 void* comm_create(int rank, int world, const uint8_t* id128, std::string* err);
 void comm_destroy(void* comm);

@@ -41,4 +41,42 @@ int launch_dot_gradient(const LinearLaunch& a, cudaStream_t s) {
   return 1;
 }
 
+// fp64 FMA micro-benchmark: 8 independent DFMA chains per thread, enough CTAs to fill every SM.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 1.0000001, c = 1e-9 * threadIdx.x;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+double measure_fp64_tflops(cudaStream_t s) {
+  int dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int ctas = n_sm * 8, iters = 1 << 15;
+  double* out = nullptr;
+  if (cudaMalloc(&out, size_t(ctas) * 256 * sizeof(double)) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, s);
+    fp64_peak_kernel<<<ctas, 256, 0, s>>>(out, iters, 1.0 + rep);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  const double flops = 2.0 * 8.0 * double(iters) * double(ctas) * 256.0;
+  return flops / (best * 1e-3) / 1e12;
+}
+
 }  // namespace ctvio

@@ -213,6 +213,9 @@ int ctvio_query_trajectory(ctvio_handle h, int32_t n, const int64_t* t, double* 
  *   out_ms[4] blocked Cholesky + triangular solves (K5)          out_ms[5] step vectors / back-substitution (K6)
  *   out_ms[6] apply step + knot-pair table (K6/K0)               out_ms[7] cost-only visual kernel */
 int ctvio_profile_kernels(ctvio_handle h, int32_t reps, int32_t flush_l2, double* out_ms8);
+/* fp64 FMA micro-benchmark (8 independent DFMA chains per thread, all SMs): measured TFLOP/s, the compute
+ * roofline denominator of the fp64-bound kernels (MEASURED_PEAKS.json has only HBM and bf16). */
+int ctvio_measure_fp64_tflops(ctvio_handle h, double* tflops);
 
 /* ---- multi-GPU: landmark-sharded residuals, one allreduce of the reduced system per LM step ----
  * Every rank holds the full (replicated) state and its own shard of image factors; rank 0 also holds

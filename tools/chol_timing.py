@@ -3,6 +3,7 @@ import ctypes as C, importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("ctrl-vio_b200"); syn = pkg.synthetic
+print("fp64 peak TFLOP/s:", pkg.setup_estimator(pkg.load(), syn.config_c1()).MeasureFp64Tflops())
 for name in ("c2", "c4"):
     w = syn.config_c2() if name == "c2" else syn.config_c4()
     est = pkg.setup_estimator(pkg.load(), w)
@@ -15,10 +16,14 @@ for name in ("c2", "c4"):
     i = 0
     print(" init+sync %.1f us" % ((t[1] - t[0]) / 1e3)); i = 1
     for k in range(nb):
-        load = t[i + 1] - t[i]; fact = t[i + 2] - t[i + 1]; slab = t[i + 3] - t[i + 2]
+        load = t[i + 1] - t[i]
+        f = [t[i + 2 + j] - t[i + 1 + j] for j in range(7)]  # main loop, 4x4 inverses, 4 merge levels, tail
+        i += 6
+        fact = sum(f); slab = t[i + 3] - t[i + 2]
+        detail = " ".join(f"{v/1e3:.1f}" for v in f)
         if k == nb - 1:
-            print(f" step {k}: load {load/1e3:.1f} factor+inv {fact/1e3:.1f} slab/xk {slab/1e3:.1f}"); i += 3; break
+            print(f" step {k}: load {load/1e3:.1f} factor+inv {fact/1e3:.1f} [{detail}] slab/xk {slab/1e3:.1f}"); i += 3; break
         s1 = t[i + 4] - t[i + 3]; upd = t[i + 5] - t[i + 4]; s2 = t[i + 6] - t[i + 5]
-        print(f" step {k}: load {load/1e3:.1f} factor+inv {fact/1e3:.1f} slab {slab/1e3:.1f} sync1 {s1/1e3:.1f} update {upd/1e3:.1f} sync2 {s2/1e3:.1f}")
+        print(f" step {k}: load {load/1e3:.1f} factor+inv {fact/1e3:.1f} [{detail}] slab {slab/1e3:.1f} sync1 {s1/1e3:.1f} update {upd/1e3:.1f} sync2 {s2/1e3:.1f}")
         i += 6
     print(" backward %.1f us, total %.1f us" % ((t[i + 1] - t[i]) / 1e3, (t[i + 1] - t[0]) / 1e3))
