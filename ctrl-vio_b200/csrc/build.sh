@@ -3,7 +3,7 @@
 set -euo pipefail
 cd "$(dirname "$0")"
 OUT=libctvio_b200.so
-SRCS="engine.cu kernels_residual.cu kernels_linear.cu chol_coop.cu misc_kernels.cu comm.cu"
+SRCS="engine.cu kernels_residual.cu kernels_linear.cu chol_coop.cu misc_kernels.cu marginalize.cu comm.cu"
 HDRS="kernels.h spline_eval.cuh device_math.cuh marginalize.h poly_min.h ../../include/ctvio.h"
 if [[ -z "${CTVIO_FORCE_BUILD:-}" && -f "$OUT" ]]; then
   newer=0

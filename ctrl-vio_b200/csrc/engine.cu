@@ -108,6 +108,7 @@ struct ctvio_engine {
   DevBuf<VisualItem> d_items;
   int n_items = 0;
   std::vector<int32_t> img_order;  // sorted position -> original index
+  std::vector<int32_t> imu_order;
   DevBuf<longlong2> d_imu_t;
   DevBuf<double2> d_imu_ga;
   DevBuf<ImuItem> d_imu_items;
@@ -297,7 +298,9 @@ int prepare(ctvio_engine* e) {
     std::vector<longlong2> it(ni);
     std::vector<double2> iga(3 * size_t(ni));
     const int64_t maxt = e->cfg.t0_ns + int64_t(e->nK - 3) * e->cfg.dt_ns;
-    std::vector<int32_t> imu_order(ni), imu_s(ni);
+    std::vector<int32_t>& imu_order = e->imu_order;
+    imu_order.assign(ni, 0);
+    std::vector<int32_t> imu_s(ni);
     for (int k = 0; k < ni; ++k) {
       const HostImu& o = e->imu[k];
       if (o.t < e->cfg.t0_ns || o.t >= maxt) return fail(CTVIO_ERR_TIME_RANGE, "imu time outside the spline");
@@ -1225,7 +1228,205 @@ int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
   if (!e || !n_out || !nb_out) return fail(CTVIO_ERR_INVALID, "null argument");
   *n_out = 0;
   *nb_out = 0;
-  return fail(CTVIO_ERR_STATE, "ctvio_marginalize: GPU marginalization is not built into this library yet");
+  cudaSetDevice(e->cfg.device);
+  e->new_prior = ctvio::PriorHost();
+  if (!e->opt.is_marg_state) return CTVIO_OK;
+  int rc = prepare(e);
+  if (rc) return rc;
+  ensure_table(e);
+  cudaStream_t st = e->stream;
+  const ProblemDims d = e->dims();
+  const int later = e->opt.ctrl_to_be_opt_later, nowk = e->opt.ctrl_to_be_opt_now;
+  const bool drop_knots = later > nowk;  // trajectory_estimator.cpp:161
+
+  // ---- which parameter blocks the recorded factors touch, and which of them are dropped ----
+  // block key order == position order: knots (rot, pos per knot), bias nodes (bg, ba), line delay, inverse depths
+  struct Key {
+    int type, index;
+    bool operator<(const Key& o) const {
+      auto rank = [](const Key& k) {
+        switch (k.type) {
+          case CTVIO_BLK_ROT: return std::make_pair(0, 2 * k.index);
+          case CTVIO_BLK_POS: return std::make_pair(0, 2 * k.index + 1);
+          case CTVIO_BLK_BG: return std::make_pair(1, 2 * k.index);
+          case CTVIO_BLK_BA: return std::make_pair(1, 2 * k.index + 1);
+          case CTVIO_BLK_LD: return std::make_pair(2, 0);
+          default: return std::make_pair(3, k.index);
+        }
+      };
+      return rank(*this) < rank(o);
+    }
+  };
+  struct Info { bool dropped = false; int pos = -1; };
+  std::map<Key, Info> blocks;
+  auto touch = [&](int type, int index, bool drop) { Info& b = blocks[Key{type, index}]; b.dropped = b.dropped || drop; };
+  bool use_prior = false;
+  if (e->prior.n > 0) {  // [1] old prior (trajectory_manager.cpp:166-203)
+    auto is_drop = [&](size_t b) {
+      const int t = e->prior.type[b], i = e->prior.index[b];
+      const bool isknot = t == CTVIO_BLK_ROT || t == CTVIO_BLK_POS;
+      return (isknot && i >= nowk && i < later) || ((t == CTVIO_BLK_BG || t == CTVIO_BLK_BA) && i == 0);
+    };
+    for (size_t b = 0; b < e->prior.type.size(); ++b) use_prior = use_prior || is_drop(b);
+    if (use_prior)
+      for (size_t b = 0; b < e->prior.type.size(); ++b) touch(e->prior.type[b], e->prior.index[b], is_drop(b));
+  }
+  std::vector<int32_t> marg_img, marg_imu;
+  for (size_t k = 0; k < e->img_order.size(); ++k) {  // [2] image factors (trajectory_estimator.cpp:325-331)
+    const HostImage& o = e->img[e->img_order[k]];
+    if (!o.marg) continue;
+    marg_img.push_back(int32_t(k));
+    int f0, l0, f1, l1;
+    knot_window(e, o.ti, f0, l0);
+    knot_window(e, o.tj, f1, l1);
+    for (int side = 0; side < 2; ++side)
+      for (int kk = (side ? f1 : f0); kk <= (side ? l1 : l0); ++kk) {
+        touch(CTVIO_BLK_ROT, kk, drop_knots && kk < later);
+        touch(CTVIO_BLK_POS, kk, drop_knots && kk < later);
+      }
+    touch(CTVIO_BLK_RHO, o.lm, true);
+    touch(CTVIO_BLK_LD, 0, false);
+  }
+  for (size_t k = 0; k < e->imu_order.size(); ++k) {  // [3] IMU factors (:249-257)
+    const HostImu& o = e->imu[e->imu_order[k]];
+    if (!o.marg) continue;
+    marg_imu.push_back(int32_t(k));
+    const int s = knot_window_first(e, o.t);
+    for (int kk = s; kk <= s + 3; ++kk) {
+      touch(CTVIO_BLK_ROT, kk, drop_knots && kk < later);
+      touch(CTVIO_BLK_POS, kk, drop_knots && kk < later);
+    }
+    touch(CTVIO_BLK_BG, o.node, true);
+    touch(CTVIO_BLK_BA, o.node, true);
+  }
+  std::vector<int2> bij;
+  std::vector<double> bs;
+  for (const HostBias& o : e->biasf) {  // [4] bias factors (:280-285), drop {bg_i, ba_i}
+    if (!o.marg) continue;
+    bij.push_back(make_int2(o.i, o.j));
+    for (int c = 0; c < 6; ++c) bs.push_back(o.s[c]);
+    touch(CTVIO_BLK_BG, o.i, true); touch(CTVIO_BLK_BG, o.j, false);
+    touch(CTVIO_BLK_BA, o.i, true); touch(CTVIO_BLK_BA, o.j, false);
+  }
+  if (blocks.empty()) return CTVIO_OK;
+  auto local_size = [](int t) { return (t == CTVIO_BLK_LD || t == CTVIO_BLK_RHO) ? 1 : 3; };
+  int pos = 0;
+  for (auto& kv : blocks) if (kv.second.dropped) { kv.second.pos = pos; pos += local_size(kv.first.type); }
+  const int m = pos;
+  for (auto& kv : blocks) if (!kv.second.dropped) { kv.second.pos = pos; pos += local_size(kv.first.type); }
+  const int n = pos - m, P = pos;
+  if (n <= 0) return CTVIO_OK;  // the reference hands back nullptr (trajectory_estimator.cpp:198-201)
+
+  std::vector<int32_t> pos_cam(d.np, -1), pos_lm(std::max(e->nL, 1), -1), prior_pos(std::max(e->prior.n, 1), -1);
+  for (const auto& kv : blocks) {
+    if (kv.first.type == CTVIO_BLK_RHO) { pos_lm[kv.first.index] = kv.second.pos; continue; }
+    const int g = ctvio::prior_block_base(kv.first.type, kv.first.index, d.nK, d.nB);
+    if (g < 0) return fail(CTVIO_ERR_INVALID, "marginalization block index out of range");
+    for (int c = 0; c < local_size(kv.first.type); ++c) pos_cam[g + c] = kv.second.pos + c;
+  }
+  if (use_prior)
+    for (size_t b = 0; b < e->prior.type.size(); ++b) {
+      const int p0 = blocks[Key{e->prior.type[b], e->prior.index[b]}].pos;
+      for (int c = 0; c < local_size(e->prior.type[b]); ++c) prior_pos[e->prior.col[b] + c] = p0 + c;
+    }
+
+  // ---- A, b on the device ----
+  DevBuf<int32_t> d_pos_cam, d_pos_lm, d_prior_pos, d_marg_img, d_marg_imu;
+  DevBuf<int2> d_bij;
+  DevBuf<double> d_bs, d_A, d_b;
+  CUDA_OK(d_pos_cam.upload(pos_cam, st));
+  CUDA_OK(d_pos_lm.upload(pos_lm, st));
+  CUDA_OK(d_prior_pos.upload(prior_pos, st));
+  CUDA_OK(d_marg_img.upload(marg_img, st));
+  CUDA_OK(d_marg_imu.upload(marg_imu, st));
+  CUDA_OK(d_bij.upload(bij, st));
+  CUDA_OK(d_bs.upload(bs, st));
+  CUDA_OK(d_A.reserve(size_t(P) * P));
+  CUDA_OK(d_b.reserve(P));
+  CUDA_OK(cudaMemsetAsync(d_A.p, 0, size_t(P) * P * sizeof(double), st));
+  CUDA_OK(cudaMemsetAsync(d_b.p, 0, size_t(P) * sizeof(double), st));
+  {
+    ctvio::MargImageArgs a;
+    a.obs = ImageObsPtrs{e->d_img_t.p, e->d_img_pi.p, e->d_img_pj.p, e->d_img_meta.p, int32_t(e->img.size())};
+    a.marg_index = d_marg_img.p; a.n_marg = int32_t(marg_img.size());
+    a.st = e->x[e->cur].ptrs(); a.sp = e->sp; a.rig = e->rig; a.cauchy = e->cfg.cauchy_marg;
+    a.pos_cam = d_pos_cam.p; a.pos_lm = d_pos_lm.p; a.idx_ld = d.idx_ld;
+    a.A = d_A.p; a.b = d_b.p; a.P = P; a.scal = e->d_scal.p;
+    e->launches += ctvio::launch_marg_image(a, st);
+    ctvio::MargImuArgs b;
+    b.obs = ImuObsPtrs{e->d_imu_t.p, e->d_imu_ga.p, int32_t(e->imu.size())};
+    b.marg_index = d_marg_imu.p; b.n_marg = int32_t(marg_imu.size());
+    b.st = a.st; b.sp = e->sp; b.rig = e->rig; b.pos_cam = d_pos_cam.p; b.idx_bias0 = d.idx_bias0;
+    b.A = d_A.p; b.b = d_b.p; b.P = P; b.scal = e->d_scal.p;
+    e->launches += ctvio::launch_marg_imu(b, st);
+    ctvio::MargSmallArgs c;
+    c.bf_ij = d_bij.p; c.bf_s = d_bs.p; c.n_bias = int32_t(bij.size());
+    c.prior = prior_ptrs(e); c.use_prior = use_prior ? 1 : 0; c.prior_pos = d_prior_pos.p;
+    c.st = a.st; c.pos_cam = d_pos_cam.p; c.idx_bias0 = d.idx_bias0; c.A = d_A.p; c.b = d_b.p; c.P = P;
+    e->launches += ctvio::launch_marg_small(c, st);
+  }
+  // ---- dense Schur complement through eigen-decompositions (marginalization_factor.cpp:240-263) ----
+  const double eps = 1e-30;
+  DevBuf<double> d_Amm, d_V, d_ev, d_Vs, d_Ainv, d_T, d_Ap, d_bp, d_Ap2, d_V2, d_ev2, d_vb, d_J, d_r;
+  CUDA_OK(d_Ap.reserve(size_t(n) * n));
+  CUDA_OK(d_bp.reserve(n));
+  CUDA_OK(cudaMemcpy2DAsync(d_Ap.p, size_t(n) * sizeof(double), d_A.p + size_t(m) * P + m, size_t(P) * sizeof(double),
+                            size_t(n) * sizeof(double), n, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(d_bp.p, d_b.p + m, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (m > 0) {
+    CUDA_OK(d_Amm.reserve(size_t(m) * m)); CUDA_OK(d_V.reserve(size_t(m) * m)); CUDA_OK(d_ev.reserve(m));
+    CUDA_OK(d_Vs.reserve(size_t(m) * m)); CUDA_OK(d_Ainv.reserve(size_t(m) * m)); CUDA_OK(d_T.reserve(size_t(n) * m));
+    e->launches += ctvio::launch_marg_elementwise(0, m, P, d_A.p, d_Amm.p, nullptr, nullptr, nullptr, eps, st);
+    e->launches += ctvio::launch_jacobi_eig(d_Amm.p, d_V.p, d_ev.p, m, st);
+    e->launches += ctvio::launch_marg_elementwise(1, m, m, d_V.p, d_Vs.p, d_ev.p, nullptr, nullptr, eps, st);
+    e->launches += ctvio::launch_dense_gemm(m, m, m, 1.0, d_Vs.p, m, false, d_V.p, m, true, 0.0, d_Ainv.p, m, st);
+    // T = Arm * Amm_inv ; A' = Arr - T * Amr ; b' = brr - T * bmm
+    e->launches += ctvio::launch_dense_gemm(n, m, m, 1.0, d_A.p + size_t(m) * P, P, false, d_Ainv.p, m, false, 0.0, d_T.p, m, st);
+    e->launches += ctvio::launch_dense_gemm(n, n, m, -1.0, d_T.p, m, false, d_A.p + m, P, false, 1.0, d_Ap.p, n, st);
+    e->launches += ctvio::launch_dense_gemm(n, 1, m, -1.0, d_T.p, m, false, d_b.p, 1, false, 1.0, d_bp.p, 1, st);
+  }
+  CUDA_OK(d_Ap2.reserve(size_t(n) * n)); CUDA_OK(d_V2.reserve(size_t(n) * n)); CUDA_OK(d_ev2.reserve(n));
+  CUDA_OK(d_vb.reserve(n)); CUDA_OK(d_J.reserve(size_t(n) * n)); CUDA_OK(d_r.reserve(n));
+  e->launches += ctvio::launch_marg_elementwise(2, n, n, d_Ap.p, d_Ap2.p, nullptr, nullptr, nullptr, eps, st);
+  e->launches += ctvio::launch_jacobi_eig(d_Ap2.p, d_V2.p, d_ev2.p, n, st);
+  e->launches += ctvio::launch_dense_gemm(n, 1, n, 1.0, d_V2.p, n, true, d_bp.p, 1, false, 0.0, d_vb.p, 1, st);
+  e->launches += ctvio::launch_marg_elementwise(3, n, n, d_V2.p, d_J.p, d_ev2.p, d_vb.p, d_r.p, eps, st);
+  rc = read_scalars(e);
+  if (rc) return rc;
+
+  // ---- the new prior: kept blocks with the current state as linearisation point ----
+  ctvio::PriorHost& np_ = e->new_prior;
+  np_.n = n;
+  np_.J.resize(size_t(n) * n);
+  np_.r.resize(n);
+  CUDA_OK(cudaMemcpy(np_.J.data(), d_J.p, np_.J.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(np_.r.data(), d_r.p, np_.r.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<double> hq(4 * size_t(e->nK)), hp(kPStride * size_t(e->nK)), hb(6 * size_t(std::max(e->nB, 1)));
+  double hld = 0;
+  CUDA_OK(cudaMemcpy(hq.data(), e->x[e->cur].q.p, hq.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(hp.data(), e->x[e->cur].p.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (e->nB) CUDA_OK(cudaMemcpy(hb.data(), e->x[e->cur].bias.p, 6 * size_t(e->nB) * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(&hld, e->x[e->cur].ld.p, sizeof(double), cudaMemcpyDeviceToHost));
+  for (const auto& kv : blocks) {
+    if (kv.second.dropped) continue;
+    np_.type.push_back(kv.first.type);
+    np_.index.push_back(kv.first.index);
+    np_.col.push_back(kv.second.pos - m);
+    double x0[4] = {0, 0, 0, 0};
+    const int i = kv.first.index;
+    switch (kv.first.type) {
+      case CTVIO_BLK_ROT: for (int c = 0; c < 4; ++c) x0[c] = hq[4 * i + c]; break;
+      case CTVIO_BLK_POS: for (int c = 0; c < 3; ++c) x0[c] = hp[kPStride * i + c]; break;
+      case CTVIO_BLK_BG: for (int c = 0; c < 3; ++c) x0[c] = hb[6 * i + c]; break;
+      case CTVIO_BLK_BA: for (int c = 0; c < 3; ++c) x0[c] = hb[6 * i + 3 + c]; break;
+      case CTVIO_BLK_LD: x0[0] = hld; break;
+      default: break;
+    }
+    for (int c = 0; c < 4; ++c) np_.x0.push_back(x0[c]);
+  }
+  *n_out = n;
+  *nb_out = int32_t(np_.type.size());
+  return CTVIO_OK;
 }
 int ctvio_get_prior(ctvio_handle e, double* J, double* r, int32_t* type, int32_t* index, int32_t* col, double* x0) {
   if (!e) return fail(CTVIO_ERR_INVALID, "null handle");

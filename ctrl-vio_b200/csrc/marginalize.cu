@@ -1,0 +1,347 @@
+// K7: marginalization on the GPU.  Replaces MarginalizationInfo::preMarginalize / marginalize
+// (factor/analytic_diff/marginalization_factor.cpp:106-265): evaluate every recorded factor at the current
+// state (image factors with the loss corrector), build the dense A = sum J'J, b = sum J'r over
+// [dropped | kept] parameter positions, Schur-complement the dropped block through its eigen-decomposition
+// (pseudo-inverse with eps = 1e-30, marginalization_factor.h:129) and factor the result into
+// (J_lin, r_lin) by a second eigen-decomposition.
+// The reference sums A on 4 pthreads (ThreadsConstructA, :141-176); here one thread per factor reduces with
+// fp64 atomics, the two eigen-decompositions run as a parallel (round-robin ordered) cyclic Jacobi solver in
+// one CTA, and the dense products are plain tiled kernels — this runs once per window, not per LM step.
+#include "marginalize.h"
+
+namespace ctvio {
+
+// ------------------------------------------------------------------------------------------------
+// recorded image / IMU factors -> A, b
+
+__global__ void marg_image_kernel(MargImageArgs a) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= a.n_marg) return;
+  const int n = a.marg_index[m];
+  const longlong2 tt = a.obs.t[n];
+  const double2 pi = a.obs.pi[n], pj = a.obs.pj[n];
+  const int4 meta = a.obs.meta[n];
+  const double rho = a.st.rho[meta.z];
+  const int64_t ld_ns = int64_t(*a.st.ld * 1e9);
+  int32_t si, sj;
+  double ui, uj;
+  if (!spline_index(a.sp, tt.x + int64_t(meta.x) * ld_ns, si, ui) ||
+      !spline_index(a.sp, tt.y + int64_t(meta.y) * ld_ns, sj, uj)) {
+    atomicOr(&a.scal->error_flags, 1);
+    return;
+  }
+  SideEval ea, eb;
+  eval_side<true, kPStride>(a.sp, a.st.q, a.st.p, a.st.tab, si, ui, ea);
+  eval_side<true, kPStride>(a.sp, a.st.q, a.st.p, a.st.tab, sj, uj, eb);
+  ImageCommon cm;
+  const double pixy[2] = {pi.x, pi.y}, pjxy[2] = {pj.x, pj.y};
+  image_common(a.rig, pixy, pjxy, rho, ea.R, ea.p, eb.R, eb.p, a.cauchy, cm);
+  // local Jacobian: 2 x 50 (+ positions)
+  double J0[50], J1[50];
+  int pos[50];
+  {
+    double rot[4][6], posb[4][6];
+    image_side_blocks(0, cm, ea, rot, posb);
+    for (int k = 0; k < 4; ++k)
+      for (int c = 0; c < 3; ++c) {
+        J0[k * 6 + c] = rot[k][c]; J1[k * 6 + c] = rot[k][3 + c];
+        J0[k * 6 + 3 + c] = posb[k][c]; J1[k * 6 + 3 + c] = posb[k][3 + c];
+        pos[k * 6 + c] = a.pos_cam[6 * (si + k) + c];
+        pos[k * 6 + 3 + c] = a.pos_cam[6 * (si + k) + 3 + c];
+      }
+    image_side_blocks(1, cm, eb, rot, posb);
+    for (int k = 0; k < 4; ++k)
+      for (int c = 0; c < 3; ++c) {
+        J0[24 + k * 6 + c] = rot[k][c]; J1[24 + k * 6 + c] = rot[k][3 + c];
+        J0[24 + k * 6 + 3 + c] = posb[k][c]; J1[24 + k * 6 + 3 + c] = posb[k][3 + c];
+        pos[24 + k * 6 + c] = a.pos_cam[6 * (sj + k) + c];
+        pos[24 + k * 6 + 3 + c] = a.pos_cam[6 * (sj + k) + 3 + c];
+      }
+  }
+  double t2[2];
+  image_jrho(a.rig, cm, ea.R, rho, t2);
+  J0[48] = t2[0]; J1[48] = t2[1]; pos[48] = a.pos_lm[meta.z];
+  image_jld(a.rig, cm, meta.x, meta.y, ea.R, ea.omega, ea.vel, eb.R, eb.omega, eb.vel, t2);
+  J0[49] = t2[0]; J1[49] = t2[1]; pos[49] = a.pos_cam[a.idx_ld];
+  const int P = a.P;
+  for (int x = 0; x < 50; ++x) {
+    if (pos[x] < 0) continue;
+    atomicAdd(a.b + pos[x], J0[x] * cm.r[0] + J1[x] * cm.r[1]);
+    for (int y = 0; y < 50; ++y) {
+      if (pos[y] < 0) continue;
+      const double h = J0[x] * J0[y] + J1[x] * J1[y];
+      if (h != 0.0) atomicAdd(a.A + size_t(pos[x]) * P + pos[y], h);
+    }
+  }
+}
+
+__global__ void marg_imu_kernel(MargImuArgs a) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= a.n_marg) return;
+  const int n = a.marg_index[m];
+  const longlong2 tn = a.obs.t_node[n];
+  const double2 g0 = a.obs.ga[3 * n], g1 = a.obs.ga[3 * n + 1], g2 = a.obs.ga[3 * n + 2];
+  const double gyro[3] = {g0.x, g0.y, g1.x}, accel[3] = {g1.y, g2.x, g2.y};
+  const int node = int(tn.y);
+  double bias[6];
+  for (int c = 0; c < 6; ++c) bias[c] = a.st.bias[6 * node + c];
+  int32_t s;
+  double u;
+  if (!spline_index(a.sp, tn.x, s, u)) {
+    atomicOr(&a.scal->error_flags, 1);
+    return;
+  }
+  ImuEvalOut o;
+  eval_imu<true, kPStride>(a.sp, a.rig, a.st.q, a.st.p, a.st.tab, s, u, gyro, accel, bias, o);
+  const int P = a.P;
+  // 30 local columns: 4 knots x (rot 3 | pos 3), bg 3, ba 3
+  for (int x = 0; x < 30; ++x) {
+    const int px = x < 24 ? a.pos_cam[6 * (s + x / 6) + x % 6] : a.pos_cam[a.idx_bias0 + 6 * node + (x - 24)];
+    if (px < 0) continue;
+    double jx[6];
+    for (int r = 0; r < 6; ++r)
+      jx[r] = x < 24 ? ((x % 6) < 3 ? o.Jrot[x / 6][3 * r + x % 6] : o.Jpos[x / 6][3 * r + x % 6 - 3])
+                     : ((x - 24) == r ? a.rig.imu_info[r] : 0.0);
+    double g = 0;
+    for (int r = 0; r < 6; ++r) g += jx[r] * o.r[r];
+    atomicAdd(a.b + px, g);
+    for (int y = 0; y < 30; ++y) {
+      const int py = y < 24 ? a.pos_cam[6 * (s + y / 6) + y % 6] : a.pos_cam[a.idx_bias0 + 6 * node + (y - 24)];
+      if (py < 0) continue;
+      double h = 0;
+      for (int r = 0; r < 6; ++r) {
+        const double jy = y < 24 ? ((y % 6) < 3 ? o.Jrot[y / 6][3 * r + y % 6] : o.Jpos[y / 6][3 * r + y % 6 - 3])
+                                 : ((y - 24) == r ? a.rig.imu_info[r] : 0.0);
+        h += jx[r] * jy;
+      }
+      if (h != 0.0) atomicAdd(a.A + size_t(px) * P + py, h);
+    }
+  }
+}
+
+// bias factors flagged marg + the old prior (if recorded); one CTA
+__global__ void marg_small_kernel(MargSmallArgs a) {
+  const int tid = threadIdx.x;
+  const int P = a.P;
+  for (int n = tid; n < a.n_bias; n += blockDim.x) {
+    const int2 ij = a.bf_ij[n];
+    for (int k = 0; k < 6; ++k) {
+      const double s = a.bf_s[6 * n + k];
+      const double r = s * (a.st.bias[6 * ij.y + k] - a.st.bias[6 * ij.x + k]);
+      const int pi = a.pos_cam[a.idx_bias0 + 6 * ij.x + k], pj = a.pos_cam[a.idx_bias0 + 6 * ij.y + k];
+      if (pi >= 0) { atomicAdd(a.b + pi, -s * r); atomicAdd(a.A + size_t(pi) * P + pi, s * s); }
+      if (pj >= 0) { atomicAdd(a.b + pj, s * r); atomicAdd(a.A + size_t(pj) * P + pj, s * s); }
+      if (pi >= 0 && pj >= 0) { atomicAdd(a.A + size_t(pi) * P + pj, -s * s); atomicAdd(a.A + size_t(pj) * P + pi, -s * s); }
+    }
+  }
+  const int n = a.prior.n;
+  if (n <= 0 || !a.use_prior) return;
+  // residual of the old prior at the current state (dx / res scratch as in small_factors_kernel)
+  for (int b = tid; b < a.prior.n_blocks; b += blockDim.x) {
+    const int type = a.prior.type[b];
+    const int index = a.prior.index[b];
+    const double* x = type == 0 ? a.st.q + 4 * index : type == 1 ? a.st.p + kPStride * index
+                    : type == 2 ? a.st.bias + 6 * index : type == 3 ? a.st.bias + 6 * index + 3 : a.st.ld;
+    const double* x0 = a.prior.x0 + 4 * b;
+    double* dx = a.prior.dx + a.prior.col[b];
+    if (type == 0) {
+      const double n2 = x0[0] * x0[0] + x0[1] * x0[1] + x0[2] * x0[2] + x0[3] * x0[3];
+      const double ax = -x0[0] / n2, ay = -x0[1] / n2, az = -x0[2] / n2, aw = x0[3] / n2;
+      const double qx = aw * x[0] + ax * x[3] + ay * x[2] - az * x[1];
+      const double qy = aw * x[1] + ay * x[3] + az * x[0] - ax * x[2];
+      const double qz = aw * x[2] + az * x[3] + ax * x[1] - ay * x[0];
+      const double qw = aw * x[3] - ax * x[0] - ay * x[1] - az * x[2];
+      const double sg = (qw >= 0) ? 2.0 : -2.0;
+      dx[0] = sg * qx; dx[1] = sg * qy; dx[2] = sg * qz;
+    } else {
+      const int sz = type == 4 ? 1 : 3;
+      for (int d = 0; d < sz; ++d) dx[d] = x[d] - x0[d];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    double s = a.prior.r[i];
+    for (int j = 0; j < n; ++j) s = fma(a.prior.J[size_t(i) * n + j], a.prior.dx[j], s);
+    a.prior.res[i] = s;
+  }
+  __syncthreads();
+  // prior_pos[j]: position of prior column j in the new ordering
+  for (int j = tid; j < n; j += blockDim.x) {
+    const int pj = a.prior_pos[j];
+    if (pj < 0) continue;
+    double g = 0;
+    for (int i = 0; i < n; ++i) g = fma(a.prior.J[size_t(i) * n + j], a.prior.res[i], g);
+    atomicAdd(a.b + pj, g);
+  }
+  for (int e = tid; e < n * n; e += blockDim.x) {
+    const int x = e / n, y = e % n;
+    const int px = a.prior_pos[x], py = a.prior_pos[y];
+    if (px < 0 || py < 0) continue;
+    const double v = a.prior.JtJ[e];
+    if (v != 0.0) atomicAdd(a.A + size_t(px) * P + py, v);
+  }
+}
+
+int launch_marg_image(const MargImageArgs& a, cudaStream_t s) {
+  if (a.n_marg <= 0) return 0;
+  marg_image_kernel<<<(a.n_marg + 63) / 64, 64, 0, s>>>(a);
+  return 1;
+}
+int launch_marg_imu(const MargImuArgs& a, cudaStream_t s) {
+  if (a.n_marg <= 0) return 0;
+  marg_imu_kernel<<<(a.n_marg + 63) / 64, 64, 0, s>>>(a);
+  return 1;
+}
+int launch_marg_small(const MargSmallArgs& a, cudaStream_t s) {
+  if (a.n_bias <= 0 && !(a.use_prior && a.prior.n > 0)) return 0;
+  marg_small_kernel<<<1, 256, 0, s>>>(a);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// symmetric eigen-decomposition: parallel cyclic Jacobi, one CTA of 1024 threads, matrix in L2
+//   A (n x n, row-major, symmetric, overwritten), V (n x n) <- eigenvectors in columns, ev[n] <- diagonal
+// Pairs of one round come from the round-robin tournament schedule: n/2 disjoint rotations at once.
+
+__global__ void __launch_bounds__(1024) jacobi_eig_kernel(double* A, double* V, double* ev, int n, int max_sweeps) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* cs = reinterpret_cast<double*>(smem_raw);           // [npairs][2]
+  int* pp = reinterpret_cast<int*>(cs + 2 * ((n + 1) / 2));   // [npairs][2]
+  __shared__ double s_off, s_diag;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int ne = (n + 1) & ~1;  // even player count (a dummy player if n is odd)
+  const int npairs = ne / 2;
+  for (int e = tid; e < n * n; e += nt) V[e] = (e / n == e % n) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    // convergence: off-diagonal mass
+    if (tid == 0) { s_off = 0.0; s_diag = 0.0; }
+    __syncthreads();
+    double off = 0, dg = 0;
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e % n;
+      const double v = A[e];
+      if (i == j) dg += v * v; else off += v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      off += __shfl_xor_sync(0xffffffffu, off, o);
+      dg += __shfl_xor_sync(0xffffffffu, dg, o);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&s_off, off); atomicAdd(&s_diag, dg); }
+    __syncthreads();
+    if (s_off <= 1e-60 || s_off <= 1e-30 * s_diag) break;
+    for (int round = 0; round < ne - 1; ++round) {
+      // tournament pairing: player ne-1 fixed, the others rotate
+      for (int k = tid; k < npairs; k += nt) {
+        int p, q;
+        if (k == 0) { p = ne - 1; q = round % (ne - 1); }
+        else { p = (round + k) % (ne - 1); q = (round + ne - 1 - k) % (ne - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, s = 0.0;
+        if (q < n) {
+          const double apq = A[size_t(p) * n + q];
+          if (apq != 0.0) {
+            const double app = A[size_t(p) * n + p], aqq = A[size_t(q) * n + q];
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = 1.0 / sqrt(t * t + 1.0);
+            s = t * c;
+          }
+        }
+        cs[2 * k] = c; cs[2 * k + 1] = s;
+        pp[2 * k] = p; pp[2 * k + 1] = q;
+      }
+      __syncthreads();
+      // columns p,q of A and V:  X[:,p] = c X[:,p] - s X[:,q] ;  X[:,q] = s X[:,p] + c X[:,q]
+      for (int e = tid; e < npairs * n; e += nt) {
+        const int k = e / n, r = e % n;
+        const int p = pp[2 * k], q = pp[2 * k + 1];
+        if (q >= n) continue;
+        const double c = cs[2 * k], s = cs[2 * k + 1];
+        if (s == 0.0) continue;
+        const double ap = A[size_t(r) * n + p], aq = A[size_t(r) * n + q];
+        A[size_t(r) * n + p] = c * ap - s * aq;
+        A[size_t(r) * n + q] = s * ap + c * aq;
+        const double vp = V[size_t(r) * n + p], vq = V[size_t(r) * n + q];
+        V[size_t(r) * n + p] = c * vp - s * vq;
+        V[size_t(r) * n + q] = s * vp + c * vq;
+      }
+      __syncthreads();
+      // rows p,q of A
+      for (int e = tid; e < npairs * n; e += nt) {
+        const int k = e / n, col = e % n;
+        const int p = pp[2 * k], q = pp[2 * k + 1];
+        if (q >= n) continue;
+        const double c = cs[2 * k], s = cs[2 * k + 1];
+        if (s == 0.0) continue;
+        const double ap = A[size_t(p) * n + col], aq = A[size_t(q) * n + col];
+        A[size_t(p) * n + col] = c * ap - s * aq;
+        A[size_t(q) * n + col] = s * ap + c * aq;
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += nt) ev[i] = A[size_t(i) * n + i];
+}
+
+int launch_jacobi_eig(double* A, double* V, double* ev, int n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const size_t smem = size_t((n + 1) / 2) * (2 * sizeof(double) + 2 * sizeof(int));
+  jacobi_eig_kernel<<<1, 1024, smem, s>>>(A, V, ev, n, 60);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small dense helpers (naive tiles; sizes are a few hundred)
+
+// C (m x n) = alpha * op(A) * op(B) + beta * C ; row-major with leading dimensions
+__global__ void dense_gemm_kernel(int m, int n, int k, double alpha, const double* A, int lda, int ta, const double* B,
+                                  int ldb, int tb, double beta, double* C, int ldc) {
+  const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+  if (i >= m || j >= n) return;
+  double s = 0;
+  for (int x = 0; x < k; ++x) {
+    const double av = ta ? A[size_t(x) * lda + i] : A[size_t(i) * lda + x];
+    const double bv = tb ? B[size_t(j) * ldb + x] : B[size_t(x) * ldb + j];
+    s = fma(av, bv, s);
+  }
+  C[size_t(i) * ldc + j] = alpha * s + (beta != 0.0 ? beta * C[size_t(i) * ldc + j] : 0.0);
+}
+int launch_dense_gemm(int m, int n, int k, double alpha, const double* A, int lda, bool ta, const double* B, int ldb,
+                      bool tb, double beta, double* C, int ldc, cudaStream_t s) {
+  if (m <= 0 || n <= 0) return 0;
+  dim3 grid((n + 15) / 16, (m + 15) / 16), block(16, 16);
+  dense_gemm_kernel<<<grid, block, 0, s>>>(m, n, k, alpha, A, lda, ta ? 1 : 0, B, ldb, tb ? 1 : 0, beta, C, ldc);
+  return 1;
+}
+
+// mode 0: Amm = 0.5 (A[0:m,0:m] + A[0:m,0:m]')           (marginalization_factor.cpp:240)
+// mode 1: scale columns of V (m x m) by 1/ev where ev > eps, else 0  -> Vs   (:243-244)
+// mode 2: symmetrise from the lower triangle (Eigen's solver reads the lower triangle, :254)
+// mode 3: J_lin[k][i] = sqrt(S_k) V[i][k] ; r_lin[k] = sqrt(1/S_k) (V' b)[k] with S_k = ev_k > eps ? ev_k : 0  (:255-263)
+__global__ void marg_elementwise_kernel(int mode, int n, int ld, const double* src, double* dst, const double* ev,
+                                        const double* vb, double* rlin, double eps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int i = idx / n, j = idx % n;
+  if (mode == 0) {
+    dst[idx] = 0.5 * (src[size_t(i) * ld + j] + src[size_t(j) * ld + i]);
+  } else if (mode == 1) {
+    dst[idx] = ev[j] > eps ? src[idx] / ev[j] : 0.0;
+  } else if (mode == 2) {
+    dst[idx] = i >= j ? src[idx] : src[size_t(j) * n + i];
+  } else {
+    const int k = i;  // row of J_lin = eigen index
+    const double S = ev[k] > eps ? ev[k] : 0.0;
+    dst[idx] = sqrt(S) * src[size_t(j) * n + k];
+    if (j == 0) rlin[k] = S > 0.0 ? sqrt(1.0 / S) * vb[k] : 0.0;
+  }
+}
+int launch_marg_elementwise(int mode, int n, int ld, const double* src, double* dst, const double* ev, const double* vb,
+                            double* rlin, double eps, cudaStream_t s) {
+  if (n <= 0) return 0;
+  marg_elementwise_kernel<<<(n * n + 255) / 256, 256, 0, s>>>(mode, n, ld, src, dst, ev, vb, rlin, eps);
+  return 1;
+}
+
+}  // namespace ctvio

@@ -35,6 +35,61 @@ int launch_gram(const double* J, int rows, int cols, double* G, cudaStream_t s);
 // scal->gd = gc . dc + gl . dl  (directional derivative of the cost along the step, candidate buffers)
 int launch_dot_gradient(const LinearLaunch& a, cudaStream_t s);
 
+// ---- K7 marginalization (marginalize.cu) --------------------------------------------------------
+struct MargImageArgs {
+  ImageObsPtrs obs;
+  const int32_t* marg_index;  // positions (in the sorted observation arrays) of the recorded factors
+  int32_t n_marg;
+  StatePtrs st;
+  SplineParams sp;
+  RigParams rig;
+  double cauchy;              // CauchyLoss(1) for marginalized features (trajectory_estimator.cpp:321)
+  const int32_t* pos_cam;     // [np] camera dim -> position in [dropped | kept] ordering, -1 = not a block
+  const int32_t* pos_lm;      // [nL]
+  int32_t idx_ld;
+  double* A;                  // [P][P]
+  double* b;                  // [P]
+  int32_t P;
+  LmScalars* scal;
+};
+struct MargImuArgs {
+  ImuObsPtrs obs;
+  const int32_t* marg_index;
+  int32_t n_marg;
+  StatePtrs st;
+  SplineParams sp;
+  RigParams rig;
+  const int32_t* pos_cam;
+  int32_t idx_bias0;
+  double* A;
+  double* b;
+  int32_t P;
+  LmScalars* scal;
+};
+struct MargSmallArgs {
+  const int2* bf_ij;          // recorded bias factors only
+  const double* bf_s;
+  int32_t n_bias;
+  PriorPtrs prior;            // the old prior (dx / res scratch reused)
+  int32_t use_prior;
+  const int32_t* prior_pos;   // [prior.n] prior column -> position
+  StatePtrs st;
+  const int32_t* pos_cam;
+  int32_t idx_bias0;
+  double* A;
+  double* b;
+  int32_t P;
+};
+int launch_marg_image(const MargImageArgs& a, cudaStream_t s);
+int launch_marg_imu(const MargImuArgs& a, cudaStream_t s);
+int launch_marg_small(const MargSmallArgs& a, cudaStream_t s);
+// symmetric eigen-decomposition (parallel cyclic Jacobi): A overwritten, V <- eigenvectors (columns), ev <- eigenvalues
+int launch_jacobi_eig(double* A, double* V, double* ev, int n, cudaStream_t s);
+int launch_dense_gemm(int m, int n, int k, double alpha, const double* A, int lda, bool ta, const double* B, int ldb,
+                      bool tb, double beta, double* C, int ldc, cudaStream_t s);
+int launch_marg_elementwise(int mode, int n, int ld, const double* src, double* dst, const double* ev, const double* vb,
+                            double* rlin, double eps, cudaStream_t s);
+
 // measured fp64 FMA throughput of the current device (TFLOP/s); < 0 on error
 double measure_fp64_tflops(cudaStream_t s);
 

@@ -212,3 +212,71 @@ def test_time_outside_window_is_reported(cuda_lib):
     with pytest.raises(pkg.CtvioError) as ei:
         g.EvalCost()
     assert "-6" in str(ei.value)
+
+
+def _c3_window_a(lib):
+    seq = syn.config_c3_sequence()
+    wa = syn.subwindow(seq, 0, 10)
+    later = int((wa.kf_times[1] - wa.t0_ns) // wa.dt_ns)
+    nowk = int((wa.kf_times[0] - wa.t0_ns) // wa.dt_ns)
+    img_marg = (wa.anchor_frame[wa.lm] == 0).astype(np.int32)
+    imu_marg = (wa.imu_t < wa.kf_times[1]).astype(np.int32)
+    bias_marg = np.zeros(len(wa.bf_i), np.int32); bias_marg[0] = 1
+    opt = pkg.make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER, is_marg_state=True,
+                           ctrl_to_be_opt_now=nowk, ctrl_to_be_opt_later=later)
+    e = pkg.setup_estimator(lib, wa, image_marg=img_marg, imu_marg=imu_marg, bias_marg=bias_marg, options=opt)
+    return e, seq, wa, nowk
+
+
+def test_marginalization_matches_oracle(oracle_lib, cuda_lib):
+    """SaveMarginalizationInfo on the GPU (K7) vs the oracle at the same state; J_lin is only defined up to
+    an orthogonal factor (eigenvector signs / degenerate subspaces), so J'J and J'r are compared (SURVEY C-9)."""
+    g, seq, wa, nowk = _c3_window_a(cuda_lib)
+    o, _, _, _ = _c3_window_a(oracle_lib)
+    so = o.Solve(6)
+    q, p = o.GetKnots()
+    for e in (g,):  # put the GPU engine at exactly the oracle's state
+        e.SetKnots(q, p); e.SetBiases(o.GetBiases()); e.SetInvDepths(o.GetInvDepths()); e.SetLineDelay(o.GetLineDelay())
+    pg = g.SaveMarginalizationInfo()
+    po = o.SaveMarginalizationInfo()
+    assert pg is not None and po is not None and pg.n == po.n
+    assert np.array_equal(pg.blk_type, po.blk_type) and np.array_equal(pg.blk_index, po.blk_index)
+    assert np.array_equal(pg.blk_col, po.blk_col) and np.allclose(pg.blk_x0, po.blk_x0, atol=1e-15)
+    Ag, Ao = pg.J.T @ pg.J, po.J.T @ po.J
+    bg_, bo_ = pg.J.T @ pg.r, po.J.T @ po.r
+    sc = np.abs(Ao).max()
+    assert np.allclose(Ag, Ao, atol=1e-7 * sc), np.abs(Ag - Ao).max() / sc
+    assert np.allclose(bg_, bo_, atol=1e-7 * np.abs(bo_).max())
+
+
+def test_c3_sequence_solve_marginalize_slide_matches_oracle(oracle_lib, cuda_lib):
+    """BASELINE config 3: window A (free line delay) -> solve -> 4-DoF re-alignment -> marginalize keyframe 0 ->
+    window B with the resulting prior; both engines run the whole sequence themselves."""
+    finals = []
+    for lib in (cuda_lib, oracle_lib):
+        e, seq, wa, nowk = _c3_window_a(lib)
+        R0 = syn.qrot(wa.q0[nowk][None], np.eye(3)).T.copy(); t0 = wa.p0[nowk].copy()
+        sa = e.Solve(15)
+        e.GaugeRealign(nowk, R0, t0)
+        pr = e.SaveMarginalizationInfo()
+        assert pr is not None
+        isb = (pr.blk_type == pkg.BLK_BG) | (pr.blk_type == pkg.BLK_BA)
+        pr.blk_index[isb] -= 1   # bias node indices are window-relative: the window slides by one keyframe
+        wb = syn.subwindow(seq, 1, 11)
+        eb = pkg.setup_estimator(lib, wb, options=pkg.make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER))
+        q, p = e.GetKnots()
+        b = np.zeros((11, 6)); b[:10] = e.GetBiases()[1:]; b[10] = b[9]
+        rho = wb.rho0.copy()
+        ra = e.GetInvDepths()
+        ga = wa.meta["lm_global"]; gb = wb.meta["lm_global"]
+        common = np.intersect1d(ga, gb)
+        rho[np.searchsorted(gb, common)] = ra[np.searchsorted(ga, common)]
+        eb.SetKnots(q, p); eb.SetBiases(b); eb.SetInvDepths(rho); eb.SetLineDelay(e.GetLineDelay())
+        eb.AddMarginalizationFactor(pr)
+        sb = eb.Solve(15)
+        finals.append((sa, sb, get_state(eb), eb))
+    (sag, sbg, stg, eg), (sao, sbo, sto, eo) = finals
+    assert sag.iterations == sao.iterations and sbg.iterations == sbo.iterations
+    assert np.isclose(sbg.final_cost, sbo.final_cost, rtol=1e-6)
+    assert_state_parity(eg, eo)
+    assert 0 <= eg.GetLineDelay() <= syn.LD_UPPER
