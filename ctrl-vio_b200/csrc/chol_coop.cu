@@ -458,7 +458,7 @@ int launch_factor_solve(const LinearLaunch& a, cudaStream_t s) {
   double* Linv = a.Linv;
   const double* rhs = a.rhs;
   double* y = a.y;
-  double* yf = a.rhs + a.npad;  // rhs buffer is allocated with 2 * npad doubles
+  double* yf = a.yf;
   LmScalars* scal = a.scal;
   void* args[] = {&M, &npad, &Linv, &rhs, &y, &yf, &scal};
   cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_coop_kernel), dim3(grid), dim3(256), args, kCholCoopSmem, s);

@@ -132,7 +132,8 @@ struct ctvio_engine {
   size_t ne_slab_len = 0;
   size_t off_gc = 0, off_hl = 0, off_gl = 0, off_wld = 0, off_W = 0;
   // linear system
-  DevBuf<double> d_M, d_Linv, d_rhs, d_y, d_sc, d_sl, d_hh, d_dc, d_dl;
+  DevBuf<double> d_M, d_Linv, d_y, d_sc, d_sl, d_hh, d_dc, d_dl, d_rho_sync;
+  DevBuf<uint8_t> d_owned;
   int npad = 0;
   DevBuf<LmScalars> d_scal;
   LmScalars* h_scal = nullptr;  // pinned
@@ -353,9 +354,8 @@ int prepare(ctvio_engine* e) {
     e->ne_slab_len = e->off_W + size_t(e->h_woff[e->nL]);
     for (int b = 0; b < 2; ++b) CUDA_OK(e->ne_slab[b].reserve(e->ne_slab_len));
     e->npad = ((d.np + kCholNB - 1) / kCholNB) * kCholNB;
-    CUDA_OK(e->d_M.reserve(size_t(e->npad) * e->npad));
+    CUDA_OK(e->d_M.reserve(size_t(e->npad) * e->npad + 3 * size_t(e->npad)));  // M | rhs | diagA | yf (all-reduce slab)
     CUDA_OK(e->d_Linv.reserve(size_t(e->npad) * kCholNB));
-    CUDA_OK(e->d_rhs.reserve(2 * size_t(e->npad)));  // rhs | forward-solved vector
     CUDA_OK(e->d_y.reserve(e->npad));
     CUDA_OK(e->d_sc.reserve(np));
     CUDA_OK(e->d_sl.reserve(e->nL));
@@ -514,11 +514,41 @@ LinearLaunch linear_launch(ctvio_engine* e, int nb) {
   a.cmask = e->d_cmask.p;
   a.active = e->d_active.p;
   a.sc = e->d_sc.p; a.sl = e->d_sl.p;
-  a.M = e->d_M.p; a.Linv = e->d_Linv.p; a.rhs = e->d_rhs.p; a.y = e->d_y.p;
+  a.M = e->d_M.p; a.Linv = e->d_Linv.p; a.y = e->d_y.p;
+  a.rhs = e->d_M.p + size_t(e->npad) * e->npad;
+  a.diagA = a.rhs + e->npad;
+  a.yf = a.diagA + e->npad;
+  a.sharded = e->world > 1 ? 1 : 0;
   a.hh = e->d_hh.p; a.dc = e->d_dc.p; a.dl = e->d_dl.p;
   a.npad = e->npad;
   a.scal = e->d_scal.p;
   return a;
+}
+
+// sharded mode: sum the per-step scalars over the landmark shards (NCCL, on the engine stream)
+int allreduce_scalars(ctvio_engine* e) {
+  if (e->world <= 1) return CTVIO_OK;
+  e->launches += ctvio::launch_flags_to_double(e->d_scal.p, e->stream);
+  std::string err;
+  if (!ctvio::comm_allreduce_sum(e->nccl_comm, &e->d_scal.p->cost_eval, kLmSumScalars, e->stream, &err))
+    return fail(CTVIO_ERR_NCCL, err);
+  return CTVIO_OK;
+}
+
+// the LM step: reduced system (+ all-reduce of [M | rhs | diagA] over NVLink in sharded mode), factor, solve
+int lm_step(ctvio_engine* e, int nb, double radius) {
+  LinearLaunch lin = linear_launch(e, nb);
+  cudaStream_t st = e->stream;
+  e->launches += launch_reduced_system(lin, radius, st);
+  if (e->world > 1) {
+    std::string err;
+    const size_t count = size_t(e->npad) * e->npad + 2 * size_t(e->npad);
+    if (!ctvio::comm_allreduce_sum(e->nccl_comm, lin.M, count, st, &err)) return fail(CTVIO_ERR_NCCL, err);
+    e->launches += launch_add_damping(lin, radius, st);
+  }
+  e->launches += launch_factor_solve(lin, st);
+  e->launches += launch_step_vectors(lin, st);
+  return CTVIO_OK;
 }
 
 // one pass over all residual blocks at state buffer xb into normal-equation buffer nb
@@ -527,7 +557,8 @@ void evaluate(ctvio_engine* e, int xb, int nb, bool full) {
   if (full) cudaMemsetAsync(e->ne_slab[nb].p, 0, e->ne_slab_len * sizeof(double), st);
   cudaMemsetAsync(&e->d_scal.p->cost_eval, 0, sizeof(double), st);
   // fork: the (latency-bound) IMU + bias + prior kernels overlap the visual kernel on a second stream
-  const bool fork = !e->imu.empty() || !e->biasf.empty() || e->prior.n > 0;
+  // sharded mode: IMU / bias / prior factors live on rank 0 only (every rank holds its own landmark shard)
+  const bool fork = (e->rank == 0) && (!e->imu.empty() || !e->biasf.empty() || e->prior.n > 0);
   if (fork) {
     cudaEventRecord(e->ev_fork, st);
     cudaStreamWaitEvent(e->stream2, e->ev_fork, 0);
@@ -542,7 +573,7 @@ void evaluate(ctvio_engine* e, int xb, int nb, bool full) {
 int read_scalars(ctvio_engine* e) {
   CUDA_OK(cudaMemcpyAsync(e->h_scal, e->d_scal.p, sizeof(LmScalars), cudaMemcpyDeviceToHost, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
-  if (e->h_scal->error_flags & 1) {
+  if ((e->h_scal->error_flags & 1) || (e->world > 1 && e->h_scal->err_sum > 0.0)) {
     cudaMemsetAsync(&e->d_scal.p->error_flags, 0, sizeof(int32_t), e->stream);
     return fail(CTVIO_ERR_TIME_RANGE, "a factor time left its knot window / the spline (line delay too large?)");
   }
@@ -804,7 +835,7 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
   const int64_t launches0 = e->launches;
   cudaEventRecord(e->ev0, st);
 
-  const bool is_constrained = !e->opt.fix_ld && e->h_active[d.idx_ld];
+  const bool is_constrained = !e->opt.fix_ld && (e->world > 1 || e->h_active[d.idx_ld]);
   if (is_constrained) {  // IterationZero: x = Plus(x, 0) projects the line delay into its bounds
     double ld;
     CUDA_OK(cudaMemcpyAsync(&ld, e->x[e->cur].ld.p, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -813,16 +844,29 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     if (c != ld) CUDA_OK(cudaMemcpyAsync(e->x[e->cur].ld.p, &c, sizeof(double), cudaMemcpyHostToDevice, st));
   }
   ensure_table(e);
+  const bool sharded = e->world > 1;
   int cur = e->cur;  // state buffer and normal-equation buffer flip together
   evaluate(e, cur, cur, true);
   sum.num_jacobian_evals++;
   LinearLaunch lin = linear_launch(e, cur);
-  e->launches += launch_jacobi_scale(lin, st);
+  if (sharded) {
+    // Jacobi scaling needs the diagonal of the WHOLE camera block: all-reduce it once
+    e->launches += launch_extract_diag(lin, st);
+    std::string err;
+    if (!ctvio::comm_allreduce_sum(e->nccl_comm, lin.diagA, size_t(e->npad), st, &err)) return fail(CTVIO_ERR_NCCL, err);
+    e->launches += launch_jacobi_scale_from_diag(lin, st);
+  } else {
+    e->launches += launch_jacobi_scale(lin, st);
+  }
   e->launches += launch_gradient_norm(lin, e->x[cur].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st);
+  rc = allreduce_scalars(e);
+  if (rc) return rc;
   rc = read_scalars(e);
   if (rc) return rc;
   double x_cost = e->h_scal->cost_eval;
-  double gmax = e->h_scal->gmax;
+  // sharded mode: the gradient max-norm is only known per shard; the 1e-10 gradient tolerance is not tested
+  // there (every rank must take identical control decisions)
+  double gmax = sharded ? 1e300 : e->h_scal->gmax;
   sum.initial_cost = x_cost;
   sum.num_successful_steps = 1;
 
@@ -840,6 +884,7 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     ap.dc = e->d_dc.p; ap.dl = e->d_dl.p;
     ap.alpha = alpha;
     ap.active = e->d_active.p;
+    ap.count_camera = e->rank == 0 ? 1 : 0;
     ap.clamp_ld = e->opt.fix_ld ? 0 : 1;
     ap.ld_lower = e->opt.ld_lower; ap.ld_upper = e->opt.ld_upper;
     ap.scal = e->d_scal.p;
@@ -853,18 +898,20 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     ++iter;
     const int cand = cur ^ 1;
     // ---- trust-region step + speculative full evaluation of the candidate ----
-    lin = linear_launch(e, cur);
-    e->launches += launch_lm_step(lin, radius, st);
+    rc = lm_step(e, cur, radius);
+    if (rc) return rc;
     sum.num_linear_solves++;
-    if (e->world > 1) { /* reduced system is all-reduced inside launch_lm_step's caller in sharded mode (see comm) */ }
     apply(cur, cand, 1.0);
     evaluate(e, cand, cand, true);
     sum.num_jacobian_evals++;
     LinearLaunch linc = linear_launch(e, cand);
     e->launches += launch_gradient_norm(linc, e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st);
+    rc = allreduce_scalars(e);
+    if (rc) return rc;
     rc = read_scalars(e);
     if (rc) return rc;
-    const LmScalars sc = *e->h_scal;
+    LmScalars sc = *e->h_scal;
+    if (sharded) { sc.gmax = 1e300; sc.dir_max = 1e300; }
     const double model_cost_change = -sc.gd - 0.5 * sc.dHd;
     const bool valid = !sc.chol_fail && std::isfinite(model_cost_change) && model_cost_change > 0.0;
     if (!valid) {
@@ -892,6 +939,8 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
         if (current.value_ok && !have_grad) {
           // directional derivative at the trial point: g(x + a d) . d from the candidate buffers
           e->launches += ctvio::launch_dot_gradient(linear_launch(e, cand), st);
+          rc = allreduce_scalars(e);
+          if (rc) return rc;
           rc = read_scalars(e);
           if (rc) return rc;
           current.gradient = e->h_scal->gd;
@@ -915,6 +964,8 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
         sum.num_jacobian_evals++;
         e->launches += launch_gradient_norm(linear_launch(e, cand), e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower,
                                             e->opt.ld_upper, st);
+        rc = allreduce_scalars(e);
+        if (rc) return rc;
         rc = read_scalars(e);
         if (rc) return rc;
         current = Sample{step, e->h_scal->cost_eval, 0.0, std::isfinite(e->h_scal->cost_eval), false};
@@ -928,11 +979,13 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
         sum.num_jacobian_evals++;
         e->launches += launch_gradient_norm(linear_launch(e, cand), e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower,
                                             e->opt.ld_upper, st);
+        rc = allreduce_scalars(e);
+        if (rc) return rc;
         rc = read_scalars(e);
         if (rc) return rc;
       }
       cand_cost = e->h_scal->cost_eval;
-      cand_gmax = e->h_scal->gmax;
+      cand_gmax = sharded ? 1e300 : e->h_scal->gmax;
       step_norm2 = e->h_scal->step_norm2;
       x_norm2 = e->h_scal->x_norm2;
     }
@@ -960,6 +1013,17 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
   }
   e->cur = cur;
   e->table_valid = true;
+  if (sharded && e->nL > 0) {
+    // every rank updated only the inverse depths of its own landmark shard: make them consistent everywhere
+    CUDA_OK(e->d_rho_sync.reserve(2 * size_t(e->nL)));
+    std::vector<uint8_t> owned(e->nL, 0);
+    for (const HostImage& o : e->img) owned[o.lm] = 1;
+    CUDA_OK(e->d_owned.upload(owned, st));
+    e->launches += ctvio::launch_rho_pack(e->x[cur].rho.p, e->d_owned.p, e->d_rho_sync.p, e->nL, st);
+    std::string err;
+    if (!ctvio::comm_allreduce_sum(e->nccl_comm, e->d_rho_sync.p, 2 * size_t(e->nL), st, &err)) return fail(CTVIO_ERR_NCCL, err);
+    e->launches += ctvio::launch_rho_unpack(e->x[cur].rho.p, e->d_rho_sync.p, e->nL, st);
+  }
   cudaEventRecord(e->ev1, st);
   CUDA_OK(cudaEventSynchronize(e->ev1));
   float ms = 0;
@@ -1160,6 +1224,7 @@ int ctvio_profile_kernels(ctvio_handle e, int32_t reps, int32_t flush_l2, double
   ap.dims = e->dims();
   ap.x = e->x[cur].ptrs(); ap.xc = e->x[cand].ptrs();
   ap.dc = e->d_dc.p; ap.dl = e->d_dl.p; ap.alpha = 1.0; ap.active = e->d_active.p;
+  ap.count_camera = 1;
   ap.clamp_ld = e->opt.fix_ld ? 0 : 1; ap.ld_lower = e->opt.ld_lower; ap.ld_upper = e->opt.ld_upper;
   ap.scal = e->d_scal.p;
   auto time_stage = [&](int stage, double* ms_out) -> int {

@@ -109,6 +109,7 @@ struct LmScalars {
   double dHd;              // delta' H delta
   double step_norm2;       // |x - x+|^2 (ambient, active blocks)
   double x_norm2;          // |x|^2 (ambient, active blocks)
+  double err_sum;          // (sharded mode) error flag as a double so that it can ride in the scalar all-reduce
   double gmax;             // max |g| over active dims (bounds-projected for the line delay)
   double dir_max;          // max |delta|
   double ld_value;         // line delay of the candidate state
@@ -116,6 +117,7 @@ struct LmScalars {
   int32_t error_flags;     // bit0: factor time outside its window / spline
   int32_t pad[2];
 };
+constexpr int kLmSumScalars = 6;  // cost_eval, gd, dHd, step_norm2, x_norm2, err_sum: plain sums over landmark shards
 
 // ---- launch wrappers (each returns the number of kernels it launched) ----------------------------
 int launch_knot_table(const StatePtrs& st, int nK, cudaStream_t s);
@@ -187,7 +189,10 @@ struct LinearLaunch {
   double* Linv;                 // [npad/NB][NB][NB] inverses of the diagonal Cholesky blocks
   double* rhs;                  // [npad]
   double* y;                    // [npad]
+  double* yf;                   // [npad] forward-solved right-hand side
   double* hh;                   // [nL] damped landmark diagonals
+  double* diagA;                // [npad] camera diagonal (sharded mode: all-reduced with M and rhs); may be null
+  int32_t sharded;              // != 0: M is built WITHOUT damping / identity rows (they are added after the all-reduce)
   double* dc;                   // [np] step (camera dims)
   double* dl;                   // [nL]
   int32_t npad;
@@ -200,10 +205,16 @@ int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s);
 int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s);
 int launch_factor_solve(const LinearLaunch& a, cudaStream_t s);
 int launch_step_vectors(const LinearLaunch& a, cudaStream_t s);
+// sharded mode: after the all-reduce of [M | rhs | diagA] add the LM damping, identity rows of constant /
+// padding dims; and the iteration-0 Jacobi scale from the all-reduced diagonal
+int launch_add_damping(const LinearLaunch& a, double radius, cudaStream_t s);
+int launch_extract_diag(const LinearLaunch& a, cudaStream_t s);
+int launch_jacobi_scale_from_diag(const LinearLaunch& a, cudaStream_t s);
 int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld, double ld_lower, double ld_upper,
                          cudaStream_t s);
 
 struct ApplyLaunch {
+  int32_t count_camera;     // sharded mode: only rank 0 counts the (replicated) camera blocks in the norms
   ProblemDims dims;
   StatePtrs x, xc;          // current, candidate
   const double* dc;

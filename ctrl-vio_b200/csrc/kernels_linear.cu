@@ -49,17 +49,23 @@ __global__ void scale_copy_kernel(LinearLaunch a, double radius) {
   if (idx >= size_t(npad) * npad) return;
   const int i = int(idx / npad), j = int(idx % npad);
   double m;
+  const double ident = a.sharded ? 0.0 : 1.0;  // sharded: identity rows are set after the all-reduce
   if (i < np && j < np) {
     if (a.cmask[i] || a.cmask[j]) {
-      m = (i == j) ? 1.0 : 0.0;
+      m = (i == j) ? ident : 0.0;
     } else {
       const double v = (i <= j) ? a.ne.A[size_t(i) * np + j] : a.ne.A[size_t(j) * np + i];
       m = a.sc[i] * v * a.sc[j];
-      if (i == j) m += fmin(fmax(m, kMinLmDiag), kMaxLmDiag) / radius;
+      if (i == j) {
+        if (a.sharded) a.diagA[i] = v;  // unscaled local diagonal, summed over ranks with M
+        else m += fmin(fmax(m, kMinLmDiag), kMaxLmDiag) / radius;
+      }
     }
   } else {
-    m = (i == j) ? 1.0 : 0.0;
+    m = (i == j) ? ident : 0.0;
+    if (a.sharded && i == j) a.diagA[i] = 0.0;
   }
+  if (a.sharded && i == j && i < np && a.cmask[i]) a.diagA[i] = 0.0;
   a.M[idx] = m;
   if (j == 0) {
     a.rhs[i] = (i < np && !a.cmask[i]) ? a.sc[i] * a.ne.gc[i] : 0.0;
@@ -254,6 +260,43 @@ __global__ void __launch_bounds__(256) landmark_step_kernel(LinearLaunch a) {
   }
 }
 
+// after the all-reduce of [M | rhs | diagA]
+__global__ void add_damping_kernel(LinearLaunch a, double radius) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.npad) return;
+  double* d = a.M + size_t(i) * a.npad + i;
+  if (i < a.dims.np && !a.cmask[i]) {
+    const double sd = a.sc[i] * a.sc[i] * a.diagA[i];
+    *d += fmin(fmax(sd, kMinLmDiag), kMaxLmDiag) / radius;
+  } else {
+    *d = 1.0;
+    a.rhs[i] = 0.0;
+  }
+}
+int launch_add_damping(const LinearLaunch& a, double radius, cudaStream_t s) {
+  add_damping_kernel<<<(a.npad + 255) / 256, 256, 0, s>>>(a, radius);
+  return 1;
+}
+__global__ void extract_diag_kernel(LinearLaunch a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.npad) return;
+  a.diagA[i] = i < a.dims.np ? a.ne.A[size_t(i) * a.dims.np + i] : 0.0;
+}
+int launch_extract_diag(const LinearLaunch& a, cudaStream_t s) {
+  extract_diag_kernel<<<(a.npad + 255) / 256, 256, 0, s>>>(a);
+  return 1;
+}
+__global__ void jacobi_scale_from_diag_kernel(LinearLaunch a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.dims.np) a.sc[i] = 1.0 / (1.0 + sqrt(a.diagA[i]));
+  if (i < a.dims.nL) a.sl[i] = 1.0 / (1.0 + sqrt(a.ne.hl[i]));
+}
+int launch_jacobi_scale_from_diag(const LinearLaunch& a, cudaStream_t s) {
+  const int n = max(a.dims.np, a.dims.nL);
+  jacobi_scale_from_diag_kernel<<<(n + 255) / 256, 256, 0, s>>>(a);
+  return 1;
+}
+
 int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s) {
   int launches = 0;
   const size_t total = size_t(a.npad) * a.npad;
@@ -331,7 +374,7 @@ __global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
     Q4 qn = q;
     if (d[0] != 0.0 || d[1] != 0.0 || d[2] != 0.0) qn = so3_mul(q, so3_exp(V3{a.alpha * d[0], a.alpha * d[1], a.alpha * d[2]}));
     a.xc.q[4 * i] = qn.x; a.xc.q[4 * i + 1] = qn.y; a.xc.q[4 * i + 2] = qn.z; a.xc.q[4 * i + 3] = qn.w;
-    if (a.active[6 * i]) {
+    if (a.count_camera && a.active[6 * i]) {
       xn += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
       sn += (q.x - qn.x) * (q.x - qn.x) + (q.y - qn.y) * (q.y - qn.y) + (q.z - qn.z) * (q.z - qn.z) + (q.w - qn.w) * (q.w - qn.w);
     }
@@ -340,7 +383,7 @@ __global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
       const double p = a.x.p[kPStride * i + c];
       const double pn = p + a.alpha * d[3 + c];
       a.xc.p[kPStride * i + c] = pn;
-      if (a.active[6 * i + 3 + c]) { xn += p * p; sn += (p - pn) * (p - pn); }
+      if (a.count_camera && a.active[6 * i + 3 + c]) { xn += p * p; sn += (p - pn) * (p - pn); }
     }
     a.xc.p[kPStride * i + 3] = 0.0;
   } else if (i < nK + 6 * nB) {
@@ -348,14 +391,14 @@ __global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
     const double v = a.x.bias[b];
     const double vn = v + a.alpha * a.dc[a.dims.idx_bias0 + b];
     a.xc.bias[b] = vn;
-    if (a.active[a.dims.idx_bias0 + b]) { xn += v * v; sn += (v - vn) * (v - vn); }
+    if (a.count_camera && a.active[a.dims.idx_bias0 + b]) { xn += v * v; sn += (v - vn) * (v - vn); }
   } else if (i == nK + 6 * nB) {
     const double v = *a.x.ld;
     double vn = v + a.alpha * a.dc[a.dims.idx_ld];
     if (a.clamp_ld) vn = fmin(fmax(vn, a.ld_lower), a.ld_upper);
     *a.xc.ld = vn;
     a.scal->ld_value = vn;
-    if (a.active[a.dims.idx_ld]) { xn += v * v; sn += (v - vn) * (v - vn); }
+    if (a.count_camera && a.active[a.dims.idx_ld]) { xn += v * v; sn += (v - vn) * (v - vn); }
   } else if (i < nK + 6 * nB + 1 + nL) {
     const int l = i - (nK + 6 * nB + 1);
     const double v = a.x.rho[l];

@@ -93,6 +93,10 @@ int launch_marg_elementwise(int mode, int n, int ld, const double* src, double* 
 // measured fp64 FMA throughput of the current device (TFLOP/s); < 0 on error
 double measure_fp64_tflops(cudaStream_t s);
 
+int launch_flags_to_double(LmScalars* scal, cudaStream_t s);
+int launch_rho_pack(const double* rho, const uint8_t* owned, double* buf, int nL, cudaStream_t s);
+int launch_rho_unpack(double* rho, const double* buf, int nL, cudaStream_t s);
+
 bool comm_unique_id(uint8_t* id128, std::string* err);
 void* comm_create(int rank, int world, const uint8_t* id128, std::string* err);
 void comm_destroy(void* comm);

@@ -41,6 +41,35 @@ int launch_dot_gradient(const LinearLaunch& a, cudaStream_t s) {
   return 1;
 }
 
+// sharded mode helpers
+__global__ void flags_to_double_kernel(LmScalars* scal) { scal->err_sum = (scal->error_flags != 0) ? 1.0 : 0.0; }
+int launch_flags_to_double(LmScalars* scal, cudaStream_t s) {
+  flags_to_double_kernel<<<1, 1, 0, s>>>(scal);
+  return 1;
+}
+// buf = [rho masked by ownership (nL) | owned (nL)] before the all-reduce, rho <- sum / count afterwards
+__global__ void rho_pack_kernel(const double* rho, const uint8_t* owned, double* buf, int nL) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nL) return;
+  buf[l] = owned[l] ? rho[l] : 0.0;
+  buf[nL + l] = owned[l] ? 1.0 : 0.0;
+}
+__global__ void rho_unpack_kernel(double* rho, const double* buf, int nL) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nL) return;
+  if (buf[nL + l] > 0.0) rho[l] = buf[l] / buf[nL + l];
+}
+int launch_rho_pack(const double* rho, const uint8_t* owned, double* buf, int nL, cudaStream_t s) {
+  if (nL <= 0) return 0;
+  rho_pack_kernel<<<(nL + 255) / 256, 256, 0, s>>>(rho, owned, buf, nL);
+  return 1;
+}
+int launch_rho_unpack(double* rho, const double* buf, int nL, cudaStream_t s) {
+  if (nL <= 0) return 0;
+  rho_unpack_kernel<<<(nL + 255) / 256, 256, 0, s>>>(rho, buf, nL);
+  return 1;
+}
+
 // fp64 FMA micro-benchmark: 8 independent DFMA chains per thread, enough CTAs to fill every SM.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
   double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
