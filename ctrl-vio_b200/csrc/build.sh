@@ -11,18 +11,7 @@ if [[ -z "${CTVIO_FORCE_BUILD:-}" && -f "$OUT" ]]; then
   [[ $newer -eq 0 ]] && exit 0
 fi
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-# NCCL: headers from the system package; at run time libnccl.so.2 resolves to the copy torch already loaded
-NCCL_LIB_DIR=${NCCL_LIB_DIR:-$(python - <<'PY'
-import os, glob
-c = glob.glob('/usr/lib/x86_64-linux-gnu/libnccl.so*')
-if c:
-    print(os.path.dirname(c[0]))
-else:
-    import importlib.util
-    s = importlib.util.find_spec('nvidia.nccl')
-    print(os.path.join(list(s.submodule_search_locations)[0], 'lib') if s else '')
-PY
-)}
+# NCCL: only <nccl.h> (types) is needed at build time; the library is dlopen'ed by comm.cu on first use.
 FLAGS="${CTVIO_EXTRA_NVCC_FLAGS:-} -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -Xptxas -v"
 objs=""
 for f in $SRCS; do
@@ -32,5 +21,5 @@ for f in $SRCS; do
   fi
   objs="$objs $o"
 done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" $objs -L"$NCCL_LIB_DIR" -l:libnccl.so.2 -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" $objs -lcudart -ldl
 echo "built $OUT"
