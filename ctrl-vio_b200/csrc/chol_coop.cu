@@ -19,7 +19,10 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 
+#include "chol_tiles.cuh"
 #include "kernels.h"
 
 namespace ctvio {
@@ -41,234 +44,6 @@ __device__ __forceinline__ void stamp(int& n) {
 #else
 #define STAMP()
 #endif
-
-constexpr int kTS = kCholNB + 2;  // shared tile row stride (doubles): rows stay 16-B aligned
-constexpr int kTile = kCholNB * kTS;
-constexpr size_t kCholCoopSmem = (5 * size_t(kTile) + 4 * kCholNB) * sizeof(double);
-
-// acc[4][4] += A * B^T for 64x64 operands, BOTH stored transposed in smem: At[c][i] = A[i][c], Bt[c][j] = B[j][c].
-// 256 threads, thread (ty, tx) owns rows 4ty.., cols 4tx..; four 16-byte shared loads feed 16 FMAs per k.
-__device__ __forceinline__ void tile_gemm_tt(const double* At, const double* Bt, double acc[4][4], int ty, int tx) {
-#pragma unroll 8
-  for (int c = 0; c < kCholNB; ++c) {
-    const double2 a01 = *reinterpret_cast<const double2*>(At + c * kTS + 4 * ty);
-    const double2 a23 = *reinterpret_cast<const double2*>(At + c * kTS + 4 * ty + 2);
-    const double2 b01 = *reinterpret_cast<const double2*>(Bt + c * kTS + 4 * tx);
-    const double2 b23 = *reinterpret_cast<const double2*>(Bt + c * kTS + 4 * tx + 2);
-    const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-    const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-  }
-}
-
-// smem tile <- TRANSPOSE of the 64x64 global block at M[r0.., c0..]: dst[c][r] = M[r0 + r][c0 + c]
-// (coalesced 16-byte global reads along c)
-__device__ __forceinline__ void load_tile_transposed(double* dst, const double* M, int npad, int r0, int c0, int tid) {
-  for (int e = tid; e < kCholNB * kCholNB / 2; e += 256) {
-    const int r = e >> 5, c = (e & 31) * 2;
-    const double2 v = *reinterpret_cast<const double2*>(M + size_t(r0 + r) * npad + c0 + c);
-    dst[c * kTS + r] = v.x;
-    dst[(c + 1) * kTS + r] = v.y;
-  }
-}
-
-// 4x4 lower Cholesky of a (registers), reciprocal pivots rd.  Returns false on a bad pivot.
-__device__ __forceinline__ bool chol4(const double a[4][4], double l[4][4], double rd[4]) {
-  bool ok = true;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    double v = a[j][j];
-#pragma unroll
-    for (int k = 0; k < j; ++k) v = fma(-l[j][k], l[j][k], v);
-    if (!(v > 0.0) || !isfinite(v)) { ok = false; v = 1.0; }
-    rd[j] = rsqrt(v);
-    l[j][j] = v * rd[j];
-#pragma unroll
-    for (int i = j + 1; i < 4; ++i) {
-      double w = a[i][j];
-#pragma unroll
-      for (int k = 0; k < j; ++k) w = fma(-l[i][k], l[j][k], w);
-      l[i][j] = w * rd[j];
-    }
-  }
-  return ok;
-}
-
-// merge step of the triangular inverse for block size h (one thread per 4x4 output tile; a 4-lane k-split
-// with shuffles and a fully unrolled templated variant were both measured slower):
-//   mode 0: T     <- L21 * X11        mode 1: X21 <- -(X22 * T), written to Xi and (transposed) to XiT
-__device__ __forceinline__ void merge_gemm(int mode, int h, const double* D, double* Xi, double* XiT, double* T, int tid) {
-  const int npair = kCholNB / (2 * h), tpb = (h / 4) * (h / 4);
-  if (tid < npair * tpb) {
-    const int pb = tid / tpb, t = tid % tpb;
-    const int r0 = 4 * (t / (h / 4)), c0 = 4 * (t % (h / 4));
-    const int o = 2 * h * pb;
-    const double* A = mode == 0 ? D + (o + h) * kTS + o : Xi + (o + h) * kTS + o + h;
-    const double* B = mode == 0 ? Xi + o * kTS + o : T + (o + h) * kTS + o;
-    double acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-#pragma unroll 4
-    for (int m = 0; m < h; ++m) {
-      double av[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = A[(r0 + i) * kTS + m];
-      const double2 b01 = *reinterpret_cast<const double2*>(B + m * kTS + c0);
-      const double2 b23 = *reinterpret_cast<const double2*>(B + m * kTS + c0 + 2);
-      const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-    }
-    if (mode == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        *reinterpret_cast<double2*>(T + (o + h + r0 + i) * kTS + o + c0) = make_double2(acc[i][0], acc[i][1]);
-        *reinterpret_cast<double2*>(T + (o + h + r0 + i) * kTS + o + c0 + 2) = make_double2(acc[i][2], acc[i][3]);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        *reinterpret_cast<double2*>(Xi + (o + h + r0 + i) * kTS + o + c0) = make_double2(-acc[i][0], -acc[i][1]);
-        *reinterpret_cast<double2*>(Xi + (o + h + r0 + i) * kTS + o + c0 + 2) = make_double2(-acc[i][2], -acc[i][3]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) XiT[(o + c0 + j) * kTS + o + h + r0 + i] = -acc[i][j];
-      }
-    }
-  }
-}
-
-// In-place lower Cholesky of the 64x64 block D (row stride kTS) by 256 threads, then Xi = D^-1 (lower
-// triangular) and XiT = Xi^T.  T is a scratch tile, rdiag[64] receives 1/L_jj.
-#ifdef CTVIO_CHOL_TIMING
-#define FSTAMP() stamp(*pn)
-#else
-#define FSTAMP()
-#endif
-__device__ bool factor_and_invert_64(double* D, double* Xi, double* XiT, double* T, double* rdiag, int* s_bad, int* pn) {
-  const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
-  if (tid == 0) *s_bad = 0;
-  double a[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const double2 v01 = *reinterpret_cast<const double2*>(D + (4 * ty + i) * kTS + 4 * tx);
-    const double2 v23 = *reinterpret_cast<const double2*>(D + (4 * ty + i) * kTS + 4 * tx + 2);
-    a[i][0] = v01.x; a[i][1] = v01.y; a[i][2] = v23.x; a[i][3] = v23.y;
-  }
-  for (int e = tid; e < kTile; e += 256) { Xi[e] = 0.0; XiT[e] = 0.0; }
-  __syncthreads();
-  if (tid == 0) {  // diagonal block 0
-    double l[4][4], rd[4];
-    if (!chol4(a, l, rd)) *s_bad = 1;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      rdiag[i] = rd[i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) D[i * kTS + j] = j <= i ? l[i][j] : 0.0;
-    }
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int jb = 0; jb < 16; ++jb) {
-    if (tx == jb && ty > jb) {
-      // panel block by substitution: x[r][c] = (a[r][c] - sum_{m<c} x[r][m] l[c][m]) / l[c][c]
-      double l[4][4], rd[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        rd[c] = rdiag[4 * jb + c];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) l[c][m] = D[(4 * jb + c) * kTS + 4 * jb + m];
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        double x[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          double t = a[r][c];
-#pragma unroll
-          for (int m = 0; m < c; ++m) t = fma(-x[m], l[c][m], t);
-          x[c] = t * rd[c];
-        }
-        *reinterpret_cast<double2*>(D + (4 * ty + r) * kTS + 4 * jb) = make_double2(x[0], x[1]);
-        *reinterpret_cast<double2*>(D + (4 * ty + r) * kTS + 4 * jb + 2) = make_double2(x[2], x[3]);
-      }
-    }
-    __syncthreads();
-    if (tx > jb && ty >= tx) {
-      double lr[4][4], lc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const double2 r01 = *reinterpret_cast<const double2*>(D + (4 * ty + i) * kTS + 4 * jb);
-        const double2 r23 = *reinterpret_cast<const double2*>(D + (4 * ty + i) * kTS + 4 * jb + 2);
-        const double2 c01 = *reinterpret_cast<const double2*>(D + (4 * tx + i) * kTS + 4 * jb);
-        const double2 c23 = *reinterpret_cast<const double2*>(D + (4 * tx + i) * kTS + 4 * jb + 2);
-        lr[i][0] = r01.x; lr[i][1] = r01.y; lr[i][2] = r23.x; lr[i][3] = r23.y;
-        lc[i][0] = c01.x; lc[i][1] = c01.y; lc[i][2] = c23.x; lc[i][3] = c23.y;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int m = 0; m < 4; ++m) a[i][j] = fma(-lr[i][m], lc[j][m], a[i][j]);
-      if (ty == jb + 1 && tx == jb + 1) {  // look-ahead: factor the next diagonal block right away
-        double l[4][4], rd[4];
-        if (!chol4(a, l, rd)) *s_bad = 1;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          rdiag[4 * tx + i] = rd[i];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) D[(4 * tx + i) * kTS + 4 * tx + j] = j <= i ? l[i][j] : 0.0;
-        }
-      }
-    }
-    __syncthreads();
-  }
-  FSTAMP();  // main loop done
-  // 4x4 inverses of the 16 diagonal blocks (off the critical path, all in parallel)
-  if (ty == tx) {
-    double l[4][4], li[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) l[i][j] = D[(4 * ty + i) * kTS + 4 * ty + j];
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (r < c) { li[r][c] = 0.0; continue; }
-        double t = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int m = c; m < r; ++m) t = fma(-l[r][m], li[m][c], t);
-        li[r][c] = t * rdiag[4 * ty + r];
-      }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        Xi[(4 * ty + i) * kTS + 4 * ty + j] = li[i][j];
-        XiT[(4 * ty + j) * kTS + 4 * ty + i] = li[i][j];
-      }
-  }
-  __syncthreads();
-  FSTAMP();  // 4x4 inverses done
-#pragma unroll 1
-  for (int h = 4; h < kCholNB; h *= 2) {
-    merge_gemm(0, h, D, Xi, XiT, T, tid);
-    __syncthreads();
-    merge_gemm(1, h, D, Xi, XiT, T, tid);
-    __syncthreads();
-    FSTAMP();  // merge level done
-  }
-  return *s_bad == 0;
-}
 
 __global__ void __launch_bounds__(256, 1)
 chol_coop_kernel(double* __restrict__ M, int npad, double* __restrict__ Linv, const double* __restrict__ rhs,
@@ -308,11 +83,7 @@ chol_coop_kernel(double* __restrict__ M, int npad, double* __restrict__ Linv, co
       }
       __syncthreads();
       STAMP();  // diag block loaded
-      #ifdef CTVIO_CHOL_TIMING
-      const bool ok = factor_and_invert_64(D, Xi, XiT, S2, rdiag, &s_bad, &stamp_n);
-#else
-      const bool ok = factor_and_invert_64(D, Xi, XiT, S2, rdiag, &s_bad, nullptr);
-#endif
+      const bool ok = factor_and_invert_64(D, Xi, XiT, S2, rdiag, &s_bad);
       if (!ok && cta == 0 && tid == 0) scal->chol_fail = 1;
       STAMP();  // factored + inverted
       // x_k = Xi * y_k  (4 lanes per row)
@@ -438,9 +209,74 @@ chol_coop_kernel(double* __restrict__ M, int npad, double* __restrict__ Linv, co
 extern "C" int ctvio_debug_chol_stamps(unsigned long long* out, int n) {
   return cudaMemcpyFromSymbol(out, g_chol_stamps, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : -1;
 }
+// latency probes (debug build only): cycles per dependent op, measured by thread 0 of one CTA with `nthreads` threads
+__global__ void latency_probe_kernel(double seed, long long* out, double* sink) {
+  __shared__ double sm[512];
+  double x = seed + threadIdx.x * 1e-9, y = 1.0 + 1e-9 * seed;
+  sm[threadIdx.x] = x;
+  __syncthreads();
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i) {
+    x = fma(x, y, 1e-3); x = fma(x, y, 1e-3); x = fma(x, y, 1e-3); x = fma(x, y, 1e-3);
+  }
+  long long t1 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i) { x = x * y; x = x * y; x = x * y; x = x * y; }
+  long long t2 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i) x = rsqrt(x + 2.0);
+  long long t3 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i) { sm[threadIdx.x] = x; __syncthreads(); x += sm[(threadIdx.x + 17) % blockDim.x]; __syncthreads(); }
+  long long t4 = clock64();
+  // 16 independent chains
+  double z[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) z[j] = x + j;
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = fma(z[j], y, 1e-3);
+  }
+  long long t5 = clock64();
+  float f = float(x);
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i) { f = fmaf(f, 1.0001f, 1e-3f); f = fmaf(f, 1.0001f, 1e-3f); f = fmaf(f, 1.0001f, 1e-3f); f = fmaf(f, 1.0001f, 1e-3f); }
+  long long t6 = clock64();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x += z[j];
+  x += f;
+  if (threadIdx.x == 0) {
+    out[0] = t1 - t0; out[1] = t2 - t1; out[2] = t3 - t2; out[3] = t4 - t3; out[4] = t5 - t4; out[5] = t6 - t5;
+  }
+  sink[threadIdx.x] = x;
+}
+extern "C" int ctvio_debug_latency(int nthreads, long long* out6) {
+  long long* d; double* sink;
+  cudaMalloc(&d, 64); cudaMalloc(&sink, 8 * 1024);
+  latency_probe_kernel<<<1, nthreads>>>(1.5, d, sink);
+  latency_probe_kernel<<<1, nthreads>>>(1.5, d, sink);
+  cudaMemcpy(out6, d, 48, cudaMemcpyDeviceToHost);
+  cudaFree(d); cudaFree(sink);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
 #endif
 
 int launch_factor_solve(const LinearLaunch& a, cudaStream_t s) {
+  static int n_sm = 0, mode = -1;  // mode: 0 auto, 1 force the barrier kernel (CTVIO_CHOL=coop)
+  if (mode < 0) {
+    const char* env = std::getenv("CTVIO_CHOL");
+    mode = (env && std::string(env) == "coop") ? 1 : 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (mode == 0 && a.chol_part && a.chol_flags && chol_dag_supported(a.npad, n_sm)) return launch_chol_dag(a, s);
+  return launch_chol_coop(a, s);
+}
+
+int launch_chol_coop(const LinearLaunch& a, cudaStream_t s) {
   static int n_sm = 0;
   static bool attr_set = false;
   if (!attr_set) {

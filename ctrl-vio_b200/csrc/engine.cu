@@ -132,7 +132,8 @@ struct ctvio_engine {
   size_t ne_slab_len = 0;
   size_t off_gc = 0, off_hl = 0, off_gl = 0, off_wld = 0, off_W = 0;
   // linear system
-  DevBuf<double> d_M, d_Linv, d_y, d_sc, d_sl, d_hh, d_dc, d_dl, d_rho_sync;
+  DevBuf<double> d_M, d_Linv, d_y, d_sc, d_sl, d_hh, d_dc, d_dl, d_rho_sync, d_chol_part;
+  DevBuf<int32_t> d_chol_flags;
   DevBuf<uint8_t> d_owned;
   int npad = 0;
   DevBuf<LmScalars> d_scal;
@@ -356,6 +357,11 @@ int prepare(ctvio_engine* e) {
     e->npad = ((d.np + kCholNB - 1) / kCholNB) * kCholNB;
     CUDA_OK(e->d_M.reserve(size_t(e->npad) * e->npad + 3 * size_t(e->npad)));  // M | rhs | diagA | yf (all-reduce slab)
     CUDA_OK(e->d_Linv.reserve(size_t(e->npad) * kCholNB));
+    CUDA_OK(e->d_chol_part.reserve(chol_dag_part_len(e->npad)));
+    if (chol_dag_flags_len(e->npad) > e->d_chol_flags.cap) {
+      CUDA_OK(e->d_chol_flags.reserve(chol_dag_flags_len(e->npad)));
+      CUDA_OK(cudaMemsetAsync(e->d_chol_flags.p, 0, e->d_chol_flags.cap * sizeof(int32_t), e->stream));
+    }
     CUDA_OK(e->d_y.reserve(e->npad));
     CUDA_OK(e->d_sc.reserve(np));
     CUDA_OK(e->d_sl.reserve(e->nL));
@@ -518,6 +524,7 @@ LinearLaunch linear_launch(ctvio_engine* e, int nb) {
   a.rhs = e->d_M.p + size_t(e->npad) * e->npad;
   a.diagA = a.rhs + e->npad;
   a.yf = a.diagA + e->npad;
+  a.chol_part = e->d_chol_part.p; a.chol_flags = e->d_chol_flags.p;
   a.sharded = e->world > 1 ? 1 : 0;
   a.hh = e->d_hh.p; a.dc = e->d_dc.p; a.dl = e->d_dl.p;
   a.npad = e->npad;

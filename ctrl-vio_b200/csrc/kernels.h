@@ -190,6 +190,8 @@ struct LinearLaunch {
   double* rhs;                  // [npad]
   double* y;                    // [npad]
   double* yf;                   // [npad] forward-solved right-hand side
+  double* chol_part;            // workspace of the tile-DAG Cholesky (chol_dag_part_len doubles); null -> barrier kernel
+  int32_t* chol_flags;          // its dependency flags (chol_dag_flags_len ints, zero-initialised once)
   double* hh;                   // [nL] damped landmark diagonals
   double* diagA;                // [npad] camera diagonal (sharded mode: all-reduced with M and rhs); may be null
   int32_t sharded;              // != 0: M is built WITHOUT damping / identity rows (they are added after the all-reduce)
@@ -204,6 +206,12 @@ int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s);
 // the three stages of launch_lm_step, separately launchable for measurement
 int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s);
 int launch_factor_solve(const LinearLaunch& a, cudaStream_t s);
+// tile-DAG variant (chol_dag.cu): usable when every tile gets its own SM
+bool chol_dag_supported(int npad, int n_sm);
+size_t chol_dag_part_len(int npad);
+size_t chol_dag_flags_len(int npad);
+int launch_chol_dag(const LinearLaunch& a, cudaStream_t s);
+int launch_chol_coop(const LinearLaunch& a, cudaStream_t s);
 int launch_step_vectors(const LinearLaunch& a, cudaStream_t s);
 // sharded mode: after the all-reduce of [M | rhs | diagA] add the LM damping, identity rows of constant /
 // padding dims; and the iteration-0 Jacobi scale from the all-reduced diagonal
