@@ -100,7 +100,7 @@ ABI_SYMBOLS = [
     "solve", "gauge_realign", "marginalize", "get_prior", "adopt_prior",
     "save_state", "restore_state",
     "eval_image_factors", "eval_imu_factors", "eval_cost", "normal_equations",
-    "query_trajectory", "profile_kernels", "measure_fp64_tflops", "nccl_unique_id", "comm_init",
+    "query_trajectory", "profile_kernels", "measure_fp64_tflops", "selfcheck_solver", "nccl_unique_id", "comm_init",
 ]
 
 
@@ -362,6 +362,12 @@ class Estimator:
         self.lib.call("profile_kernels", self.h, C.c_int32(reps), C.c_int32(int(flush_l2)), _dp(out))
         names = ["visual", "imu", "small", "reduced_schur", "cholesky_solve", "step_vectors", "apply_table", "visual_cost"]
         return dict(zip(names, out.tolist()))
+
+    def SelfcheckSolver(self, reps=50):
+        """(bitwise mismatches over `reps` repeated solves of the same reduced system, relative residual)."""
+        mm, res = C.c_int32(), C.c_double()
+        self.lib.call("selfcheck_solver", self.h, C.c_int32(reps), C.byref(mm), C.byref(res))
+        return mm.value, res.value
 
     def MeasureFp64Tflops(self):
         v = C.c_double()

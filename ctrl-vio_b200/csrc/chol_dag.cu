@@ -49,62 +49,105 @@ __device__ __forceinline__ void post_flag(int* flag, int epoch) {
   }
 }
 
-// register block of the owned tile <- global (L2 path: the tile may have been produced by another SM)
-__device__ __forceinline__ void load_block(double acc[4][4], const double* M, int npad, int r0, int c0, int ty, int tx) {
+// ---- fp64 tensor-core tiles (mma.sync.m8n8k4.f64, measured 37 TFLOP/s = the DFMA peak, at 1/5 of the
+// shared-memory operand traffic of a 4x4 register-tiled DFMA loop) ----
+// Warp (wm, wn) = (warp & 3, warp >> 2) owns rows 16 wm.., cols 32 wn.. of the 64x64 tile as 2 x 4 m8n8 fragments;
+// lane (g, q) = (lane >> 2, lane & 3) holds C[8 mt + g][8 nt + 2 q + {0, 1}] of each fragment.
+struct Frag {
+  double c[2][4][2];
+};
+struct Lane {
+  int row0, col0, g, q;  // first row / column of the warp tile, lane coordinates
+};
+__device__ __forceinline__ Lane lane_of(int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  return Lane{16 * (warp & 3), 32 * (warp >> 2), lane >> 2, lane & 3};
+}
+__device__ __forceinline__ void frag_zero(Frag& f) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const double2* p = reinterpret_cast<const double2*>(M + size_t(r0 + 4 * ty + i) * npad + c0 + 4 * tx);
-    const double2 v01 = __ldcg(p), v23 = __ldcg(p + 1);
-    acc[i][0] = v01.x; acc[i][1] = v01.y; acc[i][2] = v23.x; acc[i][3] = v23.y;
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) f.c[mt][nt][0] = f.c[mt][nt][1] = 0.0;
+}
+// f (+|-)= A * B^T with both operands in [k][row] layout in smem (At[k][i] = A[i][k], Bt[k][j] = B[j][k])
+template <bool SUB>
+__device__ __forceinline__ void tile_gemm_dmma(const double* At, const double* Bt, Frag& f, const Lane& L) {
+  const double* pa = At + L.q * kTS + L.row0 + L.g;
+  const double* pb = Bt + L.q * kTS + L.col0 + L.g;
+#pragma unroll 4
+  for (int k0 = 0; k0 < kCholNB; k0 += 4) {
+    double av[2], bv[4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) av[mt] = SUB ? -pa[k0 * kTS + 8 * mt] : pa[k0 * kTS + 8 * mt];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) bv[nt] = pb[k0 * kTS + 8 * nt];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(f.c[mt][nt][0]), "+d"(f.c[mt][nt][1])
+                     : "d"(av[mt]), "d"(bv[nt]));
   }
 }
-// smem tile <- TRANSPOSE of a 64x64 global block with row stride ld: dst[c][r] = src[r][c]
-__device__ __forceinline__ void load_tile_t_cg(double* dst, const double* src, int ld, int tid) {
+// fragments <- global tile (row-major, row stride npad; L2 path: another SM may have produced it)
+__device__ __forceinline__ void frag_load_global(Frag& f, const double* tile, int npad, const Lane& L) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(tile + size_t(L.row0 + 8 * mt + L.g) * npad + L.col0 + 8 * nt + 2 * L.q));
+      f.c[mt][nt][0] = v.x; f.c[mt][nt][1] = v.y;
+    }
+}
+// fragments -> smem row-major (dst[r][c]) / transposed (dst[c][r])
+__device__ __forceinline__ void frag_store(double* dst, const Frag& f, const Lane& L) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      *reinterpret_cast<double2*>(dst + (L.row0 + 8 * mt + L.g) * kTS + L.col0 + 8 * nt + 2 * L.q) = make_double2(f.c[mt][nt][0], f.c[mt][nt][1]);
+}
+__device__ __forceinline__ void frag_store_t(double* dst, const Frag& f, const Lane& L) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) dst[(L.col0 + 8 * nt + 2 * L.q + e) * kTS + L.row0 + 8 * mt + L.g] = f.c[mt][nt][e];
+}
+// smem tile <- 64x64 global block with row stride ld, straight copy (16-byte accesses on both sides): final tiles
+// and block inverses are PUBLISHED TRANSPOSED, i.e. already in the [k][row] operand layout
+__device__ __forceinline__ void load_tile_cg(double* dst, const double* src, int ld, int tid) {
+#pragma unroll
   for (int e = tid; e < kCholNB * kCholNB / 2; e += 256) {
     const int r = e >> 5, c = (e & 31) * 2;
-    const double2 v = __ldcg(reinterpret_cast<const double2*>(src + size_t(r) * ld + c));
-    dst[c * kTS + r] = v.x;
-    dst[(c + 1) * kTS + r] = v.y;
+    *reinterpret_cast<double2*>(dst + r * kTS + c) = __ldcg(reinterpret_cast<const double2*>(src + size_t(r) * ld + c));
   }
 }
-// acc -= A * B^T, operands transposed in smem (see tile_gemm_tt)
-__device__ __forceinline__ void tile_gemm_tt_sub(const double* At, const double* Bt, double acc[4][4], int ty, int tx) {
-#pragma unroll 8
-  for (int c = 0; c < kCholNB; ++c) {
-    const double2 a01 = *reinterpret_cast<const double2*>(At + c * kTS + 4 * ty);
-    const double2 a23 = *reinterpret_cast<const double2*>(At + c * kTS + 4 * ty + 2);
-    const double2 b01 = *reinterpret_cast<const double2*>(Bt + c * kTS + 4 * tx);
-    const double2 b23 = *reinterpret_cast<const double2*>(Bt + c * kTS + 4 * tx + 2);
-    const double av[4] = {-a01.x, -a01.y, -a23.x, -a23.y};
-    const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+// smem tile (stride kTS) -> global 64x64 slot (row stride ld), straight copy with 16-byte accesses
+__device__ __forceinline__ void store_tile_global(double* dst, int ld, const double* src, int tid) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+  for (int e = tid; e < kCholNB * kCholNB / 2; e += 256) {
+    const int r = e >> 5, c = (e & 31) * 2;
+    *reinterpret_cast<double2*>(dst + size_t(r) * ld + c) = *reinterpret_cast<const double2*>(src + r * kTS + c);
   }
 }
-// register block -> smem, transposed (dst[c][r]) or row-major (dst[r][c])
-__device__ __forceinline__ void store_block_t(double* dst, const double acc[4][4], int ty, int tx) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    *reinterpret_cast<double2*>(dst + (4 * tx + j) * kTS + 4 * ty) = make_double2(acc[0][j], acc[1][j]);
-    *reinterpret_cast<double2*>(dst + (4 * tx + j) * kTS + 4 * ty + 2) = make_double2(acc[2][j], acc[3][j]);
+// s[tid & 63] partial: sum over q = (tid >> 6), q + 4, ... < n of part[q * stride + (tid & 63)], combined over the
+// four thread groups in a fixed order through red[4][64]; returns the total for tid < 64 (after a barrier)
+__device__ __forceinline__ double sum_partials(const double* part, int n, size_t stride, double* red, int tid) {
+  const int c = tid & 63, g = tid >> 6;
+  double s = 0.0;
+  int q = g;
+  for (; q + 12 < n; q += 16) {
+    const double v0 = __ldcg(part + size_t(q) * stride + c), v1 = __ldcg(part + size_t(q + 4) * stride + c);
+    const double v2 = __ldcg(part + size_t(q + 8) * stride + c), v3 = __ldcg(part + size_t(q + 12) * stride + c);
+    s += v0; s += v1; s += v2; s += v3;
   }
-}
-__device__ __forceinline__ void store_block(double* dst, const double acc[4][4], int ty, int tx) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    *reinterpret_cast<double2*>(dst + (4 * ty + i) * kTS + 4 * tx) = make_double2(acc[i][0], acc[i][1]);
-    *reinterpret_cast<double2*>(dst + (4 * ty + i) * kTS + 4 * tx + 2) = make_double2(acc[i][2], acc[i][3]);
-  }
-}
-__device__ __forceinline__ void store_block_global(double* M, int npad, int r0, int c0, const double acc[4][4], int ty, int tx) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double2* p = reinterpret_cast<double2*>(M + size_t(r0 + 4 * ty + i) * npad + c0 + 4 * tx);
-    p[0] = make_double2(acc[i][0], acc[i][1]);
-    p[1] = make_double2(acc[i][2], acc[i][3]);
-  }
+  for (; q < n; q += 4) s += __ldcg(part + size_t(q) * stride + c);
+  red[g * kCholNB + c] = s;
+  __syncthreads();
+  return tid < kCholNB ? (red[tid] + red[kCholNB + tid]) + (red[2 * kCholNB + tid] + red[3 * kCholNB + tid]) : 0.0;
 }
 // out[r] = sum_c Lrm[r][c] * v[c]  (Lrm row-major smem tile; 4 lanes per row); optional shared copy of the result
 __device__ __forceinline__ void tile_matvec(const double* Lrm, const double* v, double* out_global, int tid,
@@ -120,23 +163,12 @@ __device__ __forceinline__ void tile_matvec(const double* Lrm, const double* v, 
     if (out_shared) out_shared[r] = s;
   }
 }
-// out[c] = sum_r Lrm[r][c] * v[r]  (4 row phases per column, reduced through `red` [4][64])
-__device__ __forceinline__ void tile_matvec_t(const double* Lrm, const double* v, double* red, double* out_global, int tid) {
-  const int c = tid & 63, pt = tid >> 6;
-  double s = 0.0;
-#pragma unroll 4
-  for (int r = pt; r < kCholNB; r += 4) s = fma(Lrm[r * kTS + c], v[r], s);
-  red[pt * kCholNB + c] = s;
-  __syncthreads();
-  if (tid < kCholNB) out_global[tid] = (red[tid] + red[kCholNB + tid]) + (red[2 * kCholNB + tid] + red[3 * kCholNB + tid]);
-}
-
 }  // namespace
 
 struct CholDagArgs {
-  double* M;          // [npad][npad], lower tiles overwritten with L (diagonal tiles untouched)
+  double* M;          // [npad][npad], strictly-lower tiles overwritten with L(i,j)^T (transposed inside the tile slot)
   int npad;
-  double* Linv;       // [nb][64][64]
+  double* Linv;       // [nb][64][64]  TRANSPOSED block inverses (Linv_j^T), the B operand of the panel GEMMs
   const double* rhs;  // [npad]
   double* y;          // [npad] solution
   double* yf;         // [npad] forward-solved right-hand side
@@ -146,6 +178,17 @@ struct CholDagArgs {
   LmScalars* scal;
 };
 
+#ifdef CTVIO_CHOL_TIMING
+__device__ unsigned long long g_dag_stamps[32 * 16];
+#define DSTAMP(j, i) do { if (threadIdx.x == 0 && (j) < 32) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_dag_stamps[(j) * 16 + (i)] = t_; } } while (0)
+extern "C" int ctvio_debug_dag_stamps(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_dag_stamps, sizeof(g_dag_stamps)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define DSTAMP(j, i)
+#endif
+
 constexpr size_t kCholDagSmem = (6 * size_t(kTile) + 8 * kCholNB) * sizeof(double);
 
 __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
@@ -153,8 +196,8 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   double* D = reinterpret_cast<double*>(dag_smem);  // column CTA: diagonal tile (row-major) -> scratch of the factor
   double* Xi = D + kTile;                            // column CTA: Linv_j
   double* XiT = Xi + kTile;                          // column CTA: Linv_j^T
-  double* S1 = XiT + kTile;                          // operand A (transposed)
-  double* S2 = S1 + kTile;                           // operand B (transposed) / factor scratch
+  double* S1 = XiT + kTile;                          // operand A ([k][row]); later the owned final tile, transposed
+  double* S2 = S1 + kTile;                           // operand B ([k][row]) / factor scratch
   double* Lrm = S2 + kTile;                          // the owned off-diagonal tile once final, row-major
   double* rdiag = Lrm + kTile;                       // [64]
   double* vec = rdiag + kCholNB;                     // [64]
@@ -162,7 +205,7 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   double* red = vec2 + kCholNB;                      // [4][64]
   __shared__ int s_bad;
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
+  const Lane L = lane_of(tid);
   const int npad = a.npad, nb = npad / kCholNB, epoch = a.epoch;
   int* tile_ready = a.flags;
   int* bwd_ready = a.flags + nb * nb;
@@ -177,108 +220,112 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     int t = cta - nb, j = 0;
     while (t >= nb - 2 - j) { t -= nb - 2 - j; ++j; }
     const int i = j + 2 + t;
-    double acc[4][4];
-    load_block(acc, a.M, npad, i * kCholNB, j * kCholNB, ty, tx);
+    double* slot = a.M + size_t(i) * kCholNB * npad + j * kCholNB;
+    Frag acc;
+    frag_load_global(acc, slot, npad, L);
     for (int k = 0; k < j; ++k) {
       wait_flag(tile_ready + i * nb + k, epoch);
-      load_tile_t_cg(S1, a.M + size_t(i) * kCholNB * npad + k * kCholNB, npad, tid);
+      load_tile_cg(S1, a.M + size_t(i) * kCholNB * npad + k * kCholNB, npad, tid);
       wait_flag(tile_ready + j * nb + k, epoch);
-      load_tile_t_cg(S2, a.M + size_t(j) * kCholNB * npad + k * kCholNB, npad, tid);
+      load_tile_cg(S2, a.M + size_t(j) * kCholNB * npad + k * kCholNB, npad, tid);
       __syncthreads();
-      tile_gemm_tt_sub(S1, S2, acc, ty, tx);
+      tile_gemm_dmma<true>(S1, S2, acc, L);
       __syncthreads();
     }
     // L(i,j) = T * Linv_j^T
-    store_block_t(S1, acc, ty, tx);
+    frag_store_t(S1, acc, L);
     wait_flag(diag_ready + j, epoch);
-    load_tile_t_cg(S2, a.Linv + size_t(j) * kCholNB * kCholNB, kCholNB, tid);
+    load_tile_cg(S2, a.Linv + size_t(j) * kCholNB * kCholNB, kCholNB, tid);
     if (tid < kCholNB) vec[tid] = __ldcg(a.yf + j * kCholNB + tid);
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-    tile_gemm_tt(S1, S2, acc, ty, tx);
-    store_block_global(a.M, npad, i * kCholNB, j * kCholNB, acc, ty, tx);
-    store_block(Lrm, acc, ty, tx);
+    frag_zero(acc);
+    tile_gemm_dmma<false>(S1, S2, acc, L);
+    __syncthreads();  // everybody is done reading S1
+    frag_store(Lrm, acc, L);
+    frag_store_t(S1, acc, L);
     __syncthreads();
+    store_tile_global(slot, npad, S1, tid);  // published transposed
     tile_matvec(Lrm, vec, fwd_part + (size_t(i) * nb + j) * kCholNB, tid);
     post_flag(tile_ready + i * nb + j, epoch);
     // backward sweep: L(i,j)^T x_i
     wait_flag(x_ready + i, epoch);
     if (tid < kCholNB) vec[tid] = __ldcg(a.y + i * kCholNB + tid);
     __syncthreads();
-    tile_matvec_t(Lrm, vec, red, bwd_part + (size_t(j) * nb + i) * kCholNB, tid);
+    tile_matvec(S1, vec, bwd_part + (size_t(j) * nb + i) * kCholNB, tid);
     post_flag(bwd_ready + i * nb + j, epoch);
     return;
   }
 
   // ======================= column CTA j: tiles (j, j) and (j, j-1) =======================
   const int j = cta;
-  double accD[4][4], accS[4][4];
-  load_block(accD, a.M, npad, j * kCholNB, j * kCholNB, ty, tx);
-  if (j >= 1) load_block(accS, a.M, npad, j * kCholNB, (j - 1) * kCholNB, ty, tx);
+  DSTAMP(j, 0);
+  Frag accD, accS;
+  frag_load_global(accD, a.M + size_t(j) * kCholNB * npad + j * kCholNB, npad, L);
+  double* slot = a.M + size_t(j) * kCholNB * npad + (j >= 1 ? j - 1 : 0) * kCholNB;
+  if (j >= 1) frag_load_global(accS, slot, npad, L);
   for (int k = 0; k + 1 < j; ++k) {
     wait_flag(tile_ready + j * nb + k, epoch);
-    load_tile_t_cg(S1, a.M + size_t(j) * kCholNB * npad + k * kCholNB, npad, tid);
+    load_tile_cg(S1, a.M + size_t(j) * kCholNB * npad + k * kCholNB, npad, tid);
     wait_flag(tile_ready + (j - 1) * nb + k, epoch);
-    load_tile_t_cg(S2, a.M + size_t(j - 1) * kCholNB * npad + k * kCholNB, npad, tid);
+    load_tile_cg(S2, a.M + size_t(j - 1) * kCholNB * npad + k * kCholNB, npad, tid);
     __syncthreads();
-    tile_gemm_tt_sub(S1, S1, accD, ty, tx);
-    tile_gemm_tt_sub(S1, S2, accS, ty, tx);
+    tile_gemm_dmma<true>(S1, S1, accD, L);
+    tile_gemm_dmma<true>(S1, S2, accS, L);
     __syncthreads();
   }
+  DSTAMP(j, 1);
   if (j >= 1) {
     // L(j,j-1) = T * Linv_{j-1}^T, then the last update of the diagonal tile
-    store_block_t(S1, accS, ty, tx);
+    frag_store_t(S1, accS, L);
     wait_flag(diag_ready + (j - 1), epoch);
-    load_tile_t_cg(S2, a.Linv + size_t(j - 1) * kCholNB * kCholNB, kCholNB, tid);
+    DSTAMP(j, 2);
+    load_tile_cg(S2, a.Linv + size_t(j - 1) * kCholNB * kCholNB, kCholNB, tid);
     if (tid < kCholNB) vec[tid] = __ldcg(a.yf + (j - 1) * kCholNB + tid);
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) accS[r][c] = 0.0;
-    tile_gemm_tt(S1, S2, accS, ty, tx);
+    DSTAMP(j, 8);
+    frag_zero(accS);
+    tile_gemm_dmma<false>(S1, S2, accS, L);
     __syncthreads();  // everybody is done reading S1
-    store_block_global(a.M, npad, j * kCholNB, (j - 1) * kCholNB, accS, ty, tx);
-    store_block(Lrm, accS, ty, tx);
-    store_block_t(S1, accS, ty, tx);
+    DSTAMP(j, 9);
+    frag_store(Lrm, accS, L);
+    frag_store_t(S1, accS, L);
     __syncthreads();
+    DSTAMP(j, 10);
+    store_tile_global(slot, npad, S1, tid);  // published transposed
     tile_matvec(Lrm, vec, fwd_part + (size_t(j) * nb + (j - 1)) * kCholNB, tid);
+    DSTAMP(j, 11);
     post_flag(tile_ready + j * nb + (j - 1), epoch);
-    tile_gemm_tt_sub(S1, S1, accD, ty, tx);
+    DSTAMP(j, 3);
+    tile_gemm_dmma<true>(S1, S1, accD, L);
   }
-  store_block(D, accD, ty, tx);
+  frag_store(D, accD, L);
+  {  // right-hand side of block j for the forward substitution (all partials L(j,k) x_k are in: fixed summation order)
+    const double sp = sum_partials(fwd_part + size_t(j) * nb * kCholNB, j, kCholNB, red, tid);
+    if (tid < kCholNB) vec[tid] = a.rhs[j * kCholNB + tid] - sp;
+  }
   __syncthreads();
+  DSTAMP(j, 4);
   if (!factor_and_invert_64(D, Xi, XiT, S2, rdiag, &s_bad) && tid == 0) a.scal->chol_fail = 1;
-  // forward substitution of block j: x_j = Linv_j (rhs_j - sum_k L(j,k) x_k), partials summed in a fixed order
-  if (tid < kCholNB) {
-    double s = a.rhs[j * kCholNB + tid];
-    for (int k = 0; k < j; ++k) s -= __ldcg(fwd_part + (size_t(j) * nb + k) * kCholNB + tid);
-    vec[tid] = s;
-  }
-  for (int e = tid; e < kCholNB * kCholNB / 2; e += 256) {  // publish Linv_j
-    const int r = e >> 5, c = (e & 31) * 2;
-    *reinterpret_cast<double2*>(a.Linv + (size_t(j) * kCholNB + r) * kCholNB + c) = *reinterpret_cast<const double2*>(Xi + r * kTS + c);
-  }
-  __syncthreads();
+  DSTAMP(j, 5);
+  // forward substitution of block j: x_j = Linv_j (rhs_j - sum_k L(j,k) x_k)
+  store_tile_global(a.Linv + size_t(j) * kCholNB * kCholNB, kCholNB, XiT, tid);  // publish Linv_j^T
   tile_matvec(Xi, vec, a.yf + j * kCholNB, tid, vec2);  // shared copy for the backward sweep
   post_flag(diag_ready + j, epoch);
+  DSTAMP(j, 6);
 
   // backward sweep: x_j = Linv_j^T (yf_j - sum_{r > j} L(r,j)^T x_r)
   for (int r = j + 1; r < nb; ++r) wait_flag(bwd_ready + r * nb + j, epoch);
-  if (tid < kCholNB) {
-    double s = vec2[tid];
-    for (int r = j + 1; r < nb; ++r) s -= __ldcg(bwd_part + (size_t(j) * nb + r) * kCholNB + tid);
-    vec[tid] = s;
+  {
+    const double sp = sum_partials(bwd_part + (size_t(j) * nb + j + 1) * kCholNB, nb - 1 - j, kCholNB, red, tid);
+    if (tid < kCholNB) vec[tid] = vec2[tid] - sp;
   }
   __syncthreads();
   tile_matvec(XiT, vec, a.y + j * kCholNB, tid, vec2);  // XiT row-major = Linv^T
   post_flag(x_ready + j, epoch);
+  DSTAMP(j, 7);
   if (j >= 1) {
-    // own sub-diagonal tile: L(j,j-1)^T x_j for column CTA j-1  (post_flag's barrier made vec2 visible)
-    tile_matvec_t(Lrm, vec2, red, bwd_part + (size_t(j - 1) * nb + j) * kCholNB, tid);
+    // own sub-diagonal tile: L(j,j-1)^T x_j for column CTA j-1  (post_flag's barrier made vec2 visible; S1 = L^T)
+    tile_matvec(S1, vec2, bwd_part + (size_t(j - 1) * nb + j) * kCholNB, tid);
     post_flag(bwd_ready + j * nb + (j - 1), epoch);
   }
 }

@@ -5,7 +5,8 @@
 
 namespace ctvio {
 
-constexpr int kTS = kCholNB + 2;  // shared tile row stride (doubles): rows stay 16-B aligned
+constexpr int kTS = kCholNB + 4;  // shared tile row stride (doubles): rows stay 16-B aligned; 68 = 4 mod 8 keeps the
+                                  // m8n8k4 fragment loads ([4 k-rows][8 consecutive]) of a half-warp on distinct banks
 constexpr int kTile = kCholNB * kTS;
 constexpr size_t kCholCoopSmem = (5 * size_t(kTile) + 4 * kCholNB) * sizeof(double);
 

@@ -1286,6 +1286,47 @@ int ctvio_profile_kernels(ctvio_handle e, int32_t reps, int32_t flush_l2, double
   return CTVIO_OK;
 }
 
+int ctvio_selfcheck_solver(ctvio_handle e, int32_t reps, int32_t* mismatches, double* rel_residual) {
+  if (!e || !mismatches || !rel_residual || reps <= 0) return fail(CTVIO_ERR_INVALID, "bad argument");
+  cudaSetDevice(e->cfg.device);
+  int rc = prepare(e);
+  if (rc) return rc;
+  ensure_table(e);
+  cudaStream_t st = e->stream;
+  const int cur = e->cur;
+  evaluate(e, cur, cur, true);
+  LinearLaunch lin = linear_launch(e, cur);
+  launch_jacobi_scale(lin, st);
+  launch_reduced_system(lin, 1e4, st);
+  const size_t n = size_t(e->npad), len = n * n + n;  // M | rhs are contiguous
+  DevBuf<double> backup;
+  CUDA_OK(backup.reserve(len));
+  CUDA_OK(cudaMemcpyAsync(backup.p, lin.M, len * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  std::vector<double> hM(len), x0(n), x(n);
+  CUDA_OK(cudaMemcpyAsync(hM.data(), lin.M, len * sizeof(double), cudaMemcpyDeviceToHost, st));
+  *mismatches = 0;
+  for (int r = 0; r < reps; ++r) {
+    if (r > 0) CUDA_OK(cudaMemcpyAsync(lin.M, backup.p, len * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    launch_factor_solve(lin, st);
+    CUDA_OK(cudaMemcpyAsync((r == 0 ? x0 : x).data(), lin.y, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (r > 0 && std::memcmp(x.data(), x0.data(), n * sizeof(double)) != 0) ++*mismatches;
+  }
+  // residual of the first solve against the (full, symmetric) host copy
+  const double* rhs = hM.data() + n * n;
+  double rmax = 0, bmax = 0;
+  for (size_t i = 0; i < n; ++i) {
+    double s = -rhs[i];
+    for (size_t j = 0; j < n; ++j) s += hM[i * n + j] * x0[j];
+    rmax = std::max(rmax, std::fabs(s));
+    bmax = std::max(bmax, std::fabs(rhs[i]));
+  }
+  *rel_residual = bmax > 0 ? rmax / bmax : rmax;
+  cudaMemsetAsync(&e->d_scal.p->error_flags, 0, sizeof(int32_t), st);
+  CUDA_OK(cudaStreamSynchronize(st));
+  return CTVIO_OK;
+}
+
 int ctvio_measure_fp64_tflops(ctvio_handle e, double* tflops) {
   if (!e || !tflops) return fail(CTVIO_ERR_INVALID, "null argument");
   cudaSetDevice(e->cfg.device);

@@ -216,6 +216,11 @@ int ctvio_profile_kernels(ctvio_handle h, int32_t reps, int32_t flush_l2, double
 /* fp64 FMA micro-benchmark (8 independent DFMA chains per thread, all SMs): measured TFLOP/s, the compute
  * roofline denominator of the fp64-bound kernels (MEASURED_PEAKS.json has only HBM and bf16). */
 int ctvio_measure_fp64_tflops(ctvio_handle h, double* tflops);
+/* Self-check of the dense solver (K5) on the reduced system of the current state: the system is built once, then
+ * factored + solved `reps` times from the same input.  mismatches = number of repetitions whose solution differs
+ * BITWISE from the first one (must be 0: the sharded mode relies on a reproducible replicated solve);
+ * rel_residual = max_i |M x - rhs|_i / max_i |rhs|_i of the first solve, evaluated on the host. */
+int ctvio_selfcheck_solver(ctvio_handle h, int32_t reps, int32_t* mismatches, double* rel_residual);
 
 /* ---- multi-GPU: landmark-sharded residuals, one allreduce of the reduced system per LM step ----
  * Every rank holds the full (replicated) state and its own shard of image factors; rank 0 also holds

@@ -354,6 +354,11 @@ int ctvo_query_trajectory(void* h, int32_t n, const int64_t* t, double* q, doubl
   return CTVIO_OK;
 }
 
+int ctvo_selfcheck_solver(void*, int32_t, int32_t* mm, double* res) {
+  if (mm) *mm = 0;
+  if (res) *res = 0.0;
+  return 0;
+}
 int ctvo_measure_fp64_tflops(void*, double* v) {
   *v = 0.0;
   return CTVIO_OK;

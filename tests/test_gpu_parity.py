@@ -282,3 +282,14 @@ def test_c3_sequence_solve_marginalize_slide_matches_oracle(oracle_lib, cuda_lib
     assert np.isclose(sbg.final_cost, sbo.final_cost, rtol=2e-5)
     assert_state_parity(eg, eo, aux_rtol=1e-3)  # weakly observable accel biases / depths: looser than the knots
     assert 0 <= eg.GetLineDelay() <= syn.LD_UPPER
+
+
+@pytest.mark.parametrize("case", ["small", "c2", "c4"])
+def test_dense_solver_is_reproducible_and_accurate(cuda_lib, case):
+    """K5 (tile-DAG Cholesky with point-to-point flags): repeated solves of the same reduced system must agree
+    BITWISE (the sharded multi-GPU mode replicates this solve on every rank) and satisfy M x = rhs."""
+    w = {"small": small_window, "c2": syn.config_c2, "c4": syn.config_c4}[case]()
+    est = pkg.setup_estimator(cuda_lib, w)
+    mismatches, rel_res = est.SelfcheckSolver(reps=300 if case != "c4" else 100)
+    assert mismatches == 0
+    assert rel_res < 1e-9
