@@ -182,6 +182,9 @@ struct CholDagArgs {
 __device__ unsigned long long g_dag_stamps[32 * 16];
 #define DSTAMP(j, i) do { if (threadIdx.x == 0 && (j) < 32) { unsigned long long t_; \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_dag_stamps[(j) * 16 + (i)] = t_; } } while (0)
+extern "C" int ctvio_debug_fac_clk(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_fac_clk, sizeof(g_fac_clk)) == cudaSuccess ? 0 : -1;
+}
 extern "C" int ctvio_debug_dag_stamps(unsigned long long* out) {
   return cudaMemcpyFromSymbol(out, g_dag_stamps, sizeof(g_dag_stamps)) == cudaSuccess ? 0 : -1;
 }

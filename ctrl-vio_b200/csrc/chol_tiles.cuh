@@ -5,6 +5,13 @@
 
 namespace ctvio {
 
+#ifdef CTVIO_CHOL_TIMING
+__device__ long long g_fac_clk[8 * 4 * 8];
+#define FCLK(s, i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_fac_clk[(threadIdx.x >> 5) * 32 + (s) * 8 + (i)] = clock64(); } while (0)
+#else
+#define FCLK(s, i)
+#endif
+
 constexpr int kTS = kCholNB + 4;  // shared tile row stride (doubles): rows stay 16-B aligned; 68 = 4 mod 8 keeps the
                                   // m8n8k4 fragment loads ([4 k-rows][8 consecutive]) of a half-warp on distinct banks
 constexpr int kTile = kCholNB * kTS;
@@ -39,6 +46,19 @@ __device__ __forceinline__ void load_tile_transposed(double* dst, const double* 
   }
 }
 
+// 1/sqrt(x) for a positive, normal x without the special-case branch of rsqrt(): hardware seed (2^-22.9) plus one
+// third-order step  y (1 + e/2 + 3 e^2/8),  e = 1 - x y^2  -> relative error ~ e^3, i.e. full double precision.
+// Branch-free on purpose: the call sits in the serial pivot chain of the factorisation and a branch would stop the
+// compiler from interleaving the chain with the independent update FMAs around it.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(y * y), x, 1.0);
+  const double p = fma(e, 0.375, 0.5);
+  const double ye = y * e;
+  return fma(p, ye, y);
+}
+
 // 4x4 lower Cholesky of a (registers), reciprocal pivots rd.  Returns false on a bad pivot.
 __device__ __forceinline__ bool chol4(const double a[4][4], double l[4][4], double rd[4]) {
   bool ok = true;
@@ -61,129 +81,142 @@ __device__ __forceinline__ bool chol4(const double a[4][4], double l[4][4], doub
   return ok;
 }
 
-// In-place lower Cholesky of the 64x64 block D (row stride kTS) by 256 threads, then Xi = D^-1 (lower
-// triangular) and XiT = Xi^T.  T is a scratch area (>= 272 doubles), rdiag[64] receives 1/L_jj.
-// Right-looking on 4x4 register blocks; the next diagonal block is factored by its owner thread while everybody
-// else is still applying the rank-4 update (look-ahead); the inverse is produced in the same sweep by the threads
-// the elimination front has retired (forward substitution of the identity), so there is no separate inversion.
+// Lower Cholesky of the 64x64 block D (row-major, row stride kTS; destroyed) by 256 threads, producing the inverse
+// factor Xi = L^-1 (lower triangular, row-major) and XiT = Xi^T.  T is scratch (>= 256 + 16 * kTS doubles),
+// rdiag[64] receives 1 / L_jj.  Returns false on a non-positive pivot (the pivot is replaced by 1 so that the
+// sweep terminates with finite numbers).
+//
+// The serial pivot chain (rsqrt -> scale -> rank-1 update of the next pivot) is what bounds this routine, so it is
+// organised around that chain: four 16-column steps, each
+//   P1  ONE warp factors the 16x16 diagonal block out of registers (lane = row, columns broadcast by shuffles, the
+//       running diagonal kept in its own register so that the next pivot needs a single shuffle): no barriers or
+//       shared-memory round trips inside the 16 dependent columns;
+//   P2  the panel below (thread per row) and the block row of the inverse (thread per column: forward
+//       substitution of the identity / of the running sums W = -sum L X) by 16-deep substitution;
+//   P3  the trailing update of D and of the running sums in Xi as m8n8k4 fp64 tensor-core tiles (K = 16).
 __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, double* XiT, double* T, double* rdiag, int* s_bad) {
-  const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
-  double* Pt = T;          // [4][64]  current block column of L, transposed: Pt[m][row]  (bank-conflict-free operand)
-  double* Ldd = T + 256;   // [4][4]   current diagonal block of L
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  double* L16t = T;      // [16][16] current diagonal block of L, transposed: L16t[c][r] = L[r][c] (r >= c valid)
+  double* Pt = T + 256;  // [16][kTS] current block column of L, transposed: Pt[m][row]
   if (tid == 0) *s_bad = 0;
-  // a: block (ty, tx) of A while tx is ahead of the elimination front, afterwards (ty > tx) the running sum
-  //    W(ty, tx) = -sum_m L(ty, m) X(m, tx) of the inverse  X = L^-1  (forward substitution of the identity,
-  //    carried by the threads the trailing update has already retired).
-  double a[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const double2 v01 = *reinterpret_cast<const double2*>(D + (4 * ty + i) * kTS + 4 * tx);
-    const double2 v23 = *reinterpret_cast<const double2*>(D + (4 * ty + i) * kTS + 4 * tx + 2);
-    a[i][0] = v01.x; a[i][1] = v01.y; a[i][2] = v23.x; a[i][3] = v23.y;
-  }
   for (int e = tid; e < kTile; e += 256) Xi[e] = 0.0;
-  if (tid == 0) {  // diagonal block 0
-    double l[4][4], rd[4];
-    if (!chol4(a, l, rd)) *s_bad = 1;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      rdiag[i] = rd[i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) Ldd[i * 4 + j] = j <= i ? l[i][j] : 0.0;
-    }
-  }
   __syncthreads();
 #pragma unroll 1
-  for (int jb = 0; jb < 16; ++jb) {
-    // ---- phase 1: block column jb of L, block row jb of X ----
-    if ((tx == jb && ty > jb) || (ty == jb && tx <= jb)) {
-      double l[4][4], rd[4];
+  for (int s = 0; s < 4; ++s) {
+    const int c0 = 16 * s;
+    const int R = 48 - c0, C = c0 + 16;
+    FCLK(s, 0);
+    if (warp == 0) {
+      // ---- P1: 16x16 diagonal block, one warp, registers + shuffles ----
+      // lanes 16..31 mirror lanes 0..15 (same row, same arithmetic, no stores) so that the shuffles are full-warp
+      const int r = lane & 15;
+      double a[16];
+      const double* row = D + (c0 + r) * kTS + c0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        rd[c] = rdiag[4 * jb + c];
-        const double2 l01 = *reinterpret_cast<const double2*>(Ldd + 4 * c);
-        const double2 l23 = *reinterpret_cast<const double2*>(Ldd + 4 * c + 2);
-        l[c][0] = l01.x; l[c][1] = l01.y; l[c][2] = l23.x; l[c][3] = l23.y;
+      for (int c = 0; c < 16; c += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(row + c);
+        a[c] = v.x; a[c + 1] = v.y;
       }
-      if (ty > jb) {
-        // panel block by substitution: x[r][c] = (a[r][c] - sum_{m<c} x[r][m] l[c][m]) / l[c][c]
-        double x[4][4];
+      double d = row[r];  // running diagonal element of this lane's row: the next pivot needs one shuffle only
+      bool bad = false;
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+      for (int j = 0; j < 16; ++j) {
+        double ajj = __shfl_sync(0xffffffffu, d, j);
+        // positive and normal <=> biased exponent in [1, 2046] and sign clear (integer test: off the fp64 pipe)
+        const unsigned hi = static_cast<unsigned>(__double2hiint(ajj));
+        if (hi - 0x00100000u >= 0x7fe00000u) { bad = true; ajj = 1.0; }
+        const double rinv = rsqrt_pos(ajj);
+        const double lij = a[j] * rinv;
+        a[j] = lij;
+        d = fma(-lij, lij, d);
+        // column j goes to the others through its (final) line of the transposed block: L16t[j][row]
+        if (lane < 16) L16t[j * 16 + r] = lij;
+        if (lane == j) rdiag[c0 + j] = rinv;
+        __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            double t = a[r][c];
-#pragma unroll
-            for (int m = 0; m < c; ++m) t = fma(-x[r][m], l[c][m], t);
-            x[r][c] = t * rd[c];
-            a[r][c] = 0.0;  // from now on this thread accumulates W(ty, jb)
-          }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          *reinterpret_cast<double2*>(Pt + c * 64 + 4 * ty) = make_double2(x[0][c], x[1][c]);
-          *reinterpret_cast<double2*>(Pt + c * 64 + 4 * ty + 2) = make_double2(x[2][c], x[3][c]);
-        }
-      } else {
-        // X(jb, tx) = Ldd^-1 * W   (W = identity on the diagonal block): forward substitution per column
-        if (tx == jb) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) a[r][c] = r == c ? 1.0 : 0.0;
-        }
-        double x[4][4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            double t = a[r][c];
-#pragma unroll
-            for (int m = 0; m < r; ++m) t = fma(-l[r][m], x[m][c], t);
-            x[r][c] = t * rd[r];
-          }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          *reinterpret_cast<double2*>(Xi + (4 * jb + r) * kTS + 4 * tx) = make_double2(x[r][0], x[r][1]);
-          *reinterpret_cast<double2*>(Xi + (4 * jb + r) * kTS + 4 * tx + 2) = make_double2(x[r][2], x[r][3]);
-        }
+        for (int k = j + 1; k < 16; ++k) a[k] = fma(-lij, L16t[j * 16 + k], a[k]);
       }
+      if (bad && lane == 0) *s_bad = 1;
     }
+    FCLK(s, 1);
     __syncthreads();
-    // ---- phase 2: rank-4 update of the trailing blocks (tx > jb) and of the inverse sums (tx <= jb) ----
-    if (ty > jb && (tx <= jb || ty >= tx)) {
-      const bool inv = tx <= jb;
-      double lr[4][4], lc[4][4];  // lr[i][m] = L(4ty+i, m), lc[j][m]: B^T operand
+    // (a per-column hand-over of P1's columns to the P2 threads through a shared flag was measured slower: the
+    //  polling exposes every shared-memory latency that the compiler otherwise hoists out of the 16-column sweep)
+    if (tid >= 32 && tid - 32 < R) {
+      // ---- P2a: panel row i below the block, x L^T = a by substitution ----
+      const int i = c0 + 16 + (tid - 32);
+      double x[16];
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const double2 r01 = *reinterpret_cast<const double2*>(Pt + m * 64 + 4 * ty);
-        const double2 r23 = *reinterpret_cast<const double2*>(Pt + m * 64 + 4 * ty + 2);
-        lr[0][m] = r01.x; lr[1][m] = r01.y; lr[2][m] = r23.x; lr[3][m] = r23.y;
-        const double* Bsrc = inv ? Xi + (4 * jb + m) * kTS + 4 * tx : Pt + m * 64 + 4 * tx;
-        const double2 c01 = *reinterpret_cast<const double2*>(Bsrc);
-        const double2 c23 = *reinterpret_cast<const double2*>(Bsrc + 2);
-        lc[0][m] = c01.x; lc[1][m] = c01.y; lc[2][m] = c23.x; lc[3][m] = c23.y;
+      for (int c = 0; c < 16; c += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(D + i * kTS + c0 + c);
+        x[c] = v.x; x[c + 1] = v.y;
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int c = 0; c < 16; ++c) {  // right-looking: the dependent chain is one multiply + one FMA per column
+        x[c] *= rdiag[c0 + c];
+        Pt[c * kTS + i] = x[c];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int m = c + 1; m < 16; ++m) x[m] = fma(-x[c], L16t[c * 16 + m], x[m]);
+      }
+    } else if (tid >= 96 && tid - 96 < C) {
+      // ---- P2b: column cc of the block row of the inverse, L x = w (running sums, or the identity) ----
+      const int cc = tid - 96;
+      double x[16];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) a[i][j] = fma(-lr[i][m], lc[j][m], a[i][j]);
-      if (ty == jb + 1 && tx == jb + 1) {  // look-ahead: factor the next diagonal block right away
-        double l[4][4], rd[4];
-        if (!chol4(a, l, rd)) *s_bad = 1;
+      for (int r = 0; r < 16; ++r) x[r] = cc < c0 ? Xi[(c0 + r) * kTS + cc] : (cc - c0 == r ? 1.0 : 0.0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          rdiag[4 * tx + i] = rd[i];
+      for (int r = 0; r < 16; ++r) {
+        x[r] *= rdiag[c0 + r];
+        Xi[(c0 + r) * kTS + cc] = x[r];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) Ldd[i * 4 + j] = j <= i ? l[i][j] : 0.0;
-        }
+        for (int m = r + 1; m < 16; ++m) x[m] = fma(-L16t[r * 16 + m], x[r], x[m]);
       }
     }
+    FCLK(s, 3);
+    __syncthreads();
+    // ---- P3: rows >= c0+16:  D(:, >= c0+16) -= P P^T (lower tiles),  Xi(:, < c0+16) -= P X(c0..c0+15, :) ----
+    // warp = column tile: its B fragments are loaded once, row tiles are taken two at a time (independent chains)
+    if (s < 3) {
+      const int ct = warp, rt0 = (c0 + 16) >> 3;
+      const bool inv = 8 * ct < C;
+      const double* pb = inv ? Xi + (c0 + q) * kTS + 8 * ct + g : Pt + q * kTS + 8 * ct + g;
+      double* base = (inv ? Xi : D) + g * kTS + 8 * ct + 2 * q;
+      double bv[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) bv[kk] = pb[4 * kk * kTS];
+      int rt = ct > rt0 ? ct : rt0;
+      for (; rt + 1 < 8; rt += 2) {
+        double2 c0v = *reinterpret_cast<const double2*>(base + 8 * rt * kTS);
+        double2 c1v = *reinterpret_cast<const double2*>(base + 8 * (rt + 1) * kTS);
+        const double* pa = Pt + q * kTS + 8 * rt + g;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const double a0 = -pa[4 * kk * kTS], a1 = -pa[4 * kk * kTS + 8];
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c0v.x), "+d"(c0v.y) : "d"(a0), "d"(bv[kk]));
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c1v.x), "+d"(c1v.y) : "d"(a1), "d"(bv[kk]));
+        }
+        *reinterpret_cast<double2*>(base + 8 * rt * kTS) = c0v;
+        *reinterpret_cast<double2*>(base + 8 * (rt + 1) * kTS) = c1v;
+      }
+      if (rt < 8) {
+        double2 c0v = *reinterpret_cast<const double2*>(base + 8 * rt * kTS);
+        const double* pa = Pt + q * kTS + 8 * rt + g;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const double a0 = -pa[4 * kk * kTS];
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c0v.x), "+d"(c0v.y) : "d"(a0), "d"(bv[kk]));
+        }
+        *reinterpret_cast<double2*>(base + 8 * rt * kTS) = c0v;
+      }
+    }
+    FCLK(s, 5);
     __syncthreads();
   }
-  // XiT = Xi^T (B operand of the slab GEMM)
+  // XiT = Xi^T (B operand of the panel GEMMs)
   for (int e = tid; e < kCholNB * kCholNB; e += 256) {
     const int r = e >> 6, c = e & 63;
     XiT[c * kTS + r] = Xi[r * kTS + c];

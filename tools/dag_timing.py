@@ -20,3 +20,10 @@ for name in ("c2", "c4"):
     d = t[j]
     print("  col %d slab detail (us): Linv^T+x loaded %.2f | gemm %.2f | stores %.2f | matvec %.2f | fence+flag %.2f" % (
         j, (d[8] - d[2]) / 1e3, (d[9] - d[8]) / 1e3, (d[10] - d[9]) / 1e3, (d[11] - d[10]) / 1e3, (d[3] - d[11]) / 1e3))
+    fc = (C.c_longlong * 256)()
+    LIB.lib.ctvio_debug_fac_clk(fc)
+    fc = np.array(fc[:], dtype=np.int64).reshape(8, 4, 8)
+    t00 = fc[0, 0, 0]
+    print("  diag factor of column 0: arrival (cycles since start) of each warp's lane 0 BEFORE the barrier ending P1 | P2 | P3, per 16-col step")
+    for s_ in range(4):
+        print("   step %d: " % s_ + "  ".join("w%d %5d %5d %5d" % (w_, fc[w_, s_, 1] - t00, fc[w_, s_, 3] - t00, fc[w_, s_, 5] - t00) for w_ in (0, 1, 2, 3, 7)))
