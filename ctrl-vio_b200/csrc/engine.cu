@@ -120,10 +120,12 @@ struct ctvio_engine {
   // landmark layout / schur batches
   std::vector<int32_t> h_lo, h_hi;
   std::vector<int64_t> h_woff;
-  DevBuf<int32_t> d_lo, d_hi, d_schur_order, d_wide;
+  DevBuf<int32_t> d_lo, d_hi;
+  DevBuf<SchurEntry> d_schur_list;
   DevBuf<int64_t> d_woff;
-  DevBuf<SchurBatch> d_batches;
-  int n_batches = 0, n_wide = 0;
+  DevBuf<SchurTileItem> d_schur_items;
+  DevBuf<double> d_lis, d_lc;
+  int n_schur_items = 0;
   DevBuf<uint8_t> d_cmask, d_active;
   std::vector<uint8_t> h_cmask, h_active;
 
@@ -264,37 +266,6 @@ int prepare(ctvio_engine* e) {
     CUDA_OK(e->d_lo.upload(e->h_lo, st));
     CUDA_OK(e->d_hi.upload(e->h_hi, st));
     CUDA_OK(e->d_woff.upload(e->h_woff, st));
-    // ---- schur batches: landmarks sorted by range, greedy batches with union range <= kSchurMaxDim ----
-    std::vector<int32_t> order, wide;
-    for (int l = 0; l < e->nL; ++l) {
-      if (e->h_hi[l] == 0) continue;  // unobserved landmark: h_l = 0, step 0
-      if (e->h_hi[l] - e->h_lo[l] > kSchurMaxDim) wide.push_back(l);
-      else order.push_back(l);
-    }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      if (e->h_lo[a] != e->h_lo[b]) return e->h_lo[a] < e->h_lo[b];
-      return e->h_hi[a] < e->h_hi[b];
-    });
-    // batch size adapts to the landmark count so that C2-sized windows still use many SMs
-    const int bcap = std::max(8, std::min(kSchurBatch, int(order.size() + 147) / 148));
-    std::vector<SchurBatch> batches;
-    for (size_t k = 0; k < order.size();) {
-      SchurBatch b{int32_t(k), 0, e->h_lo[order[k]], e->h_hi[order[k]]};
-      while (k < order.size() && b.count < bcap) {
-        const int l = order[k];
-        const int ulo = std::min(b.ulo, e->h_lo[l]), uhi = std::max(b.uhi, e->h_hi[l]);
-        if (uhi - ulo > kSchurMaxDim) break;
-        b.ulo = ulo; b.uhi = uhi;
-        ++b.count; ++k;
-      }
-      batches.push_back(b);
-    }
-    e->n_batches = int(batches.size());
-    e->n_wide = int(wide.size());
-    CUDA_OK(e->d_schur_order.upload(order, st));
-    CUDA_OK(e->d_batches.upload(batches, st));
-    CUDA_OK(e->d_wide.upload(wide, st));
-
     // ---- imu / bias factors ----
     const int ni = int(e->imu.size());
     std::vector<longlong2> it(ni);
@@ -357,6 +328,49 @@ int prepare(ctvio_engine* e) {
     e->npad = ((d.np + kCholNB - 1) / kCholNB) * kCholNB;
     CUDA_OK(e->d_M.reserve(size_t(e->npad) * e->npad + 3 * size_t(e->npad)));  // M | rhs | diagA | yf (all-reduce slab)
     CUDA_OK(e->d_Linv.reserve(size_t(e->npad) * kCholNB));
+    {
+      // ---- K4 work items: per 64x64 tile (ti >= tj) of the reduced system the landmarks whose knot-dim range
+      // [lo, hi) touches both blocks, cut into parts of `part` landmarks so that about two waves of CTAs exist
+      // whatever the window size (the line-delay row / column is a matrix-vector product done by the diagonal tiles) ----
+      const int T = e->npad / kCholNB;
+      std::vector<std::vector<int32_t>> lists(size_t(T) * (T + 1) / 2);
+      std::vector<int32_t> order;
+      for (int l = 0; l < e->nL; ++l)
+        if (e->h_hi[l] > 0) order.push_back(l);
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (e->h_lo[a] != e->h_lo[b]) return e->h_lo[a] < e->h_lo[b];
+        return e->h_hi[a] < e->h_hi[b];
+      });
+      size_t total = 0;
+      for (int l : order) {
+        int blocks[64], nbk = 0;
+        const int b0 = e->h_lo[l] / kCholNB, b1 = (e->h_hi[l] - 1) / kCholNB;
+        for (int b = b0; b <= b1 && nbk < 63; ++b) blocks[nbk++] = b;
+        for (int x = 0; x < nbk; ++x)
+          for (int y = 0; y <= x; ++y) {
+            lists[size_t(blocks[x]) * (blocks[x] + 1) / 2 + blocks[y]].push_back(l);
+            ++total;
+          }
+      }
+      int n_sm = 148;
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, e->cfg.device);
+      const int part = std::max(32, int((total / size_t(2 * n_sm) + 31) / 32) * 32);
+      std::vector<SchurTileItem> items;
+      std::vector<SchurEntry> flat;
+      flat.reserve(total);
+      for (int ti = 0; ti < T; ++ti)
+        for (int tj = 0; tj <= ti; ++tj) {
+          const std::vector<int32_t>& v = lists[size_t(ti) * (ti + 1) / 2 + tj];
+          for (size_t s0 = 0; s0 < v.size(); s0 += part)
+            items.push_back(SchurTileItem{ti, tj, int32_t(flat.size() + s0), int32_t(std::min(v.size() - s0, size_t(part)))});
+          for (int32_t l : v) flat.push_back(SchurEntry{l, e->h_lo[l], e->h_hi[l], 0, e->h_woff[l]});
+        }
+      e->n_schur_items = int(items.size());
+      CUDA_OK(e->d_schur_list.upload(flat, st));
+      CUDA_OK(e->d_schur_items.upload(items, st));
+      CUDA_OK(e->d_lis.reserve(e->nL));
+      CUDA_OK(e->d_lc.reserve(e->nL));
+    }
     CUDA_OK(e->d_chol_part.reserve(chol_dag_part_len(e->npad)));
     if (chol_dag_flags_len(e->npad) > e->d_chol_flags.cap) {
       CUDA_OK(e->d_chol_flags.reserve(chol_dag_flags_len(e->npad)));
@@ -512,11 +526,10 @@ LinearLaunch linear_launch(ctvio_engine* e, int nb) {
   a.dims = e->dims();
   a.ne = e->ne(nb);
   a.lm = e->lml();
-  a.schur_order = e->d_schur_order.p;
-  a.batches = e->d_batches.p;
-  a.n_batches = e->n_batches;
-  a.wide_lms = e->d_wide.p;
-  a.n_wide = e->n_wide;
+  a.schur_list = e->d_schur_list.p;
+  a.schur_items = e->d_schur_items.p;
+  a.n_schur_items = e->n_schur_items;
+  a.lis = e->d_lis.p; a.lc = e->d_lc.p;
   a.cmask = e->d_cmask.p;
   a.active = e->d_active.p;
   a.sc = e->d_sc.p; a.sl = e->d_sl.p;
@@ -559,10 +572,11 @@ int lm_step(ctvio_engine* e, int nb, double radius) {
 }
 
 // one pass over all residual blocks at state buffer xb into normal-equation buffer nb
-void evaluate(ctvio_engine* e, int xb, int nb, bool full) {
+// reset_cost = false: cost_eval was already zeroed by scale_copy_kernel of the same LM step
+void evaluate(ctvio_engine* e, int xb, int nb, bool full, bool reset_cost = true) {
   cudaStream_t st = e->stream;
   if (full) cudaMemsetAsync(e->ne_slab[nb].p, 0, e->ne_slab_len * sizeof(double), st);
-  cudaMemsetAsync(&e->d_scal.p->cost_eval, 0, sizeof(double), st);
+  if (reset_cost) cudaMemsetAsync(&e->d_scal.p->cost_eval, 0, sizeof(double), st);
   // fork: the (latency-bound) IMU + bias + prior kernels overlap the visual kernel on a second stream
   // sharded mode: IMU / bias / prior factors live on rank 0 only (every rank holds its own landmark shard)
   const bool fork = (e->rank == 0) && (!e->imu.empty() || !e->biasf.empty() || e->prior.n > 0);
@@ -883,7 +897,7 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
   int iter = 0;
   int term = CTVIO_TERM_NO_CONVERGENCE;
 
-  auto apply = [&](int from, int to, double alpha) {
+  auto apply = [&](int from, int to, double alpha, bool reset = true) {
     ApplyLaunch ap;
     ap.dims = d;
     ap.x = e->x[from].ptrs();
@@ -895,7 +909,7 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     ap.clamp_ld = e->opt.fix_ld ? 0 : 1;
     ap.ld_lower = e->opt.ld_lower; ap.ld_upper = e->opt.ld_upper;
     ap.scal = e->d_scal.p;
-    e->launches += launch_apply_step(ap, st);
+    e->launches += launch_apply_step(ap, st, reset);
   };
 
   while (true) {
@@ -908,11 +922,12 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     rc = lm_step(e, cur, radius);
     if (rc) return rc;
     sum.num_linear_solves++;
-    apply(cur, cand, 1.0);
-    evaluate(e, cand, cand, true);
+    // (scale_copy_kernel of lm_step zeroed step_norm2 / x_norm2 / cost_eval / gmax: no memsets on the stream)
+    apply(cur, cand, 1.0, false);
+    evaluate(e, cand, cand, true, false);
     sum.num_jacobian_evals++;
     LinearLaunch linc = linear_launch(e, cand);
-    e->launches += launch_gradient_norm(linc, e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st);
+    e->launches += launch_gradient_norm(linc, e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st, false);
     rc = allreduce_scalars(e);
     if (rc) return rc;
     rc = read_scalars(e);
@@ -1312,7 +1327,9 @@ int ctvio_selfcheck_solver(ctvio_handle e, int32_t reps, int32_t* mismatches, do
     CUDA_OK(cudaStreamSynchronize(st));
     if (r > 0 && std::memcmp(x.data(), x0.data(), n * sizeof(double)) != 0) ++*mismatches;
   }
-  // residual of the first solve against the (full, symmetric) host copy
+  // residual of the first solve against the host copy (only the lower triangle of M is maintained by K4)
+  for (size_t i = 0; i < n; ++i)
+    for (size_t j = i + 1; j < n; ++j) hM[i * n + j] = hM[j * n + i];
   const double* rhs = hM.data() + n * n;
   double rmax = 0, bmax = 0;
   for (size_t i = 0; i < n; ++i) {

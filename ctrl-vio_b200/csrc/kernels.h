@@ -97,9 +97,15 @@ struct LandmarkLayout {
   const int64_t* woff;   // [nL+1] offsets into W
 };
 
-struct SchurBatch {
-  int32_t first, count;  // landmarks [first, first+count) in schur order
-  int32_t ulo, uhi;      // union knot-dim range
+// K4 list entry: a landmark with its coupling-row layout inlined (one load instead of a chain of three)
+struct SchurEntry {
+  int32_t l, lo, hi, pad;
+  int64_t woff;  // offset of W_l[lo] in the compact coupling array
+};
+// K4 work item: part of the landmark list of one 64x64 output tile (ti >= tj) of the reduced system
+struct SchurTileItem {
+  int32_t ti, tj;        // block row / column of the tile
+  int32_t first, count;  // landmark ids schur_list[first, first + count)
 };
 
 // scalars exchanged with the host once per LM step
@@ -176,16 +182,16 @@ struct LinearLaunch {
   ProblemDims dims;
   NormalEqPtrs ne;
   LandmarkLayout lm;
-  const int32_t* schur_order;   // [nL] landmark ids in batch order
-  const SchurBatch* batches;
-  int32_t n_batches;
-  const int32_t* wide_lms;      // landmarks whose own range exceeds kSchurMaxDim (slow path)
-  int32_t n_wide;
+  const SchurEntry* schur_list; // concatenated per-tile landmark lists
+  const SchurTileItem* schur_items;
+  int32_t n_schur_items;
+  double* lis;                  // [nL] sl / sqrt(hh): scale of the landmark's coupling row (written by scale_copy_kernel)
+  double* lc;                   // [nL] lis * g_l
   const uint8_t* cmask;
   const uint8_t* active;        // [np + nL]
   double* sc;                   // [np] Jacobi scale
   double* sl;                   // [nL]
-  double* M;                    // [npad][npad] reduced system (full symmetric), npad = multiple of kCholNB
+  double* M;                    // [npad][npad] reduced system, LOWER triangle of 64x64 tiles valid (diagonal tiles full)
   double* Linv;                 // [npad/NB][NB][NB] inverses of the diagonal Cholesky blocks
   double* rhs;                  // [npad]
   double* y;                    // [npad]
@@ -218,8 +224,9 @@ int launch_step_vectors(const LinearLaunch& a, cudaStream_t s);
 int launch_add_damping(const LinearLaunch& a, double radius, cudaStream_t s);
 int launch_extract_diag(const LinearLaunch& a, cudaStream_t s);
 int launch_jacobi_scale_from_diag(const LinearLaunch& a, cudaStream_t s);
+// reset = false: the accumulator was already zeroed by scale_copy_kernel of the same LM step
 int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld, double ld_lower, double ld_upper,
-                         cudaStream_t s);
+                         cudaStream_t s, bool reset = true);
 
 struct ApplyLaunch {
   int32_t count_camera;     // sharded mode: only rank 0 counts the (replicated) camera blocks in the norms
@@ -233,7 +240,7 @@ struct ApplyLaunch {
   double ld_lower, ld_upper;
   LmScalars* scal;
 };
-int launch_apply_step(const ApplyLaunch& a, cudaStream_t s);
+int launch_apply_step(const ApplyLaunch& a, cudaStream_t s, bool reset = true);
 int launch_gauge_realign(const StatePtrs& st, int nK, int min_idx, const double* R0_t0_dev, cudaStream_t s);
 
 struct QueryLaunch {

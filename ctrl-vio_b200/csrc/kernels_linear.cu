@@ -6,8 +6,13 @@
 //   K4  scale_copy + schur     reduced camera system  M = S A S + D^2 - sum_l w_l w_l' / h_l
 //   K5  chol_panel/chol_update blocked right-looking Cholesky (NB = 64) + block triangular solves
 //   K6  backsub / quad / apply landmark back-substitution, model cost change, x (+) delta, norms
-// The Schur complement is a grouped SYRK: landmarks are batched by knot range on the host so one CTA
-// reduces a batch in a register-tiled 8x8 SYRK and flushes once.
+// The Schur complement is owner-computes by OUTPUT tile: every 64x64 tile of the lower triangle of M gets the list of
+// landmarks whose coupling row touches both of its blocks (built on the host), split into parts so that small
+// windows still fill the GPU; a CTA builds the scaled rows of 32 landmarks at a time in shared memory and reduces
+// them with fp64 tensor-core tiles (m8n8k4), then flushes its tile once.
+#include <algorithm>
+
+#include "dmma_tiles.cuh"
 #include "kernels.h"
 
 namespace ctvio {
@@ -46,6 +51,17 @@ int launch_jacobi_scale(const LinearLaunch& a, cudaStream_t s) {
 __global__ void scale_copy_kernel(LinearLaunch a, double radius) {
   const int npad = a.npad, np = a.dims.np;
   const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx < size_t(a.dims.nL)) {
+    // per-landmark prologue of the Schur complement: damped diagonal and the scale of the coupling row
+    const int l = int(idx);
+    const double sl = a.sl[l], hl = a.ne.hl[l];
+    const double hs = sl * sl * hl;
+    const double hh = hl > 0.0 ? hs + fmin(fmax(hs, kMinLmDiag), kMaxLmDiag) / radius : 0.0;
+    const double is = hh > 0.0 ? rsqrt(hh) * sl : 0.0;
+    a.hh[l] = hh;
+    a.lis[l] = is;
+    a.lc[l] = is * a.ne.gl[l];
+  }
   if (idx >= size_t(npad) * npad) return;
   const int i = int(idx / npad), j = int(idx % npad);
   double m;
@@ -70,128 +86,138 @@ __global__ void scale_copy_kernel(LinearLaunch a, double radius) {
   if (j == 0) {
     a.rhs[i] = (i < np && !a.cmask[i]) ? a.sc[i] * a.ne.gc[i] : 0.0;
     if (i == 0) {
+      // per-step accumulators of the kernels that follow in this LM step (no separate memsets on the stream)
       a.scal->gd = 0.0;
       a.scal->dHd = 0.0;
       a.scal->dir_max = 0.0;
       a.scal->chol_fail = 0;
+      a.scal->step_norm2 = 0.0;
+      a.scal->x_norm2 = 0.0;
+      a.scal->cost_eval = 0.0;
+      a.scal->gmax = 0.0;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: Schur complement of one landmark batch
-__global__ void __launch_bounds__(256) schur_batch_kernel(LinearLaunch a, double radius) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  double* V = reinterpret_cast<double*>(dyn_smem);
-  const SchurBatch b = a.batches[blockIdx.x];
-  const int U = b.uhi - b.ulo;
-  const int LD = ((U + 2 + 7) / 8) * 8;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ild = a.dims.idx_ld;
-  // prologue: v_l = sl * W_l o sc / sqrt(hh_l), extra columns: line delay, scaled landmark gradient
-  for (int r = warp; r < b.count; r += 8) {
-    const int l = a.schur_order[b.first + r];
-    const double sl = a.sl[l];
-    const double hs = sl * sl * a.ne.hl[l];
-    const double hh = hs + fmin(fmax(hs, kMinLmDiag), kMaxLmDiag) / radius;
-    if (lane == 0) a.hh[l] = hh;
-    const double is = rsqrt(hh) * sl;
-    const int lo = a.lm.lo[l], hi = a.lm.hi[l];
-    const double* Wl = a.ne.W + a.lm.woff[l] - lo;
-    double* row = V + size_t(r) * LD;
-    for (int c = lane; c < LD; c += 32) {
-      const int g = b.ulo + c;
-      double v = 0.0;
-      if (c < U) {
-        if (g >= lo && g < hi) v = is * Wl[g] * a.sc[g];
-      } else if (c == U) {
-        v = is * a.ne.wld[l] * a.sc[ild];
-      } else if (c == U + 1) {
-        v = is * a.ne.gl[l];
-      }
-      row[c] = v;
-    }
+// K4: Schur complement, one part of one output tile per CTA
+constexpr int kSchurKC = 32;  // landmarks per shared-memory operand chunk
+// scaled coupling rows of landmark chunk [c0, c0 + 32) restricted to the tile's blocks -> registers
+// (thread = (landmark k, 8 consecutive dims)); cl = {c_l, v_l[line delay], first-block flag}
+__device__ __forceinline__ void schur_fetch(const LinearLaunch& a, const SchurTileItem& it, int c0, int k, int dseg,
+                                            const double* scA, const double* scB, double sc_ld, bool diag, double va[8],
+                                            double vb[8], double cl[3]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) va[e] = vb[e] = 0.0;
+  cl[0] = cl[1] = cl[2] = 0.0;
+  if (c0 + k >= it.count) return;
+  const SchurEntry en = a.schur_list[it.first + c0 + k];
+  const double is = a.lis[en.l];
+  const double* Wl = a.ne.W + en.woff - en.lo;
+  const int ga0 = kCholNB * it.ti + dseg, gb0 = kCholNB * it.tj + dseg;
+  cl[0] = a.lc[en.l];
+  cl[1] = is * a.ne.wld[en.l] * sc_ld;
+  cl[2] = en.lo / kCholNB == it.ti ? 1.0 : 0.0;  // exactly one diagonal tile counts the landmark's ld-ld / ld-rhs terms
+  if (ga0 + 8 > en.lo && ga0 < en.hi) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (ga0 + e >= en.lo && ga0 + e < en.hi) va[e] = is * Wl[ga0 + e] * scA[dseg + e];
   }
+  if (!diag && gb0 + 8 > en.lo && gb0 < en.hi) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (gb0 + e >= en.lo && gb0 + e < en.hi) vb[e] = is * Wl[gb0 + e] * scB[dseg + e];
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) schur_tile_kernel(LinearLaunch a) {
+  __shared__ __align__(16) double At[kSchurKC * kTS];
+  __shared__ __align__(16) double Bt[kSchurKC * kTS];
+  __shared__ double scA[kCholNB], scB[kCholNB], cvec[3][kSchurKC];
+  const SchurTileItem it = a.schur_items[blockIdx.x];
+  const int tid = threadIdx.x;
+  const Lane L = lane_of(tid);
+  const int np = a.dims.np, npad = a.npad, ild = a.dims.idx_ld;
+  const bool diag = it.ti == it.tj;
+  if (tid < kCholNB) {
+    const int ga = kCholNB * it.ti + tid, gb = kCholNB * it.tj + tid;
+    scA[tid] = (ga < np && !a.cmask[ga]) ? a.sc[ga] : 0.0;
+    scB[tid] = (gb < np && !a.cmask[gb]) ? a.sc[gb] : 0.0;
+  }
+  const double sc_ld = a.cmask[ild] ? 0.0 : a.sc[ild];
   __syncthreads();
-  const int nt = LD / 8;
-  const int ntiles = nt * (nt + 1) / 2;
-  const int npad = a.npad;
-  for (int t = tid; t < ntiles; t += 256) {
-    int ti = 0, rem = t;
-    while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
-    const int tj = ti + rem;
-    double acc[64];
+  Frag acc;
+  frag_zero(acc);
+  // diagonal tiles also own, for their block: rhs -= sum_l v_l c_l and the line-delay row M[ld][block] -= sum_l v_l vld_l;
+  // lanes 0..31 of warp 0 (one landmark slot each) collect the ld-ld and ld-rhs terms of the landmarks starting here
+  double racc = 0.0, lacc = 0.0, ll = 0.0, lr = 0.0;
+  const int k = tid >> 3, dseg = (tid & 7) * 8;
+  double va[8], vb[8], cl[3];
+  schur_fetch(a, it, 0, k, dseg, scA, scB, sc_ld, diag, va, vb, cl);
+  for (int c0 = 0; c0 < it.count; c0 += kSchurKC) {
 #pragma unroll
-    for (int e = 0; e < 64; ++e) acc[e] = 0.0;
-    for (int r = 0; r < b.count; ++r) {
-      const double2* ra = reinterpret_cast<const double2*>(V + size_t(r) * LD + ti * 8);
-      const double2* rb = reinterpret_cast<const double2*>(V + size_t(r) * LD + tj * 8);
-      double av[8], bv[8];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const double2 x = ra[e], y = rb[e];
-        av[2 * e] = x.x; av[2 * e + 1] = x.y;
-        bv[2 * e] = y.x; bv[2 * e + 1] = y.y;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fma(av[i], bv[j], acc[i * 8 + j]);
+    for (int e = 0; e < 8; e += 2) {
+      *reinterpret_cast<double2*>(At + k * kTS + dseg + e) = make_double2(va[e], va[e + 1]);
+      if (!diag) *reinterpret_cast<double2*>(Bt + k * kTS + dseg + e) = make_double2(vb[e], vb[e + 1]);
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double val = acc[i * 8 + j];
-        const int la = ti * 8 + i, lb = tj * 8 + j;
-        if (val == 0.0 || la > lb || la > U || lb > U + 1) continue;
-        const int ga = la < U ? b.ulo + la : ild;
-        if (lb == U + 1) {
-          atomicAdd(a.rhs + ga, -val);
-          continue;
+    if ((tid & 7) == 0) { cvec[0][k] = cl[0]; cvec[1][k] = cl[1]; cvec[2][k] = cl[2]; }
+    __syncthreads();
+    // the next chunk's global loads fly while the tensor cores chew on this one
+    if (c0 + kSchurKC < it.count) schur_fetch(a, it, c0 + kSchurKC, k, dseg, scA, scB, sc_ld, diag, va, vb, cl);
+    tile_gemm_dmma<false, kSchurKC>(At, diag ? At : Bt, acc, L);
+    if (diag) {
+      if (tid < kCholNB) {
+#pragma unroll 8
+        for (int kk = 0; kk < kSchurKC; ++kk) {
+          const double v = At[kk * kTS + tid];
+          racc = fma(v, cvec[0][kk], racc);
+          lacc = fma(v, cvec[1][kk], lacc);
         }
-        const int gb = lb < U ? b.ulo + lb : ild;
-        atomicAdd(a.M + size_t(ga) * npad + gb, -val);
-        if (ga != gb) atomicAdd(a.M + size_t(gb) * npad + ga, -val);
+      } else if (tid < kCholNB + kSchurKC) {
+        const int kk = tid - kCholNB;
+        const double vld = cvec[1][kk] * cvec[2][kk];
+        ll = fma(vld, cvec[1][kk], ll);
+        lr = fma(vld, cvec[0][kk], lr);
       }
+    }
+    __syncthreads();
   }
-}
-
-// slow path for landmarks whose own knot range is wider than kSchurMaxDim: one warp per landmark
-__global__ void schur_wide_kernel(LinearLaunch a, double radius) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= a.n_wide) return;
-  const int l = a.wide_lms[w];
-  const double sl = a.sl[l];
-  const double hs = sl * sl * a.ne.hl[l];
-  const double hh = hs + fmin(fmax(hs, kMinLmDiag), kMaxLmDiag) / radius;
-  if (lane == 0) a.hh[l] = hh;
-  const double inv = sl * sl / hh;
-  const int lo = a.lm.lo[l], hi = a.lm.hi[l], n = hi - lo + 1, ild = a.dims.idx_ld, npad = a.npad;
-  const double* Wl = a.ne.W + a.lm.woff[l] - lo;
-  for (int e = lane; e < n * n; e += 32) {
-    const int ia = e / n, ib = e % n;
-    const int ga = ia < n - 1 ? lo + ia : ild, gb = ib < n - 1 ? lo + ib : ild;
-    const double wa = (ia < n - 1 ? Wl[ga] : a.ne.wld[l]) * a.sc[ga];
-    const double wb = (ib < n - 1 ? Wl[gb] : a.ne.wld[l]) * a.sc[gb];
-    const double v = wa * wb * inv;
-    if (v != 0.0) atomicAdd(a.M + size_t(ga) * npad + gb, -v);
-    if (ib == 0) {
-      const double g = wa * a.ne.gl[l] * inv;
-      if (g != 0.0) atomicAdd(a.rhs + ga, -g);
+  // flush: M_tile -= acc (several parts may share a tile: fp64 RED atomics), rhs_block -= racc
+  double* tile = a.M + size_t(kCholNB) * it.ti * npad + kCholNB * it.tj;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double v = acc.c[mt][nt][e];
+        if (v != 0.0) atomicAdd(tile + size_t(L.row0 + 8 * mt + L.g) * npad + L.col0 + 8 * nt + 2 * L.q + e, -v);
+      }
+  if (diag) {
+    if (tid < kCholNB) {
+      if (racc != 0.0) atomicAdd(a.rhs + kCholNB * it.ti + tid, -racc);
+      if (lacc != 0.0) atomicAdd(a.M + size_t(ild) * npad + kCholNB * it.ti + tid, -lacc);  // row ld is the last one: lower
+    } else if (tid < kCholNB + kSchurKC) {
+      ll = warp_sum_d(ll);
+      lr = warp_sum_d(lr);
+      if (tid == kCholNB) {
+        if (ll != 0.0) atomicAdd(a.M + size_t(ild) * npad + ild, -ll);
+        if (lr != 0.0) atomicAdd(a.rhs + ild, -lr);
+      }
     }
   }
 }
 
+// ------------------------------------------------------------------------------------------------
 // K5 (blocked Cholesky + triangular solves) lives in chol_coop.cu
 
 // ------------------------------------------------------------------------------------------------
 // K6
 // camera part of the step: dc = -sc o y ; gd += gc.dc ; dHd += dc' A dc ; dir_max
-__global__ void __launch_bounds__(256) camera_step_kernel(LinearLaunch a) {
+__device__ __forceinline__ void camera_step_block(const LinearLaunch& a, int block) {
   __shared__ double red[3][8];
   const int np = a.dims.np;
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per row
+  const int i = block * 8 + (threadIdx.x >> 5);  // one warp per row
   const int lane = threadIdx.x & 31;
   double gd = 0, dHd = 0, dmax = 0;
   if (i < np) {
@@ -225,10 +251,10 @@ __global__ void __launch_bounds__(256) camera_step_kernel(LinearLaunch a) {
 
 // landmark back-substitution + landmark parts of gd / dHd: one WARP per landmark (coalesced reads of
 // its coupling row), reads y (not dc) so that it can run concurrently with camera_step_kernel.
-__global__ void __launch_bounds__(256) landmark_step_kernel(LinearLaunch a) {
+__device__ __forceinline__ void landmark_step_block(const LinearLaunch& a, int block) {
   __shared__ double red[3][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int l = blockIdx.x * 8 + warp;
+  const int l = block * 8 + warp;
   double gd = 0, dHd = 0, dmax = 0;
   if (l < a.dims.nL) {
     const double sl = a.sl[l];
@@ -261,6 +287,13 @@ __global__ void __launch_bounds__(256) landmark_step_kernel(LinearLaunch a) {
 }
 
 // after the all-reduce of [M | rhs | diagA]
+// both halves of the step in ONE launch: blocks [0, ncb) take camera rows, the rest take landmarks (the landmark
+// half reads y, not dc, so the two are independent)
+__global__ void __launch_bounds__(256) step_vectors_kernel(LinearLaunch a, int ncb) {
+  if (int(blockIdx.x) < ncb) camera_step_block(a, blockIdx.x);
+  else landmark_step_block(a, blockIdx.x - ncb);
+}
+
 __global__ void add_damping_kernel(LinearLaunch a, double radius) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.npad) return;
@@ -299,35 +332,20 @@ int launch_jacobi_scale_from_diag(const LinearLaunch& a, cudaStream_t s) {
 
 int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s) {
   int launches = 0;
-  const size_t total = size_t(a.npad) * a.npad;
+  const size_t total = std::max(size_t(a.npad) * a.npad, size_t(a.dims.nL));
   scale_copy_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(a, radius);
   ++launches;
-  if (a.n_batches > 0) {
-    const size_t smem = size_t(kSchurBatch) * (kSchurMaxDim + 8) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(schur_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-      attr_set = true;
-    }
-    schur_batch_kernel<<<a.n_batches, 256, smem, s>>>(a, radius);
-    ++launches;
-  }
-  if (a.n_wide > 0) {
-    schur_wide_kernel<<<(a.n_wide * 32 + 255) / 256, 256, 0, s>>>(a, radius);
+  if (a.n_schur_items > 0) {
+    schur_tile_kernel<<<a.n_schur_items, 256, 0, s>>>(a);
     ++launches;
   }
   return launches;
 }
 
 int launch_step_vectors(const LinearLaunch& a, cudaStream_t s) {
-  int launches = 0;
-  camera_step_kernel<<<(a.dims.np + 7) / 8, 256, 0, s>>>(a);
-  ++launches;
-  if (a.dims.nL > 0) {
-    landmark_step_kernel<<<(a.dims.nL + 7) / 8, 256, 0, s>>>(a);
-    ++launches;
-  }
-  return launches;
+  const int ncb = (a.dims.np + 7) / 8, nlb = (a.dims.nL + 7) / 8;
+  step_vectors_kernel<<<ncb + nlb, 256, 0, s>>>(a, ncb);
+  return 1;
 }
 
 int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s) {
@@ -354,15 +372,22 @@ __global__ void gradient_norm_kernel(LinearLaunch a, StatePtrs st, int fix_ld, d
   if ((threadIdx.x & 31) == 0 && v > 0.0) atomic_max_pos(&a.scal->gmax, v);
 }
 int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld, double ld_lower, double ld_upper,
-                         cudaStream_t s) {
+                         cudaStream_t s, bool reset) {
   const int n = a.dims.np + a.dims.nL;
-  cudaMemsetAsync(&a.scal->gmax, 0, sizeof(double), s);
+  if (reset) cudaMemsetAsync(&a.scal->gmax, 0, sizeof(double), s);
   gradient_norm_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, st, fix_ld, ld_lower, ld_upper);
   return 1;
 }
 
 // x+ = x (+) alpha*delta  (SO(3): q * exp(delta), ceres_local_param.h:137-145; box projection of the
 // line delay, Ceres parameter_block.h Plus) and the ambient norms |x|^2, |x - x+|^2 over active blocks
+__device__ __forceinline__ Q4 stepped_knot(const ApplyLaunch& a, int i) {
+  const double* d = a.dc + 6 * i;
+  const Q4 q = load_q(a.x.q, i);
+  if (d[0] != 0.0 || d[1] != 0.0 || d[2] != 0.0) return so3_mul(q, so3_exp(V3{a.alpha * d[0], a.alpha * d[1], a.alpha * d[2]}));
+  return q;
+}
+
 __global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
   __shared__ double red[2][8];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -371,9 +396,17 @@ __global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
   if (i < nK) {
     const double* d = a.dc + 6 * i;
     const Q4 q = load_q(a.x.q, i);
-    Q4 qn = q;
-    if (d[0] != 0.0 || d[1] != 0.0 || d[2] != 0.0) qn = so3_mul(q, so3_exp(V3{a.alpha * d[0], a.alpha * d[1], a.alpha * d[2]}));
+    const Q4 qn = stepped_knot(a, i);
     a.xc.q[4 * i] = qn.x; a.xc.q[4 * i + 1] = qn.y; a.xc.q[4 * i + 2] = qn.z; a.xc.q[4 * i + 3] = qn.w;
+    if (i + 1 < nK) {
+      // K0 folded in: knot-pair table entry i of the candidate (knot i+1 is recomputed here, bit-identical to what
+      // its own thread stores)
+      const Q4 qm = stepped_knot(a, i + 1);
+      const double q2[8] = {qn.x, qn.y, qn.z, qn.w, qm.x, qm.y, qm.z, qm.w};
+      KnotPair kp;
+      make_knot_pair(q2, 0, kp);
+      a.xc.tab[i] = kp;
+    }
     if (a.count_camera && a.active[6 * i]) {
       xn += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
       sn += (q.x - qn.x) * (q.x - qn.x) + (q.y - qn.y) * (q.y - qn.y) + (q.z - qn.z) * (q.z - qn.z) + (q.w - qn.w) * (q.w - qn.w);
@@ -417,13 +450,11 @@ __global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
   }
 }
 
-int launch_apply_step(const ApplyLaunch& a, cudaStream_t s) {
+int launch_apply_step(const ApplyLaunch& a, cudaStream_t s, bool reset) {
   const int n = a.dims.nK + 6 * a.dims.nB + 1 + a.dims.nL;
-  cudaMemsetAsync(&a.scal->step_norm2, 0, 2 * sizeof(double), s);  // step_norm2, x_norm2 are adjacent
-  apply_step_kernel<<<(n + 255) / 256, 256, 0, s>>>(a);
-  int launches = 1;
-  launches += launch_knot_table(a.xc, a.dims.nK, s);
-  return launches;
+  if (reset) cudaMemsetAsync(&a.scal->step_norm2, 0, 2 * sizeof(double), s);  // step_norm2, x_norm2 are adjacent
+  apply_step_kernel<<<(n + 255) / 256, 256, 0, s>>>(a);  // also writes the candidate's knot-pair table (K0)
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------------
