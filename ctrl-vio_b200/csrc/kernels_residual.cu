@@ -117,46 +117,88 @@ __constant__ uint8_t c_tile_i[36] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1
 __constant__ uint8_t c_tile_j[36] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 2, 3, 4, 5, 6, 7, 2, 3, 4,
                                      5, 6, 7, 3, 4, 5, 6, 7, 4, 5, 6, 7, 5, 6, 7, 6, 7, 7};
 
+#ifdef CTVIO_CHOL_TIMING
+__device__ long long g_vis_clk[8];
+#define VCLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_vis_clk[(i)] = clock64(); } while (0)
+extern "C" int ctvio_debug_vis_clk(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_vis_clk, sizeof(g_vis_clk)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define VCLK(i)
+#endif
+
 size_t visual_smem_bytes() {
   return size_t(kVisObsPerRound) * kObsStride * sizeof(double) + size_t(36) * 64 * sizeof(double);
 }
 
-// Register-tiled SYRK of one round's Jacobian rows into the CTA accumulator (own register allocation:
-// kept out of line so its 64 accumulators do not spill the evaluation phase).
-// 252 threads = 7 row groups x 36 upper tiles (8x8).  The 7 partial tiles are added into the shared
-// accumulator one group at a time (shared-memory fp64 atomics are CAS loops on sm_100a).
+// SYRK of one round's Jacobian rows into the CTA accumulator (upper 8x8 tiles of the 64 local dims) on the fp64
+// tensor cores (m8n8k4; K = Jacobian rows).  The 36 upper tiles are grouped into 16x16 blocks, one or two per warp
+// (warps 0..5: the six off-diagonal blocks, warps 6, 7: two diagonal blocks each), so that every tile has ONE owner
+// warp over all rows: no cross-warp merge, the partial sums of earlier rounds are simply reloaded from accs.
+// Rows of inactive observation slots are zero (written by the evaluation phase), so K runs in whole 4-row steps.
 __device__ __noinline__ void syrk_round(const double* Jt, double* accs, int nround, int tid) {
-  const int grp = tid / 36, tile = tid % 36;
-  double acc[64];
-  if (tid < 252) {
-    const int ti = c_tile_i[tile], tj = c_tile_j[tile];
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int nblk = warp < 6 ? 1 : 2;
+  int bi[2], bj[2];
+  if (warp < 6) {
+    bi[0] = warp < 3 ? 0 : (warp < 5 ? 1 : 2);
+    bj[0] = warp < 3 ? warp + 1 : (warp < 5 ? warp - 1 : 3);
+    bi[1] = bj[1] = 0;
+  } else {
+    bi[0] = bj[0] = 2 * (warp - 6);
+    bi[1] = bj[1] = 2 * (warp - 6) + 1;
+  }
+  const bool dg = warp >= 6;
+  double acc[2][2][2][2];
 #pragma unroll
-    for (int e = 0; e < 64; ++e) acc[e] = 0.0;
-    const int nrows = 2 * nround;
-    for (int row = grp; row < nrows; row += 7) {
-      const double* rp = Jt + size_t(row >> 1) * kObsStride + (row & 1) * kRowStride;
-      const double2* ra = reinterpret_cast<const double2*>(rp + ti * 8);
-      const double2* rb = reinterpret_cast<const double2*>(rp + tj * 8);
-      double av[8], bv[8];
+  for (int b = 0; b < 2; ++b)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const double2 x = ra[e], y = rb[e];
-        av[2 * e] = x.x; av[2 * e + 1] = x.y;
-        bv[2 * e] = y.x; bv[2 * e + 1] = y.y;
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 2; ++nj) {
+        const int ti = 2 * bi[b] + mi, tj = 2 * bj[b] + nj;
+        double2 v = make_double2(0.0, 0.0);
+        if (b < nblk && ti <= tj) v = *reinterpret_cast<const double2*>(accs + (ti * 8 - ti * (ti - 1) / 2 + (tj - ti)) * 64 + g * 8 + 2 * q);
+        acc[b][mi][nj][0] = v.x; acc[b][mi][nj][1] = v.y;
       }
+  const int nsteps = (2 * nround + 3) >> 2;
+#pragma unroll 2
+  for (int st = 0; st < nsteps; ++st) {
+    const int row = 4 * st + q;
+    const double* rp = Jt + size_t(row >> 1) * kObsStride + (row & 1) * kRowStride + g;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+    for (int b = 0; b < 2; ++b) {
+      if (b < nblk) {
+        double av[2], bv[2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fma(av[i], bv[j], acc[i * 8 + j]);
+        for (int m = 0; m < 2; ++m) {
+          av[m] = rp[16 * bi[b] + 8 * m];
+          bv[m] = dg ? av[m] : rp[16 * bj[b] + 8 * m];
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nj = 0; nj < 2; ++nj) {
+            if (dg && mi == 1 && nj == 0) continue;  // strictly lower tile of a diagonal block
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(acc[b][mi][nj][0]), "+d"(acc[b][mi][nj][1])
+                         : "d"(av[mi]), "d"(bv[nj]));
+          }
+      }
     }
   }
-  for (int g = 0; g < 7; ++g) {
-    if (tid < 252 && grp == g) {
 #pragma unroll
-      for (int e = 0; e < 64; ++e) accs[tile * 64 + e] += acc[e];
-    }
-    __syncthreads();
-  }
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 2; ++nj) {
+        const int ti = 2 * bi[b] + mi, tj = 2 * bj[b] + nj;
+        if (b < nblk && ti <= tj)
+          *reinterpret_cast<double2*>(accs + (ti * 8 - ti * (ti - 1) / 2 + (tj - ti)) * 64 + g * 8 + 2 * q) =
+              make_double2(acc[b][mi][nj][0], acc[b][mi][nj][1]);
+      }
+  __syncthreads();
 }
 
 template <bool FULL>
@@ -170,6 +212,7 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
   const int lane = tid & 31, warp = tid >> 5;
   const VisualItem item = a.items[blockIdx.x];
   const int nK = a.dims.nK;
+  VCLK(0);
 
   // ---- stage the 10 active knots + 8 knot-pair entries (TMA bulk copies, one mbarrier) ----
   const int w0[2] = {item.wi0, item.wj0};
@@ -226,6 +269,7 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
   const int64_t ld_ns = int64_t(ld * 1e9);  // image_feature_factor.h:72 (truncation)
   const int side = tid & 1;
   double cost_local = 0.0;
+  VCLK(1);
 
   for (int base = 0; base < item.count; base += kVisObsPerRound) {
     const int nround = min(kVisObsPerRound, item.count - base);
@@ -306,8 +350,10 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
               const double p0v = mp ? 0.0 : ck * cm.JvR[c], p1v = mp ? 0.0 : ck * cm.JvR[3 + c];
               row0[col + c] = r0v; row1[col + c] = r1v;
               row0[col + 3 + c] = p0v; row1[col + 3 + c] = p1v;
+#ifndef CTVIO_EXPERIMENT_NO_W_ATOMICS
               if (!mr) atomicAdd(Wl + gd + c, r0v * jrho[0] + r1v * jrho[1]);
               if (!mp) atomicAdd(Wl + gd + 3 + c, p0v * jrho[0] + p1v * jrho[1]);
+#endif
             }
           });
           if (side == 0) {
@@ -338,8 +384,11 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
         if (side == 0) { row0[kColR] = row1[kColR] = 0.0; row0[kColRho] = row1[kColRho] = 0.0; }
         else { row0[kColLd] = row1[kColLd] = 0.0; row0[63] = row1[63] = 0.0; }
       }
+      VCLK(2);
       __syncthreads();
+      VCLK(3);
       syrk_round(Jt, accs, nround, tid);
+      VCLK(4);
     }
   }
 
@@ -373,6 +422,7 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
       atomicAdd(a.ne.A + size_t(g0) * np + g1, v);
     }
   }
+  VCLK(5);
 }
 
 int launch_visual(const VisualLaunch& l, bool full, cudaStream_t s) {
