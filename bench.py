@@ -339,12 +339,20 @@ def main():
 
     if rank == 0:
         peaks, how = measured_peaks()
+        # dominant kernel of the step: the dense solve (K5, chol_dag_kernel; > 50 % of the LM iteration, see
+        # profiles/r1/e_launches_c2.csv).  It computes on the fp64 tensor/FMA pipe: algorithmic flops of one launch =
+        # n^3/3 (factor) + 2 n^2 (two triangular solves), n = n_p; the denominator is the fp64 rate measured in this run
+        # (MEASURED_PEAKS.json only has HBM and bf16 numbers).  K1's HBM-side roofline is reported next to it.
+        n_p = 6 * w.n_knots + 6 * len(w.kf_times) + 1
+        chol_flops = n_p ** 3 / 3.0 + 2.0 * n_p ** 2
+        ach_tf = chol_flops / (prof["cholesky_solve"] * 1e-3) / 1e12
         alg = algorithmic_bytes_visual(w)
         ach = alg / (prof["visual"] * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_k1 = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "visual_kernel_traffic.json")) as f:
-                traffic = json.load(f).get("c2_dram_bytes_per_launch")
+            with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+                tj = json.load(f)
+                traffic, traffic_k1 = tj.get("c2_chol_dag_dram_bytes_per_launch"), tj.get("c2_visual_dram_bytes_per_launch")
         except Exception:
             pass
         cpu1 = cpu_solve_rate(w, 1, args.cpu_budget_s) if world == 1 else None
@@ -362,10 +370,16 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s_max / args.steps},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "kernel": "visual_kernel<true> (K1)",
-                         "peak_source": how, "algorithmic_bytes": alg, "kernel_ms": prof["visual"],
-                         "note": "fp64-pipe / latency bound by design (~100 flop/B): HBM fraction is expected to be small"},
+            "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": fp64_tflops, "unit": "TFLOP/s",
+                         "frac": ach_tf / fp64_tflops, "traffic": traffic, "kernel": "chol_dag_kernel (K5)",
+                         "peak_source": "fp64 DFMA/DMMA rate measured in this run (ctvio_measure_fp64_tflops); "
+                                        "MEASURED_PEAKS.json has no fp64 figure",
+                         "algorithmic_flops": chol_flops, "kernel_ms": prof["cholesky_solve"],
+                         "note": "serial pivot chain of an n=%d factorisation: latency bound, not pipe bound "
+                                 "(floor ~126 cycles per column, see DESIGN.md)" % n_p},
+            "roofline_k1": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": ach / peaks["hbm_gbs"], "traffic": traffic_k1, "kernel": "visual_kernel<true> (K1)",
+                            "peak_source": how, "algorithmic_bytes": alg, "kernel_ms": prof["visual"]},
             "stage_ms": prof,
             "fp64_peak_tflops_measured": fp64_tflops,
             "solver": {"iterations": summ.iterations, "jacobian_passes": summ.num_jacobian_evals,
