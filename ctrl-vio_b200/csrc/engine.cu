@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -140,6 +141,10 @@ struct ctvio_engine {
   int npad = 0;
   DevBuf<LmScalars> d_scal;
   LmScalars* h_scal = nullptr;  // pinned
+  LmPublished* h_pub = nullptr; // pinned + mapped: written by the last kernel of an LM step
+  unsigned long long pub_seq = 0;
+  cudaEvent_t ev_zero = nullptr;
+  bool slab_zeroed[2] = {false, false};  // the normal-equation buffer was cleared ahead of time on stream2
 
   // prior
   ctvio::PriorHost prior, new_prior;
@@ -575,7 +580,14 @@ int lm_step(ctvio_engine* e, int nb, double radius) {
 // reset_cost = false: cost_eval was already zeroed by scale_copy_kernel of the same LM step
 void evaluate(ctvio_engine* e, int xb, int nb, bool full, bool reset_cost = true) {
   cudaStream_t st = e->stream;
-  if (full) cudaMemsetAsync(e->ne_slab[nb].p, 0, e->ne_slab_len * sizeof(double), st);
+  if (full) {
+    if (e->slab_zeroed[nb]) {
+      cudaStreamWaitEvent(st, e->ev_zero, 0);  // cleared on stream2 while the linear solve was running
+      e->slab_zeroed[nb] = false;
+    } else {
+      cudaMemsetAsync(e->ne_slab[nb].p, 0, e->ne_slab_len * sizeof(double), st);
+    }
+  }
   if (reset_cost) cudaMemsetAsync(&e->d_scal.p->cost_eval, 0, sizeof(double), st);
   // fork: the (latency-bound) IMU + bias + prior kernels overlap the visual kernel on a second stream
   // sharded mode: IMU / bias / prior factors live on rank 0 only (every rank holds its own landmark shard)
@@ -591,9 +603,33 @@ void evaluate(ctvio_engine* e, int xb, int nb, bool full, bool reset_cost = true
   if (fork) cudaStreamWaitEvent(st, e->ev_join, 0);
 }
 
-int read_scalars(ctvio_engine* e) {
-  CUDA_OK(cudaMemcpyAsync(e->h_scal, e->d_scal.p, sizeof(LmScalars), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_OK(cudaStreamSynchronize(e->stream));
+// zero the normal-equation buffer the NEXT evaluation will accumulate into, on the second stream, so that it overlaps
+// the linear solve of this step (only valid when everything enqueued earlier has completed: call right after a read-back)
+void prezero_slab(ctvio_engine* e, int nb) {
+  cudaMemsetAsync(e->ne_slab[nb].p, 0, e->ne_slab_len * sizeof(double), e->stream2);
+  cudaEventRecord(e->ev_zero, e->stream2);
+  e->slab_zeroed[nb] = true;
+}
+
+// published = true: the last kernel of the step (gradient_norm_kernel) has been asked to write the scalar block to
+// mapped host memory with sequence number e->pub_seq: spin on it instead of copy + stream synchronise
+int read_scalars(ctvio_engine* e, bool published = false) {
+  if (published) {
+    volatile unsigned long long* seq = &e->h_pub->seq;
+    unsigned spins = 0;
+    while (*seq != e->pub_seq) {
+      if ((++spins & 0xfffu) == 0 && cudaStreamQuery(e->stream) != cudaErrorNotReady) {
+        if (*seq == e->pub_seq) break;
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+        if (*seq != e->pub_seq) return fail(CTVIO_ERR_CUDA, "LM step finished without publishing its scalars");
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    *e->h_scal = const_cast<const LmPublished*>(e->h_pub)->s;
+  } else {
+    CUDA_OK(cudaMemcpyAsync(e->h_scal, e->d_scal.p, sizeof(LmScalars), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+  }
   if ((e->h_scal->error_flags & 1) || (e->world > 1 && e->h_scal->err_sum > 0.0)) {
     cudaMemsetAsync(&e->d_scal.p->error_flags, 0, sizeof(int32_t), e->stream);
     return fail(CTVIO_ERR_TIME_RANGE, "a factor time left its knot window / the spline (line delay too large?)");
@@ -656,11 +692,14 @@ int ctvio_create(const ctvio_config* cfg, ctvio_handle* out) {
       cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_zero, cudaEventDisableTiming) != cudaSuccess ||
+      cudaHostAlloc(&e->h_pub, sizeof(LmPublished), cudaHostAllocMapped) != cudaSuccess ||
       cudaMallocHost(&e->h_scal, sizeof(LmScalars)) != cudaSuccess || e->d_scal.reserve(1) != cudaSuccess) {
     delete e;
     return fail(CTVIO_ERR_CUDA, "could not create stream / events / scalar block");
   }
   cudaMemsetAsync(e->d_scal.p, 0, sizeof(LmScalars), e->stream);
+  std::memset(e->h_pub, 0, sizeof(LmPublished));
   *out = e;
   return CTVIO_OK;
 }
@@ -671,6 +710,8 @@ int ctvio_destroy(ctvio_handle e) {
   cudaStreamSynchronize(e->stream);
   ctvio::comm_destroy(e->nccl_comm);
   if (e->h_scal) cudaFreeHost(e->h_scal);
+  if (e->h_pub) cudaFreeHost(e->h_pub);
+  if (e->ev_zero) cudaEventDestroy(e->ev_zero);
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
   cudaEventDestroy(e->ev_fork);
@@ -919,6 +960,7 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     ++iter;
     const int cand = cur ^ 1;
     // ---- trust-region step + speculative full evaluation of the candidate ----
+    prezero_slab(e, cand);  // everything enqueued so far has completed (scalars were read back): overlaps lm_step
     rc = lm_step(e, cur, radius);
     if (rc) return rc;
     sum.num_linear_solves++;
@@ -927,10 +969,12 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     evaluate(e, cand, cand, true, false);
     sum.num_jacobian_evals++;
     LinearLaunch linc = linear_launch(e, cand);
-    e->launches += launch_gradient_norm(linc, e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st, false);
+    const bool publish = !sharded;  // sharded: the scalars still have to go through the all-reduce
+    e->launches += launch_gradient_norm(linc, e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st, false,
+                                        publish ? e->h_pub : nullptr, ++e->pub_seq);
     rc = allreduce_scalars(e);
     if (rc) return rc;
-    rc = read_scalars(e);
+    rc = read_scalars(e, publish);
     if (rc) return rc;
     LmScalars sc = *e->h_scal;
     if (sharded) { sc.gmax = 1e300; sc.dir_max = 1e300; }

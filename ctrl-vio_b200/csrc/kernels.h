@@ -123,6 +123,13 @@ struct LmScalars {
   int32_t error_flags;     // bit0: factor time outside its window / spline
   int32_t pad[2];
 };
+// host-visible copy of the scalar block (mapped pinned memory) with a sequence number: the last kernel of an LM step
+// writes it directly, the host spins on `seq` instead of paying a device-to-host copy plus a stream synchronisation
+struct LmPublished {
+  LmScalars s;
+  unsigned long long seq;
+  unsigned long long pad;
+};
 constexpr int kLmSumScalars = 6;  // cost_eval, gd, dHd, step_norm2, x_norm2, err_sum: plain sums over landmark shards
 
 // ---- launch wrappers (each returns the number of kernels it launched) ----------------------------
@@ -225,8 +232,9 @@ int launch_add_damping(const LinearLaunch& a, double radius, cudaStream_t s);
 int launch_extract_diag(const LinearLaunch& a, cudaStream_t s);
 int launch_jacobi_scale_from_diag(const LinearLaunch& a, cudaStream_t s);
 // reset = false: the accumulator was already zeroed by scale_copy_kernel of the same LM step
+// pub != nullptr: after the norm the whole scalar block is copied to *pub (mapped host memory) and pub->seq = seq
 int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld, double ld_lower, double ld_upper,
-                         cudaStream_t s, bool reset = true);
+                         cudaStream_t s, bool reset = true, LmPublished* pub = nullptr, unsigned long long seq = 0);
 
 struct ApplyLaunch {
   int32_t count_camera;     // sharded mode: only rank 0 counts the (replicated) camera blocks in the norms

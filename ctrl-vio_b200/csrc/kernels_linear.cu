@@ -214,14 +214,18 @@ __global__ void __launch_bounds__(256, 2) schur_tile_kernel(LinearLaunch a) {
 // ------------------------------------------------------------------------------------------------
 // K6
 // camera part of the step: dc = -sc o y ; gd += gc.dc ; dHd += dc' A dc ; dir_max
-__device__ __forceinline__ void camera_step_block(const LinearLaunch& a, int block) {
+__device__ __forceinline__ void camera_step_block(const LinearLaunch& a, int block, double* dsh) {
   __shared__ double red[3][8];
   const int np = a.dims.np;
   const int i = block * 8 + (threadIdx.x >> 5);  // one warp per row
   const int lane = threadIdx.x & 31;
   double gd = 0, dHd = 0, dmax = 0;
+  // the part of the step this CTA's rows need (columns >= first row), staged once: the row loops then only stream A
+  const int j0 = block * 8;
+  for (int j = j0 + threadIdx.x; j < np; j += blockDim.x) dsh[j - j0] = a.cmask[j] ? 0.0 : -a.sc[j] * a.y[j];
+  __syncthreads();
   if (i < np) {
-    const double di = a.cmask[i] ? 0.0 : -a.sc[i] * a.y[i];
+    const double di = dsh[i - j0];
     if (lane == 0) {
       a.dc[i] = di;
       gd = a.ne.gc[i] * di;
@@ -230,10 +234,7 @@ __device__ __forceinline__ void camera_step_block(const LinearLaunch& a, int blo
     }
     if (di != 0.0) {
       double s = 0;
-      for (int j = i + lane; j < np; j += 32) {
-        const double dj = a.cmask[j] ? 0.0 : -a.sc[j] * a.y[j];
-        s = fma(a.ne.A[size_t(i) * np + j] * (j == i ? 0.5 : 1.0), dj, s);
-      }
+      for (int j = i + lane; j < np; j += 32) s = fma(a.ne.A[size_t(i) * np + j] * (j == i ? 0.5 : 1.0), dsh[j - j0], s);
       dHd = 2.0 * di * s;
     }
   }
@@ -290,7 +291,8 @@ __device__ __forceinline__ void landmark_step_block(const LinearLaunch& a, int b
 // both halves of the step in ONE launch: blocks [0, ncb) take camera rows, the rest take landmarks (the landmark
 // half reads y, not dc, so the two are independent)
 __global__ void __launch_bounds__(256) step_vectors_kernel(LinearLaunch a, int ncb) {
-  if (int(blockIdx.x) < ncb) camera_step_block(a, blockIdx.x);
+  extern __shared__ double step_dsh[];  // [np]
+  if (int(blockIdx.x) < ncb) camera_step_block(a, blockIdx.x, step_dsh);
   else landmark_step_block(a, blockIdx.x - ncb);
 }
 
@@ -344,7 +346,7 @@ int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s) 
 
 int launch_step_vectors(const LinearLaunch& a, cudaStream_t s) {
   const int ncb = (a.dims.np + 7) / 8, nlb = (a.dims.nL + 7) / 8;
-  step_vectors_kernel<<<ncb + nlb, 256, 0, s>>>(a, ncb);
+  step_vectors_kernel<<<ncb + nlb, 256, size_t(a.dims.np) * sizeof(double), s>>>(a, ncb);
   return 1;
 }
 
@@ -352,35 +354,56 @@ int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s) {
   return launch_reduced_system(a, radius, s) + launch_factor_solve(a, s) + launch_step_vectors(a, s);
 }
 
-// max-norm of the (bounds-projected) gradient over the active parameters
-__global__ void gradient_norm_kernel(LinearLaunch a, StatePtrs st, int fix_ld, double ld_lower, double ld_upper) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// max-norm of the (bounds-projected) gradient over the active parameters; ONE CTA (the vectors are small), so the
+// result needs no atomics and the same CTA can hand the finished scalar block of the LM step to the host
+__global__ void __launch_bounds__(1024) gradient_norm_kernel(LinearLaunch a, StatePtrs st, int fix_ld, double ld_lower,
+                                                             double ld_upper, LmPublished* pub, unsigned long long seq) {
+  __shared__ double red[32];
   const int np = a.dims.np, nL = a.dims.nL;
   double v = 0.0;
-  if (i < np) {
-    if (a.active[i]) {
-      v = fabs(a.ne.gc[i]);
+  for (int i = threadIdx.x; i < np + nL; i += blockDim.x) {
+    if (!a.active[i]) continue;
+    double x;
+    if (i < np) {
+      x = fabs(a.ne.gc[i]);
       if (i == a.dims.idx_ld && !fix_ld) {
         const double ld = *st.ld;
-        v = fabs(ld - fmin(fmax(ld - a.ne.gc[i], ld_lower), ld_upper));
+        x = fabs(ld - fmin(fmax(ld - a.ne.gc[i], ld_lower), ld_upper));
       }
+    } else {
+      x = fabs(a.ne.gl[i - np]);
     }
-  } else if (i < np + nL) {
-    if (a.active[i]) v = fabs(a.ne.gl[i - np]);
+    v = fmax(v, x);
   }
   v = warp_max_d(v);
-  if ((threadIdx.x & 31) == 0 && v > 0.0) atomic_max_pos(&a.scal->gmax, v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = warp_max_d(red[threadIdx.x]);
+    if (threadIdx.x == 0) {
+      a.scal->gmax = fmax(a.scal->gmax, v);
+      if (pub) {
+        __threadfence();  // the other kernels' atomics into the scalar block are complete (stream order); re-read them
+        const volatile LmScalars* src = a.scal;
+        LmScalars c;
+        c.cost_eval = src->cost_eval; c.gd = src->gd; c.dHd = src->dHd; c.step_norm2 = src->step_norm2;
+        c.x_norm2 = src->x_norm2; c.err_sum = src->err_sum; c.gmax = src->gmax; c.dir_max = src->dir_max;
+        c.ld_value = src->ld_value; c.chol_fail = src->chol_fail; c.error_flags = src->error_flags;
+        c.pad[0] = c.pad[1] = 0;
+        pub->s = c;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(&pub->seq) = seq;
+      }
+    }
+  }
 }
 int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld, double ld_lower, double ld_upper,
-                         cudaStream_t s, bool reset) {
-  const int n = a.dims.np + a.dims.nL;
+                         cudaStream_t s, bool reset, LmPublished* pub, unsigned long long seq) {
   if (reset) cudaMemsetAsync(&a.scal->gmax, 0, sizeof(double), s);
-  gradient_norm_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, st, fix_ld, ld_lower, ld_upper);
+  gradient_norm_kernel<<<1, 1024, 0, s>>>(a, st, fix_ld, ld_lower, ld_upper, pub, seq);
   return 1;
 }
 
-// x+ = x (+) alpha*delta  (SO(3): q * exp(delta), ceres_local_param.h:137-145; box projection of the
-// line delay, Ceres parameter_block.h Plus) and the ambient norms |x|^2, |x - x+|^2 over active blocks
 __device__ __forceinline__ Q4 stepped_knot(const ApplyLaunch& a, int i) {
   const double* d = a.dc + 6 * i;
   const Q4 q = load_q(a.x.q, i);
