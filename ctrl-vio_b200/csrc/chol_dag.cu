@@ -107,7 +107,7 @@ struct CholDagArgs {
   double* y;          // [npad] solution
   double* yf;         // [npad] forward-solved right-hand side
   double* part;       // [2][nb][nb][64] partial products of the forward / backward sweeps
-  int* flags;         // tile_ready[nb*nb] | bwd_ready[nb*nb] | diag_ready[nb] | x_ready[nb]
+  int* flags;         // tile_ready[nb*nb] | bwd_ready[nb*nb] | diag_ready[nb] | x_ready[nb] | fwd_ready[nb]
   int epoch;
   LmScalars* scal;
 };
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   int* bwd_ready = a.flags + nb * nb;
   int* diag_ready = a.flags + 2 * nb * nb;
   int* x_ready = diag_ready + nb;
+  int* fwd_ready = x_ready + nb;
   double* fwd_part = a.part;                          // [i][k][64] = L(i,k) x_k
   double* bwd_part = a.part + size_t(nb) * nb * kCholNB;  // [k][r][64] = L(r,k)^T x_r
 
@@ -173,7 +174,6 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     frag_store_t(S1, acc, L);
     wait_flag(diag_ready + j, epoch);
     load_tile_cg(S2, a.Linv + size_t(j) * kCholNB * kCholNB, kCholNB, tid);
-    if (tid < kCholNB) vec[tid] = __ldcg(a.yf + j * kCholNB + tid);
     __syncthreads();
     frag_zero(acc);
     tile_gemm_dmma<false>(S1, S2, acc, L);
@@ -182,6 +182,9 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     frag_store_t(S1, acc, L);
     __syncthreads();
     store_tile_global(slot, npad, S1, tid);  // published transposed
+    wait_flag(fwd_ready + j, epoch);
+    if (tid < kCholNB) vec[tid] = __ldcg(a.yf + j * kCholNB + tid);
+    __syncthreads();
     tile_matvec(Lrm, vec, fwd_part + (size_t(i) * nb + j) * kCholNB, tid);
     post_flag(tile_ready + i * nb + j, epoch);
     // backward sweep: L(i,j)^T x_i
@@ -211,13 +214,17 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     __syncthreads();
   }
   DSTAMP(j, 1);
+  {  // right-hand side of block j for the forward substitution: the partials of the other owners (all in by now), fixed
+    // summation order; this CTA's own partial L(j,j-1) x_{j-1} is added after the factorisation (side job below)
+    const double sp = sum_partials(fwd_part + size_t(j) * nb * kCholNB, j >= 1 ? j - 1 : 0, kCholNB, red, tid);
+    if (tid < kCholNB) vec[tid] = a.rhs[j * kCholNB + tid] - sp;
+  }
   if (j >= 1) {
     // L(j,j-1) = T * Linv_{j-1}^T, then the last update of the diagonal tile
     frag_store_t(S1, accS, L);
     wait_flag(diag_ready + (j - 1), epoch);
     DSTAMP(j, 2);
     load_tile_cg(S2, a.Linv + size_t(j - 1) * kCholNB * kCholNB, kCholNB, tid);
-    if (tid < kCholNB) vec[tid] = __ldcg(a.yf + (j - 1) * kCholNB + tid);
     __syncthreads();
     DSTAMP(j, 8);
     frag_zero(accS);
@@ -228,27 +235,51 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     frag_store_t(S1, accS, L);
     __syncthreads();
     DSTAMP(j, 10);
-    store_tile_global(slot, npad, S1, tid);  // published transposed
-    tile_matvec(Lrm, vec, fwd_part + (size_t(j) * nb + (j - 1)) * kCholNB, tid);
-    DSTAMP(j, 11);
-    post_flag(tile_ready + j * nb + (j - 1), epoch);
-    DSTAMP(j, 3);
     tile_gemm_dmma<true>(S1, S1, accD, L);
+    DSTAMP(j, 3);
   }
   frag_store(D, accD, L);
-  {  // right-hand side of block j for the forward substitution (all partials L(j,k) x_k are in: fixed summation order)
-    const double sp = sum_partials(fwd_part + size_t(j) * nb * kCholNB, j, kCholNB, red, tid);
-    if (tid < kCholNB) vec[tid] = a.rhs[j * kCholNB + tid] - sp;
-  }
   __syncthreads();
   DSTAMP(j, 4);
-  if (!factor_and_invert_64(D, Xi, XiT, S2, rdiag, &s_bad) && tid == 0) a.scal->chol_fail = 1;
+  // While warp 0 runs the pivot chain of the first two 16-column steps, warps 1..7 publish L(j,j-1) (tile store, fence,
+  // flag) and form its forward partial: ~2 us that used to sit on the critical chain between two factorisations.
+  double* own = red;  // [64] L(j,j-1) x_{j-1}
+  auto side = [&](int step) {
+    if (j == 0) return;
+    const int tt = tid - 32;  // 0..223
+    if (step == 0) {
+      for (int e = tt; e < kCholNB * kCholNB / 2; e += 224) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        *reinterpret_cast<double2*>(slot + size_t(r) * npad + c) = *reinterpret_cast<const double2*>(S1 + r * kTS + c);
+      }
+      asm volatile("bar.sync 1, 224;" ::: "memory");
+      if (tt == 0) {
+        __threadfence();
+        st_release(tile_ready + j * nb + (j - 1), epoch);
+      }
+    } else if (step == 1 && tt < kCholNB) {
+      // x_{j-1} was published (fwd_ready) a microsecond after Linv_{j-1}: long ago by now
+      if (tt == 0) { while (ld_acquire(fwd_ready + (j - 1)) != epoch) {} }
+      asm volatile("bar.sync 2, 64;" ::: "memory");
+      vec2[tt] = __ldcg(a.yf + (j - 1) * kCholNB + tt);
+    } else if (step == 2 && tt < 128) {
+      const int r = tt >> 1, pt = tt & 1;
+      double acc = 0.0;
+#pragma unroll 8
+      for (int c = pt; c < kCholNB; c += 2) acc = fma(Lrm[r * kTS + c], vec2[c], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (pt == 0) own[r] = acc;
+    }
+  };
+  if (!factor_and_invert_64(D, Xi, XiT, S2, rdiag, &s_bad, side) && tid == 0) a.scal->chol_fail = 1;
   DSTAMP(j, 5);
   // forward substitution of block j: x_j = Linv_j (rhs_j - sum_k L(j,k) x_k)
-  store_tile_global(a.Linv + size_t(j) * kCholNB * kCholNB, kCholNB, XiT, tid);  // publish Linv_j^T
-  tile_matvec(Xi, vec, a.yf + j * kCholNB, tid, vec2);  // shared copy for the backward sweep
-  post_flag(diag_ready + j, epoch);
+  if (j >= 1 && tid < kCholNB) vec[tid] -= own[tid];
+  store_tile_global(a.Linv + size_t(j) * kCholNB * kCholNB, kCholNB, XiT, tid);  // publish Linv_j^T first: it is what
+  post_flag(diag_ready + j, epoch);                                               // the next column's chain waits for
   DSTAMP(j, 6);
+  tile_matvec(Xi, vec, a.yf + j * kCholNB, tid, vec2);  // x_j (forward); shared copy for the backward sweep
+  post_flag(fwd_ready + j, epoch);
 
   // backward sweep: x_j = Linv_j^T (yf_j - sum_{r > j} L(r,j)^T x_r)
   for (int r = j + 1; r < nb; ++r) wait_flag(bwd_ready + r * nb + j, epoch);
@@ -278,7 +309,7 @@ size_t chol_dag_part_len(int npad) {
 }
 size_t chol_dag_flags_len(int npad) {
   const size_t nb = npad / kCholNB;
-  return 2 * nb * nb + 2 * nb;
+  return 2 * nb * nb + 3 * nb;
 }
 
 int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {

@@ -94,7 +94,15 @@ __device__ __forceinline__ bool chol4(const double a[4][4], double l[4][4], doub
 //   P2  the panel below (thread per row) and the block row of the inverse (thread per column: forward
 //       substitution of the identity / of the running sums W = -sum L X) by 16-deep substitution;
 //   P3  the trailing update of D and of the running sums in Xi as m8n8k4 fp64 tensor-core tiles (K = 16).
-__device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, double* XiT, double* T, double* rdiag, int* s_bad) {
+//
+// `side(s)` is called by the threads of warps 1..7 (tid >= 32) at the start of 16-column step s, i.e. while warp 0
+// runs the P1 chain and they would otherwise idle at the barrier: room for ~1 us of unrelated work per step.
+struct NoSideJob {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+template <class Side = NoSideJob>
+__device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, double* XiT, double* T, double* rdiag, int* s_bad,
+                                                     Side side = Side()) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, q = lane & 3;
   double* L16t = T;      // [16][16] current diagonal block of L, transposed: L16t[c][r] = L[r][c] (r >= c valid)
@@ -138,6 +146,8 @@ __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, doub
         for (int k = j + 1; k < 16; ++k) a[k] = fma(-lij, L16t[j * 16 + k], a[k]);
       }
       if (bad && lane == 0) *s_bad = 1;
+    } else {
+      side(s);
     }
     FCLK(s, 1);
     __syncthreads();

@@ -13,13 +13,13 @@ for name in ("c2", "c4"):
     t = np.array(buf[:], dtype=np.float64).reshape(32, 16)
     nb = (6 * w.n_knots + 6 * len(w.kf_times) + 1 + 63) // 64
     t0 = t[:nb, 0].min()
-    print(name, "nb", nb, " columns: start | old-updates done | Linv(j-1) seen | L(j,j-1) posted | diag updated | factored | diag_ready posted | x_ready posted  (us from kernel start)")
+    print(name, "nb", nb, " columns: start | old-updates done | Linv(j-1) seen | diag-update gemm done | D stored + rhs | factored | diag_ready posted | x_ready posted  (us from kernel start)")
     for j in range(nb):
         print("  col %2d: " % j + " ".join("%7.1f" % ((v - t0) / 1e3) for v in t[j, :8]))
     j = min(3, nb - 1)
     d = t[j]
-    print("  col %d slab detail (us): Linv^T+x loaded %.2f | gemm %.2f | stores %.2f | matvec %.2f | fence+flag %.2f" % (
-        j, (d[8] - d[2]) / 1e3, (d[9] - d[8]) / 1e3, (d[10] - d[9]) / 1e3, (d[11] - d[10]) / 1e3, (d[3] - d[11]) / 1e3))
+    print("  col %d slab detail (us): Linv^T+x loaded %.2f | slab gemm %.2f | smem stores %.2f | diagonal update gemm %.2f" % (
+        j, (d[8] - d[2]) / 1e3, (d[9] - d[8]) / 1e3, (d[10] - d[9]) / 1e3, (d[3] - d[10]) / 1e3))
     fc = (C.c_longlong * 256)()
     LIB.lib.ctvio_debug_fac_clk(fc)
     fc = np.array(fc[:], dtype=np.int64).reshape(8, 4, 8)
