@@ -180,6 +180,24 @@ def run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch):
     return out
 
 
+def run_c5_streaming(lib, n_windows, device):
+    """BASELINE configs[4]: streaming sliding window at 20 Hz keyframes, end-to-end ms per window through the public
+    API with host buffers (state + factors + prior re-uploaded every window like the reference rebuilds its problem;
+    solve(8) -> gauge re-alignment -> marginalization -> state read-back all inside the timed region)."""
+    st = importlib.import_module("ctrl-vio_b200.streaming")
+    seq = st.config_c5_sequence(n_windows)
+    r = st.StreamingRunner(lib, seq, iters=8, device=device)
+    r.run(n_windows)
+    ms = np.array([x["ms"] for x in r.records[3:]])  # the first windows include allocation / module load
+    dev = np.array([x["device_ms"] for x in r.records[3:]])
+    return {"workload": f"C5: {n_windows} windows of 11 keyframes @20 Hz, {r.records[-1]['n_obs']} RS obs, "
+                        f"{r.records[-1]['n_knots']} ctrl pts, prior dim {r.records[-1]['prior_dim']}, solve(8) + re-align + marginalize",
+            "ms_per_window_mean": float(ms.mean()), "ms_per_window_median": float(np.median(ms)),
+            "ms_per_window_p99": float(np.percentile(ms, 99)), "solve_device_ms_mean": float(dev.mean()),
+            "windows_per_s": float(1e3 / ms.mean()), "realtime_factor_at_20hz": float(50.0 / ms.mean()),
+            "final_cost_last": r.records[-1]["final_cost"]}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -235,6 +253,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--c5-windows", type=int, default=60)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ctvio", choices=["ctvio", "reference"])
@@ -327,6 +346,7 @@ def main():
     c4 = None
     if not args.no_c4:
         c4 = run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch)
+    c5 = run_c5_streaming(lib, args.c5_windows, local_rank) if (rank == 0 and args.c5_windows > 0) else None
 
     # ---------------- reduce over ranks ----------------
     t = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64, device="cuda")
@@ -397,6 +417,8 @@ def main():
                                                   "solve_ms": cpu_all["solve_ms"]}}
         if c4 is not None:
             line["c4"] = c4
+        if c5 is not None:
+            line["c5"] = c5
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -94,7 +94,7 @@ class Summary(C.Structure):
 # export-completeness test and by the binder.
 ABI_SYMBOLS = [
     "last_error", "abi_version", "create", "destroy", "set_options",
-    "set_knots", "set_biases", "set_inv_depths", "set_line_delay",
+    "set_knots", "set_biases", "set_inv_depths", "set_line_delay", "set_time_origin",
     "get_knots", "get_biases", "get_inv_depths", "get_line_delay",
     "clear_factors", "add_image_features", "add_imu_measurements", "add_bias_factors", "set_prior",
     "solve", "gauge_realign", "marginalize", "get_prior", "adopt_prior",
@@ -226,6 +226,10 @@ class Estimator:
         r = _f64(r, (-1,))
         self.n_lm = r.shape[0]
         self.lib.call("set_inv_depths", self.h, C.c_int32(self.n_lm), _dp(r))
+
+    def SetTimeOrigin(self, t0_ns):
+        """Move the window: knot 0 of the next SetKnots slice sits at t0_ns (on the knot grid)."""
+        self.lib.call("set_time_origin", self.h, C.c_int64(int(t0_ns)))
 
     def SetLineDelay(self, ld):
         self.lib.call("set_line_delay", self.h, C.c_double(ld))

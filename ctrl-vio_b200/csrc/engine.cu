@@ -153,6 +153,12 @@ struct ctvio_engine {
   bool prior_dirty = true;
 
   DevBuf<double> d_tmp;  // scratch (gauge inputs, probe outputs)
+  // marginalization workspace (K7), kept across windows: allocation / free costs more than the kernels
+  struct MargWs {
+    DevBuf<int32_t> pos_cam, pos_lm, prior_pos, marg_img, marg_imu;
+    DevBuf<int2> bij;
+    DevBuf<double> bs, A, b, Amm, V, ev, Vs, Ainv, T, Ap, bp, Ap2, V2, ev2, vb, J, r;
+  } mws;
 
   // multi-GPU
   void* nccl_comm = nullptr;
@@ -768,6 +774,16 @@ int ctvio_set_inv_depths(ctvio_handle e, int32_t n, const double* r) {
   if (n > 0) CUDA_OK(cudaMemcpyAsync(e->x[e->cur].rho.p, r, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
   e->have_rho = true;
+  return CTVIO_OK;
+}
+
+int ctvio_set_time_origin(ctvio_handle e, int64_t t0_ns) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  if ((t0_ns - e->cfg.t0_ns) % e->cfg.dt_ns != 0) return fail(CTVIO_ERR_INVALID, "time origin off the knot grid");
+  e->cfg.t0_ns = t0_ns;
+  e->sp.t0_ns = t0_ns;
+  e->structure_dirty = true;
+  e->table_valid = false;
   return CTVIO_OK;
 }
 
@@ -1505,9 +1521,11 @@ int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
     }
 
   // ---- A, b on the device ----
-  DevBuf<int32_t> d_pos_cam, d_pos_lm, d_prior_pos, d_marg_img, d_marg_imu;
-  DevBuf<int2> d_bij;
-  DevBuf<double> d_bs, d_A, d_b;
+  ctvio_engine::MargWs& ws = e->mws;
+  DevBuf<int32_t>&d_pos_cam = ws.pos_cam, &d_pos_lm = ws.pos_lm, &d_prior_pos = ws.prior_pos, &d_marg_img = ws.marg_img,
+      &d_marg_imu = ws.marg_imu;
+  DevBuf<int2>& d_bij = ws.bij;
+  DevBuf<double>&d_bs = ws.bs, &d_A = ws.A, &d_b = ws.b;
   CUDA_OK(d_pos_cam.upload(pos_cam, st));
   CUDA_OK(d_pos_lm.upload(pos_lm, st));
   CUDA_OK(d_prior_pos.upload(prior_pos, st));
@@ -1541,7 +1559,8 @@ int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
   }
   // ---- dense Schur complement through eigen-decompositions (marginalization_factor.cpp:240-263) ----
   const double eps = 1e-30;
-  DevBuf<double> d_Amm, d_V, d_ev, d_Vs, d_Ainv, d_T, d_Ap, d_bp, d_Ap2, d_V2, d_ev2, d_vb, d_J, d_r;
+  DevBuf<double>&d_Amm = ws.Amm, &d_V = ws.V, &d_ev = ws.ev, &d_Vs = ws.Vs, &d_Ainv = ws.Ainv, &d_T = ws.T, &d_Ap = ws.Ap,
+      &d_bp = ws.bp, &d_Ap2 = ws.Ap2, &d_V2 = ws.V2, &d_ev2 = ws.ev2, &d_vb = ws.vb, &d_J = ws.J, &d_r = ws.r;
   CUDA_OK(d_Ap.reserve(size_t(n) * n));
   CUDA_OK(d_bp.reserve(n));
   CUDA_OK(cudaMemcpy2DAsync(d_Ap.p, size_t(n) * sizeof(double), d_A.p + size_t(m) * P + m, size_t(P) * sizeof(double),

@@ -132,6 +132,12 @@ int ctvio_set_knots(ctvio_handle h, int32_t n_knots, const double* q_xyzw, const
 int ctvio_set_biases(ctvio_handle h, int32_t n_nodes, const double* bg_ba6);
 int ctvio_set_inv_depths(ctvio_handle h, int32_t n_landmarks, const double* inv_depth);
 int ctvio_set_line_delay(ctvio_handle h, double line_delay);
+/* Sliding the window: the reference keeps ONE growing spline and freezes the control points below
+ * fixed_control_point_index (estimator/trajectory_estimator.h:90, trajectory_manager.cpp:352-361); here the caller
+ * uploads only the window's slice of control points and moves the time origin to the slice's first knot
+ * (t0 must stay on the knot grid of ctvio_config.t0_ns / dt_ns). Factors and the prior are re-added by the caller
+ * with knot / bias-node indices relative to the new slice. */
+int ctvio_set_time_origin(ctvio_handle h, int64_t t0_ns);
 
 /* state out — the solver updates the blocks in place in the reference; here
  * the caller reads them back. HBM -> host copies. */

@@ -87,6 +87,12 @@ int ctvo_set_inv_depths(void* h, int32_t n, const double* r) {
   E(h)->w.rho.assign(r, r + size_t(n));
   return CTVIO_OK;
 }
+int ctvo_set_time_origin(void* h, int64_t t0_ns) {
+  Window& w = E(h)->w;
+  if ((t0_ns - w.grid.t0_ns) % w.grid.dt_ns != 0) return fail(CTVIO_ERR_INVALID, "time origin off the knot grid");
+  w.grid.set(t0_ns, w.grid.dt_ns, w.grid.n_knots);
+  return CTVIO_OK;
+}
 int ctvo_set_line_delay(void* h, double ld) {
   E(h)->w.ld = ld;
   return CTVIO_OK;

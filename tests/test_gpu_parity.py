@@ -293,3 +293,32 @@ def test_dense_solver_is_reproducible_and_accurate(cuda_lib, case):
     mismatches, rel_res = est.SelfcheckSolver(reps=300 if case != "c4" else 100)
     assert mismatches == 0
     assert rel_res < 1e-9
+
+
+def test_c5_streaming_windows_match_oracle(oracle_lib, cuda_lib):
+    """BASELINE config 5 (streaming, 20 Hz keyframes): a few consecutive windows of
+    solve -> re-align -> marginalize -> slide (time origin moved, prior re-indexed), GPU engine vs oracle, each
+    running the whole chain on its own."""
+    import importlib
+    st = importlib.import_module("ctrl-vio_b200.streaming")
+    seq = st.config_c5_sequence(4)
+    runs = []
+    for lib in (cuda_lib, oracle_lib):
+        r = st.StreamingRunner(lib, seq, iters=8)
+        r.run(3)
+        runs.append(r)
+    g, o = runs
+    # The reference's prior comes from pseudo-inverses with eps = 1e-30 (marginalization_factor.h:129): eigenvalues
+    # that are pure rounding noise (the 4-DoF gauge directions) are inverted, so r_lin carries O(noise / sqrt(noise))
+    # components that differ between ANY two implementations (and between two runs of the atomics-based GPU
+    # accumulation).  The optimum of the following windows moves by ~1e-4 m along those weak directions; window 0
+    # (no prior yet) must still agree to the north-star tolerance.
+    assert g.records[0]["iterations"] == o.records[0]["iterations"]
+    assert np.isclose(g.records[0]["final_cost"], o.records[0]["final_cost"], rtol=1e-9)
+    for rg, ro in zip(g.records, o.records):
+        assert rg["iterations"] == ro["iterations"] and rg["prior_dim"] == ro["prior_dim"]
+        assert np.isclose(rg["final_cost"], ro["final_cost"], rtol=1e-3)
+    scale = np.abs(o.p).max()
+    assert np.abs(g.p - o.p).max() <= 1e-3 * scale
+    assert rot_angle_between(g.q, o.q).max() <= 1e-4
+    assert abs(g.ld - o.ld) <= 1e-3 * syn.LD_UPPER
