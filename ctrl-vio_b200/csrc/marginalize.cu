@@ -231,6 +231,10 @@ __global__ void __launch_bounds__(1024) jacobi_eig_kernel(double* A, double* V, 
     __syncthreads();
     // converged, or stagnating at the rounding floor (the off-diagonal mass no longer halves per sweep once it is
     // below ~(n eps)^2 of the diagonal mass): more sweeps only shuffle noise
+    // converged, or stagnating at the rounding floor (the off-diagonal mass no longer halves per sweep once it is
+    // below ~(n eps)^2 of the diagonal mass): more sweeps only shuffle noise.  (Stopping earlier, e.g. one sweep after
+    // 1e-20, is NOT an option: the eps = 1e-30 pseudo-inverse of the reference inverts the smallest eigenvalues, so
+    // their RELATIVE accuracy matters - measured: 5e-3 cost drift over a few windows.)
     const double prev = sweep > 0 ? s_prev : 1e300;
     if (s_off <= 1e-60 || s_off <= 1e-30 * s_diag || (s_off <= 1e-24 * s_diag && s_off > 0.5 * prev)) break;
     __syncthreads();
@@ -326,6 +330,10 @@ __global__ void __launch_bounds__(1024) jacobi_eig_smem_kernel(double* Ag, doubl
     __syncthreads();
     // converged, or stagnating at the rounding floor (the off-diagonal mass no longer halves per sweep once it is
     // below ~(n eps)^2 of the diagonal mass): more sweeps only shuffle noise
+    // converged, or stagnating at the rounding floor (the off-diagonal mass no longer halves per sweep once it is
+    // below ~(n eps)^2 of the diagonal mass): more sweeps only shuffle noise.  (Stopping earlier, e.g. one sweep after
+    // 1e-20, is NOT an option: the eps = 1e-30 pseudo-inverse of the reference inverts the smallest eigenvalues, so
+    // their RELATIVE accuracy matters - measured: 5e-3 cost drift over a few windows.)
     const double prev = sweep > 0 ? s_prev : 1e300;
     if (s_off <= 1e-60 || s_off <= 1e-30 * s_diag || (s_off <= 1e-24 * s_diag && s_off > 0.5 * prev)) break;
     __syncthreads();
