@@ -314,28 +314,19 @@ extern "C" int ctvio_debug_latency(int nthreads, long long* out6) {
 #endif
 
 int launch_factor_solve(const LinearLaunch& a, cudaStream_t s) {
-  static int n_sm = 0, mode = -1;  // mode: 0 auto, 1 force the barrier kernel (CTVIO_CHOL=coop)
+  static int mode = -1;  // 0 auto, 1 force the barrier kernel (CTVIO_CHOL=coop)
   if (mode < 0) {
     const char* env = std::getenv("CTVIO_CHOL");
     mode = (env && std::string(env) == "coop") ? 1 : 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  if (mode == 0 && a.chol_part && a.chol_flags && chol_dag_supported(a.npad, n_sm)) return launch_chol_dag(a, s);
+  if (mode == 0 && a.chol_part && a.chol_flags && chol_dag_supported(a.npad, device_sm_count())) return launch_chol_dag(a, s);
   return launch_chol_coop(a, s);
 }
 
 int launch_chol_coop(const LinearLaunch& a, cudaStream_t s) {
-  static int n_sm = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(chol_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCholCoopSmem));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) cudaFuncSetAttribute(chol_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCholCoopSmem));
+  const int n_sm = device_sm_count();
   const int nb = a.npad / kCholNB;
   const int t0 = nb - 1;
   int grid = std::max(1, std::min(n_sm, std::max(t0, t0 * (t0 + 1) / 2)));

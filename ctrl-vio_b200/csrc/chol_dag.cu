@@ -313,17 +313,15 @@ size_t chol_dag_flags_len(int npad) {
 }
 
 int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
-  static bool attr_set = false;
-  static int epoch = 0;
-  if (!attr_set) {
-    cudaFuncSetAttribute(chol_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCholDagSmem));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  static std::atomic<unsigned> epoch_src{0};
+  if (once.first()) cudaFuncSetAttribute(chol_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCholDagSmem));
   CholDagArgs a;
   a.M = l.M; a.npad = l.npad; a.Linv = l.Linv; a.rhs = l.rhs; a.y = l.y; a.yf = l.yf;
   a.part = l.chol_part; a.flags = l.chol_flags; a.scal = l.scal;
-  epoch = epoch == 0x7fffffff ? 1 : epoch + 1;
-  a.epoch = epoch;
+  // process-wide unique, never 0 (flag buffers start zeroed); a wrap after 2^31 launches would need the flags of a
+  // buffer to hold exactly the value 2^31 launches old: not a practical concern
+  a.epoch = int(epoch_src.fetch_add(1, std::memory_order_relaxed) % 0x7ffffffeu) + 1;
   void* args[] = {&a};
   cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_dag_kernel), dim3(dag_grid(l.npad / kCholNB)), dim3(256), args,
                               kCholDagSmem, s);

@@ -363,8 +363,7 @@ int prepare(ctvio_engine* e) {
             ++total;
           }
       }
-      int n_sm = 148;
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, e->cfg.device);
+      const int n_sm = device_sm_count();
       const int part = std::max(32, int((total / size_t(2 * n_sm) + 31) / 32) * 32);
       std::vector<SchurTileItem> items;
       std::vector<SchurEntry> flat;

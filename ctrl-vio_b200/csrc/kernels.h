@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <cstdint>
 
 #include "spline_eval.cuh"
@@ -131,6 +133,29 @@ struct LmPublished {
   unsigned long long pad;
 };
 constexpr int kLmSumScalars = 6;  // cost_eval, gd, dHd, step_norm2, x_norm2, err_sum: plain sums over landmark shards
+
+// Per-device one-time initialisation (cudaFuncSetAttribute applies to the CURRENT device only; one process may
+// drive several GPUs) and a cached SM count of the current device.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    return !(mask.fetch_or(bit) & bit);
+  }
+};
+inline int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int d = 0;
+  cudaGetDevice(&d);
+  int v = cache[d & 63].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
+    cache[d & 63].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 
 // ---- launch wrappers (each returns the number of kernels it launched) ----------------------------
 int launch_knot_table(const StatePtrs& st, int nK, cudaStream_t s);

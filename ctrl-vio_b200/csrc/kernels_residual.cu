@@ -428,11 +428,10 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
 int launch_visual(const VisualLaunch& l, bool full, cudaStream_t s) {
   if (l.n_items <= 0) return 0;
   VisArgs a{l.obs, l.items, l.st, l.ne, l.lm, l.dims, l.sp, l.rig, l.cauchy, l.cmask, l.scal, l.use_tma ? 1 : 0};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(visual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(visual_smem_bytes()));
     cudaFuncSetAttribute(visual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(visual_smem_bytes()));
-    attr_set = true;
   }
   if (full) visual_kernel<true><<<l.n_items, kVisThreads, visual_smem_bytes(), s>>>(a);
   else visual_kernel<false><<<l.n_items, kVisThreads, 0, s>>>(a);
@@ -570,11 +569,8 @@ int launch_imu(const ImuLaunch& l, bool full, cudaStream_t s) {
   if (l.n_items <= 0) return 0;
   ImuArgs a{l.obs, l.items, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal};
   const size_t smem = (size_t(kImuMaxPerItem) * 6 * kImuRowStride + 10 * 64) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(imu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) cudaFuncSetAttribute(imu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (full) imu_kernel<true><<<l.n_items, kImuThreads, smem, s>>>(a);
   else imu_kernel<false><<<l.n_items, kImuThreads, 0, s>>>(a);
   return 1;

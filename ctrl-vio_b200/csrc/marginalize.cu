@@ -399,11 +399,8 @@ int launch_jacobi_eig(double* A, double* V, double* ev, int n, cudaStream_t s) {
   const size_t pairs = size_t((n + 1) / 2) * (2 * sizeof(double) + 2 * sizeof(int));
   const size_t smem_res = 2 * size_t(n) * (n | 1) * sizeof(double) + pairs;
   if (smem_res <= 220 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(jacobi_eig_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      attr_set = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(jacobi_eig_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     jacobi_eig_smem_kernel<<<1, 1024, smem_res, s>>>(A, V, ev, n, 60);
     return 1;
   }
