@@ -42,21 +42,51 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML in a thread (a sample every ~10 ms, the timed
+    region of the C2 window is only tens of milliseconds), `nvidia-smi -lms` as the fallback."""
 
     def __init__(self, index):
-        self.rows = []
-        self.proc = None
         self.index = index
+        self.rows = []      # (sm_mhz, sm_max_mhz, reasons bitmask or list)
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.mode = None
+        self.proc = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.mode = "nvml"
+
+            def loop():
+                while True:
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.rows.append((float(sm), float(mx), int(rs)))
+                    except Exception:
+                        pass
+                    if self.stop_flag.wait(0.01):
+                        break
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -67,8 +97,20 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.mode == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+            import pynvml
+            names = {"hw_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(n for n, bit in names.items() if any(r[2] & bit for r in self.rows))
+            sm = [r[0] for r in self.rows]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.rows[0][1] if self.rows else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -84,7 +126,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def oracle_lib():
