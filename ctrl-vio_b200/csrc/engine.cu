@@ -566,7 +566,7 @@ int allreduce_scalars(ctvio_engine* e) {
 }
 
 // the LM step: reduced system (+ all-reduce of [M | rhs | diagA] over NVLink in sharded mode), factor, solve
-int lm_step(ctvio_engine* e, int nb, double radius) {
+int lm_step(ctvio_engine* e, int nb, double radius, const ApplyLaunch* fused_apply = nullptr) {
   LinearLaunch lin = linear_launch(e, nb);
   cudaStream_t st = e->stream;
   e->launches += launch_reduced_system(lin, radius, st);
@@ -577,7 +577,8 @@ int lm_step(ctvio_engine* e, int nb, double radius) {
     e->launches += launch_add_damping(lin, radius, st);
   }
   e->launches += launch_factor_solve(lin, st);
-  e->launches += launch_step_vectors(lin, st);
+  if (fused_apply) e->launches += launch_step_and_apply(lin, *fused_apply, st);
+  else e->launches += launch_step_vectors(lin, st);
   return CTVIO_OK;
 }
 
@@ -953,7 +954,7 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
   int iter = 0;
   int term = CTVIO_TERM_NO_CONVERGENCE;
 
-  auto apply = [&](int from, int to, double alpha, bool reset = true) {
+  auto make_apply = [&](int from, int to, double alpha) {
     ApplyLaunch ap;
     ap.dims = d;
     ap.x = e->x[from].ptrs();
@@ -965,7 +966,10 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     ap.clamp_ld = e->opt.fix_ld ? 0 : 1;
     ap.ld_lower = e->opt.ld_lower; ap.ld_upper = e->opt.ld_upper;
     ap.scal = e->d_scal.p;
-    e->launches += launch_apply_step(ap, st, reset);
+    return ap;
+  };
+  auto apply = [&](int from, int to, double alpha, bool reset = true) {
+    e->launches += launch_apply_step(make_apply(from, to, alpha), st, reset);
   };
 
   while (true) {
@@ -976,11 +980,12 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     const int cand = cur ^ 1;
     // ---- trust-region step + speculative full evaluation of the candidate ----
     prezero_slab(e, cand);  // everything enqueued so far has completed (scalars were read back): overlaps lm_step
-    rc = lm_step(e, cur, radius);
+    // (scale_copy_kernel of lm_step zeroes step_norm2 / x_norm2 / cost_eval / gmax: no memsets on the stream; the full
+    //  step is applied by the same launch that forms the step vectors)
+    const ApplyLaunch full_step = make_apply(cur, cand, 1.0);
+    rc = lm_step(e, cur, radius, &full_step);
     if (rc) return rc;
     sum.num_linear_solves++;
-    // (scale_copy_kernel of lm_step zeroed step_norm2 / x_norm2 / cost_eval / gmax: no memsets on the stream)
-    apply(cur, cand, 1.0, false);
     evaluate(e, cand, cand, true, false);
     sum.num_jacobian_evals++;
     LinearLaunch linc = linear_launch(e, cand);

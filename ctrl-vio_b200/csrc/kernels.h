@@ -274,6 +274,8 @@ struct ApplyLaunch {
   LmScalars* scal;
 };
 int launch_apply_step(const ApplyLaunch& a, cudaStream_t s, bool reset = true);
+// step vectors + full step (alpha = 1) applied in one launch; the per-step accumulators must already be zero
+int launch_step_and_apply(const LinearLaunch& a, const ApplyLaunch& ap, cudaStream_t s);
 int launch_gauge_realign(const StatePtrs& st, int nK, int min_idx, const double* R0_t0_dev, cudaStream_t s);
 
 struct QueryLaunch {

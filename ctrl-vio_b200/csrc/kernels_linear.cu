@@ -252,8 +252,10 @@ __device__ __forceinline__ void camera_step_block(const LinearLaunch& a, int blo
 
 // landmark back-substitution + landmark parts of gd / dHd: one WARP per landmark (coalesced reads of
 // its coupling row), reads y (not dc) so that it can run concurrently with camera_step_kernel.
-__device__ __forceinline__ void landmark_step_block(const LinearLaunch& a, int block) {
+__device__ __forceinline__ void landmark_step_block(const LinearLaunch& a, int block, const ApplyLaunch* ap = nullptr) {
   __shared__ double red[3][8];
+  __shared__ double red2[2][8];
+  double xn = 0, sn = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int l = block * 8 + warp;
   double gd = 0, dHd = 0, dmax = 0;
@@ -274,16 +276,23 @@ __device__ __forceinline__ void landmark_step_block(const LinearLaunch& a, int b
       dHd = 2.0 * d * (-wy) + a.ne.hl[l] * d * d;  // W_l . dc = -wy
       dmax = fabs(d);
       if (!isfinite(d)) a.scal->chol_fail = 1;
+      if (ap) {  // fused apply (alpha = 1): candidate inverse depth and its share of the norms
+        const double v = ap->x.rho[l], vn = v + d;
+        ap->xc.rho[l] = vn;
+        if (ap->active[a.dims.np + l]) { xn = v * v; sn = (v - vn) * (v - vn); }
+      }
     }
   }
-  if (lane == 0) { red[0][warp] = gd; red[1][warp] = dHd; red[2][warp] = dmax; }
+  if (lane == 0) { red[0][warp] = gd; red[1][warp] = dHd; red[2][warp] = dmax; red2[0][warp] = xn; red2[1][warp] = sn; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double g = 0, h = 0, m = 0;
-    for (int w = 0; w < 8; ++w) { g += red[0][w]; h += red[1][w]; m = fmax(m, red[2][w]); }
+    double g = 0, h = 0, m = 0, x = 0, s = 0;
+    for (int w = 0; w < 8; ++w) { g += red[0][w]; h += red[1][w]; m = fmax(m, red[2][w]); x += red2[0][w]; s += red2[1][w]; }
     if (g != 0.0) atomicAdd(&a.scal->gd, g);
     if (h != 0.0) atomicAdd(&a.scal->dHd, h);
     if (m > 0.0) atomic_max_pos(&a.scal->dir_max, m);
+    if (x != 0.0) atomicAdd(&a.scal->x_norm2, x);
+    if (s != 0.0) atomicAdd(&a.scal->step_norm2, s);
   }
 }
 
@@ -293,7 +302,7 @@ __device__ __forceinline__ void landmark_step_block(const LinearLaunch& a, int b
 __global__ void __launch_bounds__(256) step_vectors_kernel(LinearLaunch a, int ncb) {
   extern __shared__ double step_dsh[];  // [np]
   if (int(blockIdx.x) < ncb) camera_step_block(a, blockIdx.x, step_dsh);
-  else landmark_step_block(a, blockIdx.x - ncb);
+  else landmark_step_block(a, blockIdx.x - ncb, nullptr);
 }
 
 __global__ void add_damping_kernel(LinearLaunch a, double radius) {
@@ -404,27 +413,40 @@ int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld,
   return 1;
 }
 
-__device__ __forceinline__ Q4 stepped_knot(const ApplyLaunch& a, int i) {
-  const double* d = a.dc + 6 * i;
+// camera part of the step either from the stored vector dc or straight from the solution y of the reduced system
+// (dc = -sc o y on the non-constant dims), so that the state update does not have to wait for the kernel that writes dc
+struct StepSource {
+  const double* dc;      // non-null: stored step
+  const double* y;       // else: -sc[g] * y[g]
+  const double* sc;
+  const uint8_t* cmask;
+  __device__ __forceinline__ double operator()(int g) const {
+    if (dc) return dc[g];
+    return cmask[g] ? 0.0 : -sc[g] * y[g];
+  }
+};
+
+__device__ __forceinline__ Q4 stepped_knot(const ApplyLaunch& a, const StepSource& src, int i) {
+  const double d0 = src(6 * i), d1 = src(6 * i + 1), d2 = src(6 * i + 2);
   const Q4 q = load_q(a.x.q, i);
-  if (d[0] != 0.0 || d[1] != 0.0 || d[2] != 0.0) return so3_mul(q, so3_exp(V3{a.alpha * d[0], a.alpha * d[1], a.alpha * d[2]}));
+  if (d0 != 0.0 || d1 != 0.0 || d2 != 0.0) return so3_mul(q, so3_exp(V3{a.alpha * d0, a.alpha * d1, a.alpha * d2}));
   return q;
 }
 
-__global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
+// x+ = x (+) alpha * delta for element i of [knots | bias dims | line delay | landmarks (only if with_landmarks)]
+__device__ __forceinline__ void apply_step_block(const ApplyLaunch& a, const StepSource& src, int block, bool with_landmarks) {
   __shared__ double red[2][8];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nK = a.dims.nK, nB = a.dims.nB, nL = a.dims.nL;
+  const int i = block * blockDim.x + threadIdx.x;
+  const int nK = a.dims.nK, nB = a.dims.nB, nL = with_landmarks ? a.dims.nL : 0;
   double xn = 0, sn = 0;
   if (i < nK) {
-    const double* d = a.dc + 6 * i;
     const Q4 q = load_q(a.x.q, i);
-    const Q4 qn = stepped_knot(a, i);
+    const Q4 qn = stepped_knot(a, src, i);
     a.xc.q[4 * i] = qn.x; a.xc.q[4 * i + 1] = qn.y; a.xc.q[4 * i + 2] = qn.z; a.xc.q[4 * i + 3] = qn.w;
     if (i + 1 < nK) {
       // K0 folded in: knot-pair table entry i of the candidate (knot i+1 is recomputed here, bit-identical to what
       // its own thread stores)
-      const Q4 qm = stepped_knot(a, i + 1);
+      const Q4 qm = stepped_knot(a, src, i + 1);
       const double q2[8] = {qn.x, qn.y, qn.z, qn.w, qm.x, qm.y, qm.z, qm.w};
       KnotPair kp;
       make_knot_pair(q2, 0, kp);
@@ -437,7 +459,7 @@ __global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const double p = a.x.p[kPStride * i + c];
-      const double pn = p + a.alpha * d[3 + c];
+      const double pn = p + a.alpha * src(6 * i + 3 + c);
       a.xc.p[kPStride * i + c] = pn;
       if (a.count_camera && a.active[6 * i + 3 + c]) { xn += p * p; sn += (p - pn) * (p - pn); }
     }
@@ -445,12 +467,12 @@ __global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
   } else if (i < nK + 6 * nB) {
     const int b = i - nK;
     const double v = a.x.bias[b];
-    const double vn = v + a.alpha * a.dc[a.dims.idx_bias0 + b];
+    const double vn = v + a.alpha * src(a.dims.idx_bias0 + b);
     a.xc.bias[b] = vn;
     if (a.count_camera && a.active[a.dims.idx_bias0 + b]) { xn += v * v; sn += (v - vn) * (v - vn); }
   } else if (i == nK + 6 * nB) {
     const double v = *a.x.ld;
-    double vn = v + a.alpha * a.dc[a.dims.idx_ld];
+    double vn = v + a.alpha * src(a.dims.idx_ld);
     if (a.clamp_ld) vn = fmin(fmax(vn, a.ld_lower), a.ld_upper);
     *a.xc.ld = vn;
     a.scal->ld_value = vn;
@@ -473,10 +495,32 @@ __global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
   }
 }
 
+__global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {
+  apply_step_block(a, StepSource{a.dc, nullptr, nullptr, nullptr}, blockIdx.x, true);
+}
+
 int launch_apply_step(const ApplyLaunch& a, cudaStream_t s, bool reset) {
   const int n = a.dims.nK + 6 * a.dims.nB + 1 + a.dims.nL;
   if (reset) cudaMemsetAsync(&a.scal->step_norm2, 0, 2 * sizeof(double), s);  // step_norm2, x_norm2 are adjacent
   apply_step_kernel<<<(n + 255) / 256, 256, 0, s>>>(a);  // also writes the candidate's knot-pair table (K0)
+  return 1;
+}
+
+// K6 in ONE launch for the full step (alpha = 1): blocks [0, ncb) camera rows (dc, g'd, d'Hd), [ncb, ncb + nlb)
+// landmarks (back-substitution + the candidate's inverse depths + their norms), the rest the candidate's knots,
+// biases, line delay and knot-pair table computed straight from y.
+__global__ void __launch_bounds__(256) step_apply_kernel(LinearLaunch a, ApplyLaunch ap, int ncb, int nlb) {
+  extern __shared__ double step_dsh[];  // [np]
+  const int b = blockIdx.x;
+  if (b < ncb) camera_step_block(a, b, step_dsh);
+  else if (b < ncb + nlb) landmark_step_block(a, b - ncb, &ap);
+  else apply_step_block(ap, StepSource{nullptr, a.y, a.sc, a.cmask}, b - ncb - nlb, false);
+}
+
+int launch_step_and_apply(const LinearLaunch& a, const ApplyLaunch& ap, cudaStream_t s) {
+  const int ncb = (a.dims.np + 7) / 8, nlb = (a.dims.nL + 7) / 8;
+  const int nab = (a.dims.nK + 6 * a.dims.nB + 1 + 255) / 256;
+  step_apply_kernel<<<ncb + nlb + nab, 256, size_t(a.dims.np) * sizeof(double), s>>>(a, ap, ncb, nlb);
   return 1;
 }
 
