@@ -338,7 +338,13 @@ int launch_chol_coop(const LinearLaunch& a, cudaStream_t s) {
   double* yf = a.yf;
   LmScalars* scal = a.scal;
   void* args[] = {&M, &npad, &Linv, &rhs, &y, &yf, &scal};
-  cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_coop_kernel), dim3(grid), dim3(256), args, kCholCoopSmem, s);
+  if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_coop_kernel), dim3(grid), dim3(256), args, kCholCoopSmem, s) !=
+      cudaSuccess) {
+    // nothing ran: make the step fail loudly (the LM driver treats chol_fail as an invalid step and eventually
+    // terminates with FAILURE) instead of consuming a stale solution
+    cudaGetLastError();
+    cudaMemsetAsync(&scal->chol_fail, 0xff, sizeof(int32_t), s);
+  }
   return 1;
 }
 

@@ -323,8 +323,14 @@ int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
   // buffer to hold exactly the value 2^31 launches old: not a practical concern
   a.epoch = int(epoch_src.fetch_add(1, std::memory_order_relaxed) % 0x7ffffffeu) + 1;
   void* args[] = {&a};
-  cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_dag_kernel), dim3(dag_grid(l.npad / kCholNB)), dim3(256), args,
-                              kCholDagSmem, s);
+  const cudaError_t err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_dag_kernel), dim3(dag_grid(l.npad / kCholNB)),
+                                                      dim3(256), args, kCholDagSmem, s);
+  if (err != cudaSuccess) {
+    // the flag protocol needs every CTA resident; if the runtime cannot promise that (MIG slice, fewer usable SMs than
+    // reported, ...) the barrier kernel with its own, smaller grid is the safe path
+    cudaGetLastError();
+    return launch_chol_coop(l, s);
+  }
   return 1;
 }
 
