@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     load_tile_cg(S2, a.Linv + size_t(j) * kCholNB * kCholNB, kCholNB, tid);
     __syncthreads();
     frag_zero(acc);
-    tile_gemm_dmma<false>(S1, S2, acc, L);
+    tile_gemm_dmma<false, kCholNB, kGemmLowerB>(S1, S2, acc, L);
     __syncthreads();  // everybody is done reading S1
     frag_store(Lrm, acc, L);
     frag_store_t(S1, acc, L);
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     wait_flag(tile_ready + (j - 1) * nb + k, epoch);
     load_tile_cg(S2, a.M + size_t(j - 1) * kCholNB * npad + k * kCholNB, npad, tid);
     __syncthreads();
-    tile_gemm_dmma<true>(S1, S1, accD, L);
+    tile_gemm_dmma<true, kCholNB, kGemmLowerOut>(S1, S1, accD, L);
     tile_gemm_dmma<true>(S1, S2, accS, L);
     __syncthreads();
   }
@@ -228,14 +228,14 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     __syncthreads();
     DSTAMP(j, 8);
     frag_zero(accS);
-    tile_gemm_dmma<false>(S1, S2, accS, L);
+    tile_gemm_dmma<false, kCholNB, kGemmLowerB>(S1, S2, accS, L);
     __syncthreads();  // everybody is done reading S1
     DSTAMP(j, 9);
     frag_store(Lrm, accS, L);
     frag_store_t(S1, accS, L);
     __syncthreads();
     DSTAMP(j, 10);
-    tile_gemm_dmma<true>(S1, S1, accD, L);
+    tile_gemm_dmma<true, kCholNB, kGemmLowerOut>(S1, S1, accD, L);
     DSTAMP(j, 3);
   }
   frag_store(D, accD, L);

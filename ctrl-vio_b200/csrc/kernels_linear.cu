@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256, 2) schur_tile_kernel(LinearLaunch a) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const double v = acc.c[mt][nt][e];
-        if (v != 0.0) atomicAdd(tile + size_t(L.row0 + 8 * mt + L.g) * npad + L.col0 + 8 * nt + 2 * L.q + e, -v);
+        if (v != 0.0) atomicAdd(tile + size_t(L.row(mt)) * npad + L.col(nt) + e, -v);
       }
   if (diag) {
     if (tid < kCholNB) {
