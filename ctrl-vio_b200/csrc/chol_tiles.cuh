@@ -93,13 +93,103 @@ __device__ __forceinline__ bool chol4(const double a[4][4], double l[4][4], doub
 //       shared-memory round trips inside the 16 dependent columns;
 //   P2  the panel below (thread per row) and the block row of the inverse (thread per column: forward
 //       substitution of the identity / of the running sums W = -sum L X) by 16-deep substitution;
-//   P3  the trailing update of D and of the running sums in Xi as m8n8k4 fp64 tensor-core tiles (K = 16).
+//   P3  the trailing update of D and of the running sums in Xi as m8n8k4 fp64 tensor-core tiles (K = 16), overlapped
+//       with P1 of the next step (warp 0 updates the next diagonal block first and starts its pivot chain at once).
 //
 // `side(s)` is called by the threads of warps 1..7 (tid >= 32) at the start of 16-column step s, i.e. while warp 0
 // runs the P1 chain and they would otherwise idle at the barrier: room for ~1 us of unrelated work per step.
 struct NoSideJob {
   __device__ __forceinline__ void operator()(int) const {}
 };
+// P1 of 16-column step s (c0 = 16 s): executed by ONE full warp.  Lanes 16..31 mirror lanes 0..15 (same row, same
+// arithmetic, no stores) so that the shuffles are full-warp.
+__device__ __forceinline__ void factor_p1_warp(double* D, double* L16t, double* rdiag, int* s_bad, int c0, int lane) {
+  const int r = lane & 15;
+  double a[16];
+  const double* row = D + (c0 + r) * kTS + c0;
+#pragma unroll
+  for (int c = 0; c < 16; c += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(row + c);
+    a[c] = v.x; a[c + 1] = v.y;
+  }
+  double d = row[r];  // running diagonal element of this lane's row: the next pivot needs one shuffle only
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    double ajj = __shfl_sync(0xffffffffu, d, j);
+    // positive and normal <=> biased exponent in [1, 2046] and sign clear (integer test: off the fp64 pipe)
+    const unsigned hi = static_cast<unsigned>(__double2hiint(ajj));
+    if (hi - 0x00100000u >= 0x7fe00000u) { bad = true; ajj = 1.0; }
+    const double rinv = rsqrt_pos(ajj);
+    const double lij = a[j] * rinv;
+    a[j] = lij;
+    d = fma(-lij, lij, d);
+    // column j goes to the others through its (final) line of the transposed block: L16t[j][row]
+    if (lane < 16) L16t[j * 16 + r] = lij;
+    if (lane == j) rdiag[c0 + j] = rinv;
+    __syncwarp();
+#pragma unroll
+    for (int k = j + 1; k < 16; ++k) a[k] = fma(-lij, L16t[j * 16 + k], a[k]);
+  }
+  if (bad && lane == 0) *s_bad = 1;
+}
+
+// one m8n8 fragment of P3: C(rt, ct) -= P(rt) * B(ct)^T over the 16 columns of the current panel; B = the panel itself
+// (trailing part of D) or the freshly finished block row of the inverse (running sums in Xi)
+__device__ __forceinline__ void factor_p3_fragment(double* D, double* Xi, const double* Pt, int c0, int C, int rt, int ct, int g, int q) {
+  const bool inv = 8 * ct < C;
+  double* cp = (inv ? Xi : D) + (8 * rt + g) * kTS + 8 * ct + 2 * q;
+  const double* pa = Pt + q * kTS + 8 * rt + g;
+  const double* pb = inv ? Xi + (c0 + q) * kTS + 8 * ct + g : Pt + q * kTS + 8 * ct + g;
+  double2 cv = *reinterpret_cast<const double2*>(cp);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const double av = -pa[4 * kk * kTS], bv = pb[4 * kk * kTS];
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(cv.x), "+d"(cv.y) : "d"(av), "d"(bv));
+  }
+  *reinterpret_cast<double2*>(cp) = cv;
+}
+
+// P3 of step s for one fragment column ct (B fragments loaded once, fragment rows two at a time); rows < skip_below
+// are left out (they belong to the look-ahead warp)
+__device__ __forceinline__ void factor_p3_column(double* D, double* Xi, const double* Pt, int c0, int C, int ct, int rt_first,
+                                                 int g, int q) {
+  const bool inv = 8 * ct < C;
+  const double* pb = inv ? Xi + (c0 + q) * kTS + 8 * ct + g : Pt + q * kTS + 8 * ct + g;
+  double* base = (inv ? Xi : D) + g * kTS + 8 * ct + 2 * q;
+  double bv[4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) bv[kk] = pb[4 * kk * kTS];
+  int rt = rt_first;
+  for (; rt + 1 < 8; rt += 2) {
+    double2 c0v = *reinterpret_cast<const double2*>(base + 8 * rt * kTS);
+    double2 c1v = *reinterpret_cast<const double2*>(base + 8 * (rt + 1) * kTS);
+    const double* pa = Pt + q * kTS + 8 * rt + g;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const double a0 = -pa[4 * kk * kTS], a1 = -pa[4 * kk * kTS + 8];
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0v.x), "+d"(c0v.y) : "d"(a0), "d"(bv[kk]));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c1v.x), "+d"(c1v.y) : "d"(a1), "d"(bv[kk]));
+    }
+    *reinterpret_cast<double2*>(base + 8 * rt * kTS) = c0v;
+    *reinterpret_cast<double2*>(base + 8 * (rt + 1) * kTS) = c1v;
+  }
+  if (rt < 8) {
+    double2 c0v = *reinterpret_cast<const double2*>(base + 8 * rt * kTS);
+    const double* pa = Pt + q * kTS + 8 * rt + g;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const double a0 = -pa[4 * kk * kTS];
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0v.x), "+d"(c0v.y) : "d"(a0), "d"(bv[kk]));
+    }
+    *reinterpret_cast<double2*>(base + 8 * rt * kTS) = c0v;
+  }
+}
+
 template <class Side = NoSideJob>
 __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, double* XiT, double* T, double* rdiag, int* s_bad,
                                                      Side side = Side()) {
@@ -110,49 +200,15 @@ __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, doub
   if (tid == 0) *s_bad = 0;
   for (int e = tid; e < kTile; e += 256) Xi[e] = 0.0;
   __syncthreads();
+  FCLK(0, 0);
+  if (warp == 0) factor_p1_warp(D, L16t, rdiag, s_bad, 0, lane);
+  else side(0);
+  FCLK(0, 1);
+  __syncthreads();
 #pragma unroll 1
   for (int s = 0; s < 4; ++s) {
     const int c0 = 16 * s;
     const int R = 48 - c0, C = c0 + 16;
-    FCLK(s, 0);
-    if (warp == 0) {
-      // ---- P1: 16x16 diagonal block, one warp, registers + shuffles ----
-      // lanes 16..31 mirror lanes 0..15 (same row, same arithmetic, no stores) so that the shuffles are full-warp
-      const int r = lane & 15;
-      double a[16];
-      const double* row = D + (c0 + r) * kTS + c0;
-#pragma unroll
-      for (int c = 0; c < 16; c += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(row + c);
-        a[c] = v.x; a[c + 1] = v.y;
-      }
-      double d = row[r];  // running diagonal element of this lane's row: the next pivot needs one shuffle only
-      bool bad = false;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        double ajj = __shfl_sync(0xffffffffu, d, j);
-        // positive and normal <=> biased exponent in [1, 2046] and sign clear (integer test: off the fp64 pipe)
-        const unsigned hi = static_cast<unsigned>(__double2hiint(ajj));
-        if (hi - 0x00100000u >= 0x7fe00000u) { bad = true; ajj = 1.0; }
-        const double rinv = rsqrt_pos(ajj);
-        const double lij = a[j] * rinv;
-        a[j] = lij;
-        d = fma(-lij, lij, d);
-        // column j goes to the others through its (final) line of the transposed block: L16t[j][row]
-        if (lane < 16) L16t[j * 16 + r] = lij;
-        if (lane == j) rdiag[c0 + j] = rinv;
-        __syncwarp();
-#pragma unroll
-        for (int k = j + 1; k < 16; ++k) a[k] = fma(-lij, L16t[j * 16 + k], a[k]);
-      }
-      if (bad && lane == 0) *s_bad = 1;
-    } else {
-      side(s);
-    }
-    FCLK(s, 1);
-    __syncthreads();
-    // (a per-column hand-over of P1's columns to the P2 threads through a shared flag was measured slower: the
-    //  polling exposes every shared-memory latency that the compiler otherwise hoists out of the 16-column sweep)
     if (tid >= 32 && tid - 32 < R) {
       // ---- P2a: panel row i below the block, x L^T = a by substitution ----
       const int i = c0 + 16 + (tid - 32);
@@ -185,42 +241,28 @@ __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, doub
     }
     FCLK(s, 3);
     __syncthreads();
-    // ---- P3: rows >= c0+16:  D(:, >= c0+16) -= P P^T (lower tiles),  Xi(:, < c0+16) -= P X(c0..c0+15, :) ----
-    // warp = column tile: its B fragments are loaded once, row tiles are taken two at a time (independent chains)
+    // ---- P3 (rows >= c0+16:  D(:, >= c0+16) -= P P^T on the lower fragments,  Xi(:, < c0+16) -= P X(c0..c0+15, :))
+    //      overlapped with P1 of the NEXT step: warp 0 updates the three fragments of the next 16x16 diagonal block first
+    //      and runs its pivot chain while warps 1..7 do the rest of the update (fragment column = warp; warp 7 also takes
+    //      fragment column 0) and then the side job of the next step ----
     if (s < 3) {
-      const int ct = warp, rt0 = (c0 + 16) >> 3;
-      const bool inv = 8 * ct < C;
-      const double* pb = inv ? Xi + (c0 + q) * kTS + 8 * ct + g : Pt + q * kTS + 8 * ct + g;
-      double* base = (inv ? Xi : D) + g * kTS + 8 * ct + 2 * q;
-      double bv[4];
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) bv[kk] = pb[4 * kk * kTS];
-      int rt = ct > rt0 ? ct : rt0;
-      for (; rt + 1 < 8; rt += 2) {
-        double2 c0v = *reinterpret_cast<const double2*>(base + 8 * rt * kTS);
-        double2 c1v = *reinterpret_cast<const double2*>(base + 8 * (rt + 1) * kTS);
-        const double* pa = Pt + q * kTS + 8 * rt + g;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const double a0 = -pa[4 * kk * kTS], a1 = -pa[4 * kk * kTS + 8];
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                       : "+d"(c0v.x), "+d"(c0v.y) : "d"(a0), "d"(bv[kk]));
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                       : "+d"(c1v.x), "+d"(c1v.y) : "d"(a1), "d"(bv[kk]));
-        }
-        *reinterpret_cast<double2*>(base + 8 * rt * kTS) = c0v;
-        *reinterpret_cast<double2*>(base + 8 * (rt + 1) * kTS) = c1v;
-      }
-      if (rt < 8) {
-        double2 c0v = *reinterpret_cast<const double2*>(base + 8 * rt * kTS);
-        const double* pa = Pt + q * kTS + 8 * rt + g;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const double a0 = -pa[4 * kk * kTS];
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                       : "+d"(c0v.x), "+d"(c0v.y) : "d"(a0), "d"(bv[kk]));
-        }
-        *reinterpret_cast<double2*>(base + 8 * rt * kTS) = c0v;
+      const int rt0 = (c0 + 16) >> 3;
+      if (warp == 0) {
+        factor_p3_fragment(D, Xi, Pt, c0, C, rt0, rt0, g, q);
+        factor_p3_fragment(D, Xi, Pt, c0, C, rt0 + 1, rt0, g, q);
+        factor_p3_fragment(D, Xi, Pt, c0, C, rt0 + 1, rt0 + 1, g, q);
+        __syncwarp();
+        factor_p1_warp(D, L16t, rdiag, s_bad, c0 + 16, lane);
+      } else {
+        // fragment rows of column ct start at max(ct, rt0); the look-ahead fragments (rt0, rt0), (rt0+1, rt0),
+        // (rt0+1, rt0+1) are warp 0's
+        const int ct = warp;
+        int first = ct > rt0 ? ct : rt0;
+        if (ct == rt0) first = rt0 + 2;
+        else if (ct == rt0 + 1) first = rt0 + 2;
+        factor_p3_column(D, Xi, Pt, c0, C, ct, first, g, q);
+        if (warp == 7) factor_p3_column(D, Xi, Pt, c0, C, 0, rt0, g, q);
+        side(s + 1);
       }
     }
     FCLK(s, 5);
