@@ -359,29 +359,33 @@ __global__ void __launch_bounds__(1024) jacobi_eig_smem_kernel(double* Ag, doubl
         pp[2 * k] = p; pp[2 * k + 1] = q;
       }
       __syncthreads();
-      for (int e = tid; e < npairs * n; e += nt) {
-        const int k = e / n, r = e % n;
+      // warp = pair (k, k + 32, ...), lanes stride over the rows / columns: no integer divisions in the hot loops
+      const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+      for (int k = warp; k < npairs; k += nwarps) {
         const int p = pp[2 * k], q = pp[2 * k + 1];
         if (q >= n) continue;
         const double c = cs[2 * k], s = cs[2 * k + 1];
         if (s == 0.0) continue;
-        const double ap = A[r * ld + p], aq = A[r * ld + q];
-        A[r * ld + p] = c * ap - s * aq;
-        A[r * ld + q] = s * ap + c * aq;
-        const double vp = V[r * ld + p], vq = V[r * ld + q];
-        V[r * ld + p] = c * vp - s * vq;
-        V[r * ld + q] = s * vp + c * vq;
+        for (int r = lane; r < n; r += 32) {
+          const double ap = A[r * ld + p], aq = A[r * ld + q];
+          A[r * ld + p] = c * ap - s * aq;
+          A[r * ld + q] = s * ap + c * aq;
+          const double vp = V[r * ld + p], vq = V[r * ld + q];
+          V[r * ld + p] = c * vp - s * vq;
+          V[r * ld + q] = s * vp + c * vq;
+        }
       }
       __syncthreads();
-      for (int e = tid; e < npairs * n; e += nt) {
-        const int k = e / n, col = e % n;
+      for (int k = warp; k < npairs; k += nwarps) {
         const int p = pp[2 * k], q = pp[2 * k + 1];
         if (q >= n) continue;
         const double c = cs[2 * k], s = cs[2 * k + 1];
         if (s == 0.0) continue;
-        const double ap = A[p * ld + col], aq = A[q * ld + col];
-        A[p * ld + col] = c * ap - s * aq;
-        A[q * ld + col] = s * ap + c * aq;
+        for (int col = lane; col < n; col += 32) {
+          const double ap = A[p * ld + col], aq = A[q * ld + col];
+          A[p * ld + col] = c * ap - s * aq;
+          A[q * ld + col] = s * ap + c * aq;
+        }
       }
       __syncthreads();
     }
