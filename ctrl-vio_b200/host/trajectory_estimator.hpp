@@ -101,6 +101,10 @@ class TrajectoryEstimator {
   TrajectoryEstimator& operator=(const TrajectoryEstimator&) = delete;
 
   void SetFixedIndex(int idx) { fixed_control_point_index_ = idx; }  // trajectory_estimator.h:90
+  // Sliding the window: the Trajectory handed to the constructor holds only the window's slice of control points; when
+  // the slice moves, shift its time origin (the reference instead keeps one growing spline and freezes old knots,
+  // trajectory_manager.cpp:352-361).  Knot / bias indices of the prior are relative to the slice.
+  void SetTimeOrigin(int64_t t0_ns) { check(ctvio_set_time_origin(h_, t0_ns), "ctvio_set_time_origin"); }
 
   // trajectory_estimator.cpp:219-263
   void AddIMUMeasurementAnalytic(int64_t timestamp, const double gyro[3], const double accel[3], double* gyro_bias,
