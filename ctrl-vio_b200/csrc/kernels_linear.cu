@@ -392,14 +392,20 @@ __global__ void __launch_bounds__(1024) gradient_norm_kernel(LinearLaunch a, Sta
     if (threadIdx.x == 0) {
       a.scal->gmax = fmax(a.scal->gmax, v);
       if (pub) {
-        __threadfence();  // the other kernels' atomics into the scalar block are complete (stream order); re-read them
-        const volatile LmScalars* src = a.scal;
-        LmScalars c;
-        c.cost_eval = src->cost_eval; c.gd = src->gd; c.dHd = src->dHd; c.step_norm2 = src->step_norm2;
-        c.x_norm2 = src->x_norm2; c.err_sum = src->err_sum; c.gmax = src->gmax; c.dir_max = src->dir_max;
-        c.ld_value = src->ld_value; c.chol_fail = src->chol_fail; c.error_flags = src->error_flags;
-        c.pad[0] = c.pad[1] = 0;
-        pub->s = c;
+        // the other kernels' atomics into the scalar block are complete (stream order) and live in L2: fetch the block
+        // with six independent 16-byte L2 loads (one latency instead of eleven volatile reads) and hand it
+        // to the host
+        static_assert(sizeof(LmScalars) == 88, "scalar block is copied as five 16-byte words + one 8-byte word");
+        __threadfence();
+        const uint4* src = reinterpret_cast<const uint4*>(a.scal);
+        uint4 w[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[k] = __ldcg(src + k);
+        const uint2 w5 = __ldcg(reinterpret_cast<const uint2*>(src + 5));
+        uint4* dst = reinterpret_cast<uint4*>(&pub->s);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) dst[k] = w[k];
+        *reinterpret_cast<uint2*>(dst + 5) = w5;
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long*>(&pub->seq) = seq;
       }

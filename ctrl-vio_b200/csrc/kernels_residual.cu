@@ -286,6 +286,8 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
       const double2 pj = a.obs.pj[oi];
       const int4 meta = a.obs.meta[oi];
       const double rho = a.st.rho[meta.z];
+      // the landmark's coupling-row base (two dependent L2 loads): issued here so that the pose evaluation hides them
+      const int64_t w_base = FULL ? a.lm.woff[meta.z] - a.lm.lo[meta.z] : 0;
       const int64_t t_eval = side == 0 ? tt.x + int64_t(meta.x) * ld_ns : tt.y + int64_t(meta.y) * ld_ns;
       int32_t s;
       double u;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
           const int cb = side * 30;
           const int gk0 = w0[side];
           const int l = meta.z;
-          double* Wl = a.ne.W + a.lm.woff[l] - a.lm.lo[l];
+          double* Wl = a.ne.W + w_base;
           {
             const int unused = cb + (slot == 0 ? 4 : 0) * 6;
 #pragma unroll
