@@ -1,19 +1,16 @@
-// K5: blocked right-looking Cholesky of the reduced camera system + both triangular solves in ONE
-// cooperative persistent kernel (grid-wide barriers instead of two launches per block column).
+// K5 (fallback path): blocked right-looking Cholesky of the reduced camera system + both triangular solves in ONE
+// cooperative persistent kernel with grid-wide barriers.  The product path is the tile-DAG kernel (chol_dag.cu);
+// this one is used when the window is so large that not every 64x64 tile can have its own SM (n_p > ~1000), when the
+// runtime refuses the DAG's cooperative launch, or on request (CTVIO_CHOL=coop, A/B measurements).
 // Replaces the factor/solve half of Ceres' SPARSE_NORMAL_CHOLESKY step (trajectory_estimator.cpp:374;
 // Ceres is not under /root/reference) on the Schur-reduced system.
 //
 //   per block column k (NB = 64):
 //     phase P  every CTA that owns a panel slab loads the (already updated) diagonal block, factors it
-//              and inverts the factor redundantly in shared memory, turns its slabs' TRSM into a GEMM
-//              with that inverse, and folds the forward substitution of the right-hand side in;
-//     phase U  the trailing tiles are spread over all CTAs (64^3 register-tiled GEMM each).
+//              and inverts the factor redundantly in shared memory (factor_and_invert_64, chol_tiles.cuh), turns its
+//              slabs' TRSM into a GEMM with that inverse, and folds the forward substitution of the right-hand side in;
+//     phase U  the trailing tiles are spread over all CTAs (64^3 register-tiled DFMA GEMM each).
 //   afterwards CTA 0 runs the backward substitution with the stored block inverses.
-// The 64x64 diagonal factorisation is the serial critical path (measured: profiles/r1/c_chol_phase_timing.txt),
-// so it is latency-optimised: right-looking on 4x4 register blocks, the next diagonal block is factored
-// by its owner thread while everybody else is still applying the rank-4 update (look-ahead), panels use
-// substitution with the 4 reciprocal pivots (no inverse on the path), 4x4 inverses + recursive merges
-// afterwards, both the inverse and its transpose are produced so that no shared-memory transpose is needed.
 // M: lower triangle used; strictly-lower panels are overwritten with L, diagonal blocks are left
 // untouched (only their inverses, Linv, are kept).
 #include <cooperative_groups.h>

@@ -246,8 +246,11 @@ int prepare(ctvio_engine* e) {
     }
     // work items: chunks of one group; chunk size adapts so that small problems still spread over the SMs
     // (a group is split into equal chunks of at most `cap` observations, cap a multiple of the 128-observation round)
-    int cap = 512;
-    if (n < 148 * 512) cap = std::max(kVisObsPerRound, ((n / 148 + kVisObsPerRound - 1) / kVisObsPerRound) * kVisObsPerRound);
+    // one evaluation round (<= 128 observations, a lane pair each) per CTA: the round is latency bound whatever its
+    // fill, so a group is cut into EQUAL chunks of at most one round (263 observations -> 3 x 88, not 128 + 128 + 7)
+    // and every chunk gets its own CTA; CTVIO_VIS_CAP overrides (multiples of 128) for experiments
+    int cap = kVisObsPerRound;
+    if (const char* env = std::getenv("CTVIO_VIS_CAP")) cap = std::max(kVisObsPerRound, std::atoi(env) / kVisObsPerRound * kVisObsPerRound);
     std::vector<VisualItem> items;
     for (int k = 0; k < n;) {
       const int a = e->img_order[k];

@@ -18,8 +18,6 @@ constexpr int kRowStride = 66;     // shared-memory stride of one Jacobian row (
 constexpr int kObsStride = 2 * kRowStride + 2;  // stride of one observation's 2 rows: 268 words -> 2-way store conflicts instead of 16-way
 constexpr int kWinKnots = 5;       // knots of a padded evaluation window (se3_spline.h:463-503 with 39 ms padding)
 constexpr int kColLd = 60, kColR = 61, kColRho = 62;
-constexpr int kSchurMaxDim = 192;  // widest landmark-batch knot range handled by the tiled Schur kernel
-constexpr int kSchurBatch = 64;
 constexpr int kCholNB = 64;
 
 // ---- state at one linearisation point (all HBM) ------------------------------------------------

@@ -4,7 +4,7 @@
 // (trajectory_estimator.cpp:367-408 -> Ceres 1.14 levenberg_marquardt_strategy.cc +
 // SPARSE_NORMAL_CHOLESKY; Ceres is not under /root/reference):
 //   K4  scale_copy + schur     reduced camera system  M = S A S + D^2 - sum_l w_l w_l' / h_l
-//   K5  chol_panel/chol_update blocked right-looking Cholesky (NB = 64) + block triangular solves
+//   K5  (chol_dag.cu, chol_coop.cu) dense Cholesky (NB = 64) + block triangular solves
 //   K6  backsub / quad / apply landmark back-substitution, model cost change, x (+) delta, norms
 // The Schur complement is owner-computes by OUTPUT tile: every 64x64 tile of the lower triangle of M gets the list of
 // landmarks whose coupling row touches both of its blocks (built on the host), split into parts so that small
