@@ -282,3 +282,21 @@ def test_prior_factor_roundtrip(oracle_lib):
     s = eb.Solve(15)
     assert s.final_cost < s.initial_cost
     assert 0 <= eb.GetLineDelay() <= syn.LD_UPPER
+
+
+def test_set_time_origin_slides_the_knot_slice(oracle_lib):
+    """ctvio_set_time_origin (streaming, BASELINE config 5): dropping the first k control points and moving the origin
+    by k*dt leaves every trajectory query unchanged; an origin off the knot grid is rejected."""
+    w = small_window(seed=5, n_knots=8, n_kf=5, per_frame=4)
+    est = pkg.setup_estimator(oracle_lib, w)
+    t = w.t0_ns + np.array([1.2, 2.5, 3.7, 4.9], float) * w.dt_ns
+    t = t.astype(np.int64) + 123
+    ref = est.QueryTrajectory(t)
+    k = 1
+    est.SetTimeOrigin(w.t0_ns + k * w.dt_ns)
+    est.SetKnots(w.q0[k:], w.p0[k:])
+    got = est.QueryTrajectory(t)
+    for a, b in zip(ref, got):
+        assert np.allclose(a, b, rtol=0, atol=1e-12 * max(1.0, np.abs(a).max()))
+    with pytest.raises(pkg.CtvioError):
+        est.SetTimeOrigin(w.t0_ns + k * w.dt_ns + 7)
