@@ -41,6 +41,15 @@ __device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
   }
   __syncthreads();
 }
+// two flags at once: two polling threads in different warps, one barrier
+__device__ __forceinline__ void wait_flags2(const int* f1, const int* f2, int epoch) {
+  if (threadIdx.x == 0) {
+    while (ld_acquire(f1) != epoch) {}
+  } else if (threadIdx.x == 32) {
+    while (ld_acquire(f2) != epoch) {}
+  }
+  __syncthreads();
+}
 // all threads have written their part of the payload; publish it
 __device__ __forceinline__ void post_flag(int* flag, int epoch) {
   __syncthreads();
@@ -162,9 +171,8 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     Frag acc;
     frag_load_global(acc, slot, npad, L);
     for (int k = 0; k < j; ++k) {
-      wait_flag(tile_ready + i * nb + k, epoch);
+      wait_flags2(tile_ready + i * nb + k, tile_ready + j * nb + k, epoch);
       load_tile_cg(S1, a.M + size_t(i) * kCholNB * npad + k * kCholNB, npad, tid);
-      wait_flag(tile_ready + j * nb + k, epoch);
       load_tile_cg(S2, a.M + size_t(j) * kCholNB * npad + k * kCholNB, npad, tid);
       __syncthreads();
       tile_gemm_dmma<true>(S1, S2, acc, L);
@@ -204,9 +212,8 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   double* slot = a.M + size_t(j) * kCholNB * npad + (j >= 1 ? j - 1 : 0) * kCholNB;
   if (j >= 1) frag_load_global(accS, slot, npad, L);
   for (int k = 0; k + 1 < j; ++k) {
-    wait_flag(tile_ready + j * nb + k, epoch);
+    wait_flags2(tile_ready + j * nb + k, tile_ready + (j - 1) * nb + k, epoch);
     load_tile_cg(S1, a.M + size_t(j) * kCholNB * npad + k * kCholNB, npad, tid);
-    wait_flag(tile_ready + (j - 1) * nb + k, epoch);
     load_tile_cg(S2, a.M + size_t(j - 1) * kCholNB * npad + k * kCholNB, npad, tid);
     __syncthreads();
     tile_gemm_dmma<true, kCholNB, kGemmLowerOut>(S1, S1, accD, L);
@@ -282,20 +289,32 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   post_flag(fwd_ready + j, epoch);
 
   // backward sweep: x_j = Linv_j^T (yf_j - sum_{r > j} L(r,j)^T x_r)
-  for (int r = j + 1; r < nb; ++r) wait_flag(bwd_ready + r * nb + j, epoch);
+  // all partials of this block column: one polling thread per flag (the early ones cost a single L2 round trip in
+  // parallel instead of nb - 1 - j sequential ones), then one barrier
+  if (tid < nb - 1 - j) {
+    const int* f = bwd_ready + (j + 1 + tid) * nb + j;
+    while (ld_acquire(f) != epoch) {}
+  }
+  __syncthreads();
   {
     const double sp = sum_partials(bwd_part + (size_t(j) * nb + j + 1) * kCholNB, nb - 1 - j, kCholNB, red, tid);
     if (tid < kCholNB) vec[tid] = vec2[tid] - sp;
   }
   __syncthreads();
   tile_matvec(XiT, vec, a.y + j * kCholNB, tid, vec2);  // XiT row-major = Linv^T
-  post_flag(x_ready + j, epoch);
-  DSTAMP(j, 7);
   if (j >= 1) {
-    // own sub-diagonal tile: L(j,j-1)^T x_j for column CTA j-1  (post_flag's barrier made vec2 visible; S1 = L^T)
-    tile_matvec(S1, vec2, bwd_part + (size_t(j - 1) * nb + j) * kCholNB, tid);
-    post_flag(bwd_ready + j * nb + (j - 1), epoch);
+    // own sub-diagonal tile: L(j,j-1)^T x_j for column CTA j-1, published together with x_j (one fence for both:
+    // the next column of the backward chain waits for exactly this partial)
+    __syncthreads();
+    tile_matvec(S1, vec2, bwd_part + (size_t(j - 1) * nb + j) * kCholNB, tid);  // S1 = L(j,j-1)^T
   }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (j >= 1) st_release(bwd_ready + j * nb + (j - 1), epoch);
+    st_release(x_ready + j, epoch);
+  }
+  DSTAMP(j, 7);
 }
 
 // number of CTAs the DAG kernel needs for nb block columns
