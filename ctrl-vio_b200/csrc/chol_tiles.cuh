@@ -82,7 +82,7 @@ __device__ __forceinline__ bool chol4(const double a[4][4], double l[4][4], doub
 }
 
 // Lower Cholesky of the 64x64 block D (row-major, row stride kTS; destroyed) by 256 threads, producing the inverse
-// factor Xi = L^-1 (lower triangular, row-major) and XiT = Xi^T.  T is scratch (>= 256 + 16 * kTS doubles),
+// factor Xi = L^-1 (lower triangular, row-major) and XiT = Xi^T.  T is scratch (>= 256 + 16 * kTS + 16 * kX16Stride doubles),
 // rdiag[64] receives 1 / L_jj.  Returns false on a non-positive pivot (the pivot is replaced by 1 so that the
 // sweep terminates with finite numbers).
 //
@@ -91,8 +91,8 @@ __device__ __forceinline__ bool chol4(const double a[4][4], double l[4][4], doub
 //   P1  ONE warp factors the 16x16 diagonal block out of registers (lane = row, columns broadcast by shuffles, the
 //       running diagonal kept in its own register so that the next pivot needs a single shuffle): no barriers or
 //       shared-memory round trips inside the 16 dependent columns;
-//   P2  the panel below (thread per row) and the block row of the inverse (thread per column: forward
-//       substitution of the identity / of the running sums W = -sum L X) by 16-deep substitution;
+//   P2  the panel below and the block row of the inverse as small tensor-core products with the explicit 16x16
+//       inverse, which the 16 otherwise idle lanes of the P1 warp compute alongside the factorisation;
 //   P3  the trailing update of D and of the running sums in Xi as m8n8k4 fp64 tensor-core tiles (K = 16), overlapped
 //       with P1 of the next step (warp 0 updates the next diagonal block first and starts its pivot chain at once).
 //
@@ -101,16 +101,21 @@ __device__ __forceinline__ bool chol4(const double a[4][4], double l[4][4], doub
 struct NoSideJob {
   __device__ __forceinline__ void operator()(int) const {}
 };
-// P1 of 16-column step s (c0 = 16 s): executed by ONE full warp.  Lanes 16..31 mirror lanes 0..15 (same row, same
-// arithmetic, no stores) so that the shuffles are full-warp.
-__device__ __forceinline__ void factor_p1_warp(double* D, double* L16t, double* rdiag, int* s_bad, int c0, int lane) {
+constexpr int kX16Stride = 20;  // row stride (doubles) of the 16x16 inverse block: m8n8k4 fragment loads conflict-free
+
+// P1 of 16-column step s (c0 = 16 s): executed by ONE full warp.  Lanes 0..15 hold the rows of the diagonal block;
+// lanes 16..31 run the SAME instruction stream on the columns of the identity, i.e. lane 16 + c forward-substitutes
+// column c of X16 = L16^-1 one pivot behind the factorisation, for free (SIMT).  XT16[m][k] = X16[k][m].
+__device__ __forceinline__ void factor_p1_warp(double* D, double* L16t, double* XT16, double* rdiag, int* s_bad, int c0, int lane) {
   const int r = lane & 15;
+  const bool real = lane < 16;
   double a[16];
   const double* row = D + (c0 + r) * kTS + c0;
 #pragma unroll
   for (int c = 0; c < 16; c += 2) {
     const double2 v = *reinterpret_cast<const double2*>(row + c);
-    a[c] = v.x; a[c + 1] = v.y;
+    a[c] = real ? v.x : (c == r ? 1.0 : 0.0);
+    a[c + 1] = real ? v.y : (c + 1 == r ? 1.0 : 0.0);
   }
   double d = row[r];  // running diagonal element of this lane's row: the next pivot needs one shuffle only
   bool bad = false;
@@ -121,15 +126,19 @@ __device__ __forceinline__ void factor_p1_warp(double* D, double* L16t, double* 
     const unsigned hi = static_cast<unsigned>(__double2hiint(ajj));
     if (hi - 0x00100000u >= 0x7fe00000u) { bad = true; ajj = 1.0; }
     const double rinv = rsqrt_pos(ajj);
-    const double lij = a[j] * rinv;
+    const double lij = a[j] * rinv;  // lanes 0..15: L[row][j];  lanes 16..31: X16[j][column]
     a[j] = lij;
     d = fma(-lij, lij, d);
     // column j goes to the others through its (final) line of the transposed block: L16t[j][row]
-    if (lane < 16) L16t[j * 16 + r] = lij;
+    if (real) L16t[j * 16 + r] = lij;
     if (lane == j) rdiag[c0 + j] = rinv;
     __syncwarp();
 #pragma unroll
     for (int k = j + 1; k < 16; ++k) a[k] = fma(-lij, L16t[j * 16 + k], a[k]);
+  }
+  if (!real) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) *reinterpret_cast<double2*>(XT16 + r * kX16Stride + k) = make_double2(a[k], a[k + 1]);
   }
   if (bad && lane == 0) *s_bad = 1;
 }
@@ -197,11 +206,12 @@ __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, doub
   const int g = lane >> 2, q = lane & 3;
   double* L16t = T;      // [16][16] current diagonal block of L, transposed: L16t[c][r] = L[r][c] (r >= c valid)
   double* Pt = T + 256;  // [16][kTS] current block column of L, transposed: Pt[m][row]
+  double* XT16 = T + 256 + 16 * kTS;  // [16][kX16Stride] inverse of the current diagonal block, transposed
   if (tid == 0) *s_bad = 0;
   for (int e = tid; e < kTile; e += 256) Xi[e] = 0.0;
   __syncthreads();
   FCLK(0, 0);
-  if (warp == 0) factor_p1_warp(D, L16t, rdiag, s_bad, 0, lane);
+  if (warp == 0) factor_p1_warp(D, L16t, XT16, rdiag, s_bad, 0, lane);
   else side(0);
   FCLK(0, 1);
   __syncthreads();
@@ -209,34 +219,49 @@ __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, doub
   for (int s = 0; s < 4; ++s) {
     const int c0 = 16 * s;
     const int R = 48 - c0, C = c0 + 16;
-    if (tid >= 32 && tid - 32 < R) {
-      // ---- P2a: panel row i below the block, x L^T = a by substitution ----
-      const int i = c0 + 16 + (tid - 32);
-      double x[16];
+    {
+      // ---- P2 as small tensor-core products with the explicit 16x16 inverse from P1:
+      //   P2a  panel  L(rows below, c0..c0+15) = A_panel * X16^T            -> Pt (transposed, the operand of P3)
+      //   P2b  block row of the inverse  X(c0..c0+15, cols < c0) = X16 * W   (in place in Xi), plus the diagonal block
+      // one task = one 8x8 panel fragment / one fragment column of the block row (both row fragments: the product is
+      // in place) / the copy of the diagonal block; tasks are spread over the 8 warps ----
+      const int n_a = 2 * (R >> 3), n_b = c0 >> 3, ntask = n_a + n_b + 1;
+      for (int t = warp; t < ntask; t += 8) {
+        if (t < n_a) {
+          const int i0 = c0 + 16 + 8 * (t >> 1), n0 = 8 * (t & 1);
+          const double* pa = D + (i0 + g) * kTS + c0 + q;        // A[i0 + g][k0 + q]
+          const double* pb = XT16 + q * kX16Stride + n0 + g;     // B[k0 + q][n0 + g] = X16[n0 + g][k0 + q]
+          double2 cv = make_double2(0.0, 0.0);
+          const int nk = n0 ? 4 : 2;                              // X16 is lower triangular: k <= n
+          for (int kk = 0; kk < nk; ++kk)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(cv.x), "+d"(cv.y) : "d"(pa[4 * kk]), "d"(pb[4 * kk * kX16Stride]));
+          Pt[(n0 + 2 * q) * kTS + i0 + g] = cv.x;
+          Pt[(n0 + 2 * q + 1) * kTS + i0 + g] = cv.y;
+        } else if (t < n_a + n_b) {
+          const int n0 = 8 * (t - n_a);
+          double bv[4];
 #pragma unroll
-      for (int c = 0; c < 16; c += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(D + i * kTS + c0 + c);
-        x[c] = v.x; x[c + 1] = v.y;
-      }
+          for (int kk = 0; kk < 4; ++kk) bv[kk] = Xi[(c0 + 4 * kk + q) * kTS + n0 + g];   // W rows (running sums)
+          const double* pa = XT16 + q * kX16Stride + g;          // A[r0 + g][k0 + q] = X16[r0 + g][k0 + q]
+          double2 c0v = make_double2(0.0, 0.0), c1v = make_double2(0.0, 0.0);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {  // right-looking: the dependent chain is one multiply + one FMA per column
-        x[c] *= rdiag[c0 + c];
-        Pt[c * kTS + i] = x[c];
-#pragma unroll
-        for (int m = c + 1; m < 16; ++m) x[m] = fma(-x[c], L16t[c * 16 + m], x[m]);
-      }
-    } else if (tid >= 96 && tid - 96 < C) {
-      // ---- P2b: column cc of the block row of the inverse, L x = w (running sums, or the identity) ----
-      const int cc = tid - 96;
-      double x[16];
-#pragma unroll
-      for (int r = 0; r < 16; ++r) x[r] = cc < c0 ? Xi[(c0 + r) * kTS + cc] : (cc - c0 == r ? 1.0 : 0.0);
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        x[r] *= rdiag[c0 + r];
-        Xi[(c0 + r) * kTS + cc] = x[r];
-#pragma unroll
-        for (int m = r + 1; m < 16; ++m) x[m] = fma(-L16t[r * 16 + m], x[r], x[m]);
+          for (int kk = 0; kk < 4; ++kk) {
+            if (kk < 2)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(c0v.x), "+d"(c0v.y) : "d"(pa[4 * kk * kX16Stride]), "d"(bv[kk]));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c1v.x), "+d"(c1v.y) : "d"(pa[4 * kk * kX16Stride + 8]), "d"(bv[kk]));
+          }
+          // every lane's W values went through the mma above before any lane gets here: in place is safe
+          *reinterpret_cast<double2*>(Xi + (c0 + g) * kTS + n0 + 2 * q) = c0v;
+          *reinterpret_cast<double2*>(Xi + (c0 + 8 + g) * kTS + n0 + 2 * q) = c1v;
+        } else {
+          for (int e = lane; e < 256; e += 32) {
+            const int rr = e >> 4, cc = e & 15;
+            Xi[(c0 + rr) * kTS + c0 + cc] = cc <= rr ? XT16[cc * kX16Stride + rr] : 0.0;
+          }
+        }
       }
     }
     FCLK(s, 3);
@@ -252,7 +277,7 @@ __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, doub
         factor_p3_fragment(D, Xi, Pt, c0, C, rt0 + 1, rt0, g, q);
         factor_p3_fragment(D, Xi, Pt, c0, C, rt0 + 1, rt0 + 1, g, q);
         __syncwarp();
-        factor_p1_warp(D, L16t, rdiag, s_bad, c0 + 16, lane);
+        factor_p1_warp(D, L16t, XT16, rdiag, s_bad, c0 + 16, lane);
       } else {
         // fragment rows of column ct start at max(ct, rt0); the look-ahead fragments (rt0, rt0), (rt0+1, rt0),
         // (rt0+1, rt0+1) are warp 0's
