@@ -143,23 +143,6 @@ __device__ __forceinline__ void factor_p1_warp(double* D, double* L16t, double* 
   if (bad && lane == 0) *s_bad = 1;
 }
 
-// one m8n8 fragment of P3: C(rt, ct) -= P(rt) * B(ct)^T over the 16 columns of the current panel; B = the panel itself
-// (trailing part of D) or the freshly finished block row of the inverse (running sums in Xi)
-__device__ __forceinline__ void factor_p3_fragment(double* D, double* Xi, const double* Pt, int c0, int C, int rt, int ct, int g, int q) {
-  const bool inv = 8 * ct < C;
-  double* cp = (inv ? Xi : D) + (8 * rt + g) * kTS + 8 * ct + 2 * q;
-  const double* pa = Pt + q * kTS + 8 * rt + g;
-  const double* pb = inv ? Xi + (c0 + q) * kTS + 8 * ct + g : Pt + q * kTS + 8 * ct + g;
-  double2 cv = *reinterpret_cast<const double2*>(cp);
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    const double av = -pa[4 * kk * kTS], bv = pb[4 * kk * kTS];
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(cv.x), "+d"(cv.y) : "d"(av), "d"(bv));
-  }
-  *reinterpret_cast<double2*>(cp) = cv;
-}
-
 // P3 of step s for one fragment column ct (B fragments loaded once, fragment rows two at a time); rows < skip_below
 // are left out (they belong to the look-ahead warp)
 __device__ __forceinline__ void factor_p3_column(double* D, double* Xi, const double* Pt, int c0, int C, int ct, int rt_first,
@@ -223,21 +206,29 @@ __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, doub
       // ---- P2 as small tensor-core products with the explicit 16x16 inverse from P1:
       //   P2a  panel  L(rows below, c0..c0+15) = A_panel * X16^T            -> Pt (transposed, the operand of P3)
       //   P2b  block row of the inverse  X(c0..c0+15, cols < c0) = X16 * W   (in place in Xi), plus the diagonal block
-      // one task = one 8x8 panel fragment / one fragment column of the block row (both row fragments: the product is
-      // in place) / the copy of the diagonal block; tasks are spread over the 8 warps ----
-      const int n_a = 2 * (R >> 3), n_b = c0 >> 3, ntask = n_a + n_b + 1;
+      // one task = one panel row fragment (both column fragments) / one fragment column of the block row (both row
+      // fragments: the product is in place) / the copy of the diagonal block ----
+      const int n_a = R >> 3, n_b = c0 >> 3, ntask = n_a + n_b + 1;  // = 7 in every step: one task per warp
       for (int t = warp; t < ntask; t += 8) {
         if (t < n_a) {
-          const int i0 = c0 + 16 + 8 * (t >> 1), n0 = 8 * (t & 1);
+          // both column fragments of one panel row fragment: shared A operand, two independent accumulator chains
+          const int i0 = c0 + 16 + 8 * t;
           const double* pa = D + (i0 + g) * kTS + c0 + q;        // A[i0 + g][k0 + q]
-          const double* pb = XT16 + q * kX16Stride + n0 + g;     // B[k0 + q][n0 + g] = X16[n0 + g][k0 + q]
-          double2 cv = make_double2(0.0, 0.0);
-          const int nk = n0 ? 4 : 2;                              // X16 is lower triangular: k <= n
-          for (int kk = 0; kk < nk; ++kk)
+          const double* pb = XT16 + q * kX16Stride + g;          // B[k0 + q][n0 + g] = X16[n0 + g][k0 + q]
+          double2 cl = make_double2(0.0, 0.0), ch = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const double av = pa[4 * kk];
+            if (kk < 2)                                           // X16 is lower triangular: k <= n
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(cl.x), "+d"(cl.y) : "d"(av), "d"(pb[4 * kk * kX16Stride]));
             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(cv.x), "+d"(cv.y) : "d"(pa[4 * kk]), "d"(pb[4 * kk * kX16Stride]));
-          Pt[(n0 + 2 * q) * kTS + i0 + g] = cv.x;
-          Pt[(n0 + 2 * q + 1) * kTS + i0 + g] = cv.y;
+                         : "+d"(ch.x), "+d"(ch.y) : "d"(av), "d"(pb[4 * kk * kX16Stride + 8]));
+          }
+          Pt[(2 * q) * kTS + i0 + g] = cl.x;
+          Pt[(2 * q + 1) * kTS + i0 + g] = cl.y;
+          Pt[(8 + 2 * q) * kTS + i0 + g] = ch.x;
+          Pt[(8 + 2 * q + 1) * kTS + i0 + g] = ch.y;
         } else if (t < n_a + n_b) {
           const int n0 = 8 * (t - n_a);
           double bv[4];
@@ -268,24 +259,44 @@ __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, doub
     __syncthreads();
     // ---- P3 (rows >= c0+16:  D(:, >= c0+16) -= P P^T on the lower fragments,  Xi(:, < c0+16) -= P X(c0..c0+15, :))
     //      overlapped with P1 of the NEXT step: warp 0 updates the three fragments of the next 16x16 diagonal block first
-    //      and runs its pivot chain while warps 1..7 do the rest of the update (fragment column = warp; warp 7 also takes
-    //      fragment column 0) and then the side job of the next step ----
+    //      and runs its pivot chain while warps 1..7 do the rest of the update, then the side job of the next step ----
     if (s < 3) {
       const int rt0 = (c0 + 16) >> 3;
       if (warp == 0) {
-        factor_p3_fragment(D, Xi, Pt, c0, C, rt0, rt0, g, q);
-        factor_p3_fragment(D, Xi, Pt, c0, C, rt0 + 1, rt0, g, q);
-        factor_p3_fragment(D, Xi, Pt, c0, C, rt0 + 1, rt0 + 1, g, q);
+        {  // the three lower fragments of the next diagonal block, three independent accumulator chains
+          double* cp0 = D + (8 * rt0 + g) * kTS + 8 * rt0 + 2 * q;
+          double* cp1 = cp0 + 8 * kTS;      // (rt0 + 1, rt0)
+          double* cp2 = cp1 + 8;            // (rt0 + 1, rt0 + 1)
+          double2 v0 = *reinterpret_cast<const double2*>(cp0), v1 = *reinterpret_cast<const double2*>(cp1),
+                  v2 = *reinterpret_cast<const double2*>(cp2);
+          const double* pp = Pt + q * kTS + 8 * rt0 + g;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const double p0 = pp[4 * kk * kTS], p1 = pp[4 * kk * kTS + 8];
+            const double a0 = -p0, a1 = -p1;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(v0.x), "+d"(v0.y) : "d"(a0), "d"(p0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(v1.x), "+d"(v1.y) : "d"(a1), "d"(p0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(v2.x), "+d"(v2.y) : "d"(a1), "d"(p1));
+          }
+          *reinterpret_cast<double2*>(cp0) = v0;
+          *reinterpret_cast<double2*>(cp1) = v1;
+          *reinterpret_cast<double2*>(cp2) = v2;
+        }
         __syncwarp();
         factor_p1_warp(D, L16t, XT16, rdiag, s_bad, c0 + 16, lane);
       } else {
-        // fragment rows of column ct start at max(ct, rt0); the look-ahead fragments (rt0, rt0), (rt0+1, rt0),
-        // (rt0+1, rt0+1) are warp 0's
+        // fragment column = warp (warp 7 also takes column 0); fragment rows start at max(ct, rt0); the look-ahead
+        // fragments (rt0, rt0), (rt0+1, rt0), (rt0+1, rt0+1) are warp 0's.  (Keeping warp 4 - same scheduler as the
+        // pivot warp - out of the tensor-core work was measured to change nothing: the pivot chain runs at ~0.3x
+        // while the other warps' DMMAs are in flight whichever scheduler issues them, i.e. the fp64 pipe behaves as
+        // one SM-wide resource; the overlap still hides about half of P3.)
         const int ct = warp;
         int first = ct > rt0 ? ct : rt0;
-        if (ct == rt0) first = rt0 + 2;
-        else if (ct == rt0 + 1) first = rt0 + 2;
-        factor_p3_column(D, Xi, Pt, c0, C, ct, first, g, q);
+        if (ct == rt0 || ct == rt0 + 1) first = rt0 + 2;
+        if (first < 8) factor_p3_column(D, Xi, Pt, c0, C, ct, first, g, q);
         if (warp == 7) factor_p3_column(D, Xi, Pt, c0, C, 0, rt0, g, q);
         side(s + 1);
       }
