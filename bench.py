@@ -318,6 +318,15 @@ def main():
         raise SystemExit("bench.py --impl ctvio needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one window per GPU, each driven by its own host thread (launches + a spin on mapped memory once per LM step):
+        # give every rank its own slice of the host cores so that the ranks do not migrate onto each other
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = len(cpus) // world
+            if per >= 4:
+                os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per])
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
