@@ -100,7 +100,7 @@ ABI_SYMBOLS = [
     "solve", "gauge_realign", "marginalize", "get_prior", "adopt_prior",
     "save_state", "restore_state",
     "eval_image_factors", "eval_imu_factors", "eval_cost", "normal_equations",
-    "query_trajectory", "profile_kernels", "measure_fp64_tflops", "selfcheck_solver", "nccl_unique_id", "comm_init",
+    "query_trajectory", "triangulate", "profile_kernels", "measure_fp64_tflops", "selfcheck_solver", "nccl_unique_id", "comm_init",
 ]
 
 
@@ -360,6 +360,18 @@ class Estimator:
         q = np.zeros((n, 4)); p = np.zeros((n, 3)); w = np.zeros((n, 3)); v = np.zeros((n, 3)); a = np.zeros((n, 3))
         self.lib.call("query_trajectory", self.h, C.c_int32(n), _lp(t), _dp(q), _dp(p), _dp(w), _dp(v), _dp(a))
         return q, p, w, v, a
+
+    def Triangulate(self, Rs, Ps, ric, tic, start_frame, obs_offset, obs_point, depth, window_size=10,
+                    init_depth=5.0):
+        """FeatureManager::triangulate (feature_manager.cpp:230-275) over CSR-packed landmark observations;
+        returns the updated depth array (entries > 0 are kept)."""
+        Rs = _f64(Rs, (-1, 9)); Ps = _f64(Ps, (-1, 3)); ric = _f64(ric, (9,)); tic = _f64(tic, (3,))
+        start_frame = _i32(start_frame); obs_offset = _i32(obs_offset); obs_point = _f64(obs_point, (-1, 3))
+        depth = _f64(depth, (-1,)).copy()
+        self.lib.call("triangulate", self.h, C.c_int32(Rs.shape[0]), _dp(Rs), _dp(Ps), _dp(ric), _dp(tic),
+                      C.c_int32(start_frame.shape[0]), _ip(start_frame), _ip(obs_offset), _dp(obs_point),
+                      C.c_int32(window_size), C.c_double(init_depth), _dp(depth))
+        return depth
 
     def ProfileKernels(self, reps=20, flush_l2=True):
         out = np.zeros(8)

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/ctvio.h"
+#include "frontend.h"
 #include "kernels.h"
 #include "marginalize.h"
 #include "poly_min.h"
@@ -153,6 +154,7 @@ struct ctvio_engine {
   bool prior_dirty = true;
 
   DevBuf<double> d_tmp;  // scratch (gauge inputs, probe outputs)
+  DevBuf<int32_t> d_tri_idx;  // ctvio_triangulate: start frames | observation offsets
   // marginalization workspace (K7), kept across windows: allocation / free costs more than the kernels
   struct MargWs {
     DevBuf<int32_t> pos_cam, pos_lm, prior_pos, marg_img, marg_imu;
@@ -163,6 +165,7 @@ struct ctvio_engine {
   // multi-GPU
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  bool shard_checked = false;  // landmark ownership verified for the current factor set
 
   int64_t launches = 0;
 
@@ -212,6 +215,7 @@ int prepare(ctvio_engine* e) {
   cudaStream_t st = e->stream;
   const ProblemDims d = e->dims();
   if (e->structure_dirty) {
+    e->shard_checked = false;
     // ---- image factors: frame-pair groups ----
     const int n = int(e->img.size());
     std::vector<int32_t> wi0(n), wj0(n);
@@ -475,6 +479,7 @@ int prepare_prior(ctvio_engine* e) {
   CUDA_OK(e->d_prior_JtJ.reserve(size_t(pr.n) * pr.n));
   CUDA_OK(e->d_prior_dx.reserve(pr.n));
   CUDA_OK(e->d_prior_res.reserve(pr.n));
+  CUDA_OK(cudaMemsetAsync(e->d_prior_dx.p, 0, size_t(pr.n) * sizeof(double), st));
   e->launches += ctvio::launch_gram(e->d_prior_J.p, pr.n, pr.n, e->d_prior_JtJ.p, st);
   return CTVIO_OK;
 }
@@ -565,6 +570,47 @@ int allreduce_scalars(ctvio_engine* e) {
   std::string err;
   if (!ctvio::comm_allreduce_sum(e->nccl_comm, &e->d_scal.p->cost_eval, kLmSumScalars, e->stream, &err))
     return fail(CTVIO_ERR_NCCL, err);
+  return CTVIO_OK;
+}
+
+// sharded mode: every rank must enter (or skip) the collectives of a solve together.  Sums a per-rank error flag; returns
+// CTVIO_OK only if every rank reported local_rc == 0 (a failing rank keeps its own message).
+int shard_consensus(ctvio_engine* e, int local_rc) {
+  if (e->world <= 1) return local_rc;
+  const std::string local_msg = g_err;
+  cudaStream_t st = e->stream;
+  CUDA_OK(e->d_tmp.reserve(16));
+  const double flag = local_rc ? 1.0 : 0.0;
+  double total = 0.0;
+  CUDA_OK(cudaMemcpyAsync(e->d_tmp.p, &flag, sizeof(double), cudaMemcpyHostToDevice, st));
+  std::string err;
+  if (!ctvio::comm_allreduce_sum(e->nccl_comm, e->d_tmp.p, 1, st, &err)) return fail(CTVIO_ERR_NCCL, err);
+  CUDA_OK(cudaMemcpyAsync(&total, e->d_tmp.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (local_rc) return fail(local_rc, local_msg);
+  if (total != 0.0) return fail(CTVIO_ERR_STATE, "another rank of the sharded solve failed before the first collective");
+  return CTVIO_OK;
+}
+
+// sharded mode: the landmark prologue (hh, lis, lc) and the per-landmark Schur terms are formed from rank-local sums, so
+// all observations of one landmark must live on ONE rank.  Checked once per structure change with one all-reduce of the
+// per-landmark owner counts.
+int shard_check_ownership(ctvio_engine* e) {
+  if (e->world <= 1 || e->shard_checked) return CTVIO_OK;
+  cudaStream_t st = e->stream;
+  std::vector<double> owned(size_t(std::max(e->nL, 1)), 0.0);
+  for (const HostImage& o : e->img) owned[o.lm] = 1.0;
+  CUDA_OK(e->d_rho_sync.reserve(2 * size_t(std::max(e->nL, 1))));
+  CUDA_OK(cudaMemcpyAsync(e->d_rho_sync.p, owned.data(), owned.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  std::string err;
+  if (!ctvio::comm_allreduce_sum(e->nccl_comm, e->d_rho_sync.p, owned.size(), st, &err)) return fail(CTVIO_ERR_NCCL, err);
+  CUDA_OK(cudaMemcpyAsync(owned.data(), e->d_rho_sync.p, owned.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  for (int l = 0; l < e->nL; ++l)
+    if (owned[l] > 1.0)
+      return fail(CTVIO_ERR_INVALID, "sharded solve: landmark " + std::to_string(l) + " has observations on " +
+                                         std::to_string(int(owned[l])) + " ranks (shard image factors by landmark)");
+  e->shard_checked = true;
   return CTVIO_OK;
 }
 
@@ -675,6 +721,9 @@ int ctvio_abi_version(void) { return CTVIO_ABI_VERSION; }
 int ctvio_create(const ctvio_config* cfg, ctvio_handle* out) {
   if (!cfg || !out) return fail(CTVIO_ERR_INVALID, "null argument");
   if (cfg->dt_ns <= 0) return fail(CTVIO_ERR_INVALID, "dt_ns must be positive");
+  if (cfg->rs_padding_ns < 0 || cfg->rs_padding_ns > cfg->dt_ns)
+    return fail(CTVIO_ERR_INVALID, "rs_padding_ns must lie in [0, dt_ns]: the staged knot window holds 5 knots "
+                                   "(4 + one interval of rolling-shutter padding, se3_spline.h:463-503 with 39 ms / 50 ms)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(CTVIO_ERR_NO_DEVICE, "no CUDA device visible: the ctvio engine has no CPU fallback");
@@ -886,6 +935,21 @@ int ctvio_set_prior(ctvio_handle e, int32_t n, const double* J, const double* r,
   e->masks_dirty = true;  // the prior's blocks count as touched parameters
   if (n <= 0) return CTVIO_OK;
   if (!J || !r || nb <= 0 || !type || !index || !col || !x0) return fail(CTVIO_ERR_INVALID, "null argument");
+  {
+    // the blocks must tile the n columns exactly: col[b] + c indexes host tables and device scratch (dx, col2g)
+    std::vector<uint8_t> covered(size_t(n), 0);
+    for (int b = 0; b < nb; ++b) {
+      if (type[b] < CTVIO_BLK_ROT || type[b] > CTVIO_BLK_RHO) return fail(CTVIO_ERR_INVALID, "prior block type out of range");
+      const int ls = (type[b] == CTVIO_BLK_LD || type[b] == CTVIO_BLK_RHO) ? 1 : 3;
+      if (col[b] < 0 || col[b] + ls > n) return fail(CTVIO_ERR_INVALID, "prior block column outside [0, n)");
+      for (int c = 0; c < ls; ++c) {
+        if (covered[col[b] + c]) return fail(CTVIO_ERR_INVALID, "prior blocks overlap");
+        covered[col[b] + c] = 1;
+      }
+    }
+    for (int c = 0; c < n; ++c)
+      if (!covered[c]) return fail(CTVIO_ERR_INVALID, "prior blocks do not cover all n columns");
+  }
   e->prior.n = n;
   e->prior.J.assign(J, J + size_t(n) * n);
   e->prior.r.assign(r, r + n);
@@ -901,7 +965,10 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
   if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
   cudaSetDevice(e->cfg.device);
   int rc = prepare(e);
+  rc = shard_consensus(e, rc);  // every rank leaves here together, or none enters the collectives below
   if (rc) return rc;
+  rc = shard_check_ownership(e);
+  if (rc) return rc;  // the all-reduced counts are identical on every rank: all of them return
   cudaStream_t st = e->stream;
   const ProblemDims d = e->dims();
   // Ceres 1.14 Solver::Options defaults
@@ -1291,6 +1358,44 @@ int ctvio_query_trajectory(ctvio_handle e, int32_t n, const int64_t* t, double* 
   return CTVIO_OK;
 }
 
+int ctvio_triangulate(ctvio_handle e, int32_t n_frames, const double* Rs, const double* Ps, const double* ric,
+                      const double* tic, int32_t nl, const int32_t* start_frame, const int32_t* obs_offset,
+                      const double* obs_point, int32_t window_size, double init_depth, double* depth) {
+  if (!e || n_frames <= 0 || !Rs || !Ps || !ric || !tic || nl < 0 || (nl > 0 && (!start_frame || !obs_offset || !obs_point || !depth)))
+    return fail(CTVIO_ERR_INVALID, "bad argument");
+  if (nl == 0) return CTVIO_OK;
+  cudaSetDevice(e->cfg.device);
+  const int total = obs_offset[nl];
+  if (total < 0) return fail(CTVIO_ERR_INVALID, "obs_offset must be non-decreasing");
+  for (int l = 0; l < nl; ++l)
+    if (obs_offset[l + 1] < obs_offset[l]) return fail(CTVIO_ERR_INVALID, "obs_offset must be non-decreasing");
+  cudaStream_t st = e->stream;
+  // one staging buffer: [Rs | Ps | obs points | depth] doubles, [start | offsets] ints
+  const size_t nd = 12 * size_t(n_frames) + 3 * size_t(total) + size_t(nl);
+  CUDA_OK(e->d_tmp.reserve(nd));
+  CUDA_OK(e->d_tri_idx.reserve(2 * size_t(nl) + 1));
+  double* dRs = e->d_tmp.p;
+  double* dPs = dRs + 9 * size_t(n_frames);
+  double* dobs = dPs + 3 * size_t(n_frames);
+  double* ddepth = dobs + 3 * size_t(total);
+  CUDA_OK(cudaMemcpyAsync(dRs, Rs, 9 * size_t(n_frames) * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dPs, Ps, 3 * size_t(n_frames) * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (total) CUDA_OK(cudaMemcpyAsync(dobs, obs_point, 3 * size_t(total) * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(ddepth, depth, size_t(nl) * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->d_tri_idx.p, start_frame, size_t(nl) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->d_tri_idx.p + nl, obs_offset, (size_t(nl) + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  ctvio::TriangulateArgs a;
+  a.n_frames = n_frames; a.Rs = dRs; a.Ps = dPs;
+  for (int k = 0; k < 9; ++k) a.ric.m[k] = ric[k];
+  a.tic = V3{tic[0], tic[1], tic[2]};
+  a.n_landmarks = nl; a.start_frame = e->d_tri_idx.p; a.obs_offset = e->d_tri_idx.p + nl; a.obs_point = dobs;
+  a.window_size = window_size; a.init_depth = init_depth; a.depth = ddepth;
+  e->launches += ctvio::launch_triangulate(a, st);
+  CUDA_OK(cudaMemcpyAsync(depth, ddepth, size_t(nl) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return CTVIO_OK;
+}
+
 int ctvio_profile_kernels(ctvio_handle e, int32_t reps, int32_t flush_l2, double* out) {
   if (!e || !out || reps <= 0) return fail(CTVIO_ERR_INVALID, "bad argument");
   cudaSetDevice(e->cfg.device);
@@ -1664,6 +1769,7 @@ int ctvio_comm_init(ctvio_handle e, int32_t rank, int32_t world, const uint8_t* 
   e->nccl_comm = comm;
   e->rank = rank;
   e->world = world;
+  e->shard_checked = false;
   return CTVIO_OK;
 }
 

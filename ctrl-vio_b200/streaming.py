@@ -1,15 +1,20 @@
 """BASELINE config 5: streaming sliding window over a long synthetic sequence.
 
-Mirrors the reference's per-image cycle (TrajectoryManager::UpdateTrajectory -> double2vector re-alignment ->
-UpdatePrior, src/estimator/trajectory_manager.cpp:130-516) through the public Estimator API: every window
-  1. moves the time origin to the first control point the window touches and uploads the window's slice of control
-     points, bias nodes, inverse depths (carried over from the previous window's solution; new ones from the tracker /
-     initial guess),
-  2. re-adds the window's image / IMU / bias factors (oldest keyframe flagged for marginalization) and the prior,
-  3. solves, re-aligns the 4-DoF gauge, marginalizes the oldest keyframe into the next prior,
-  4. reads the state back.
-The host-side slicing of the synthetic sequence (the "feature tracker") is not part of the timed region; everything
-that crosses the C-ABI is.  Used by tests (GPU vs oracle over a few windows) and by bench.py ("c5").
+Mirrors the reference's per-image cycle (odometry_manager.cpp:253-281) through the public Estimator API:
+
+  1. ExtendTrajectory(t_img + 40 ms)   trajectory_manager.cpp:108-120: new control points = copies of the last one
+  2. InitTrajectory                     :288-315: IMU-only predictor over [max_bef_ns, maxTime), control points
+                                        <= max_bef_idx fixed, biases locked, Solve(8)   (skipped for the first window)
+  3. UpdateTrajectory(..., 15)          :317-483: prior + image + IMU + bias factors, Solve(15),
+     double2vector                      :485-516: 4-DoF re-alignment to the pre-solve pose of the first control point
+  4. UpdateVIOPrior(marg_flag)          :122-286: MARGIN_OLD marginalizes the oldest keyframe (its control points,
+                                        bias node 0, the landmarks anchored in it) into the next prior;
+                                        MARGIN_SECOND_NEW keeps the prior untouched
+  5. SlideWindow                        drop the oldest / the second-newest frame
+
+The host-side slicing of the synthetic sequence (the "feature tracker / feature manager") is not part of the timed
+region; everything that crosses the C-ABI is.  The same class drives the CUDA engine and (tests / bench CPU leg) the
+oracle.  Used by tests (GPU vs oracle over a few windows) and by bench.py ("c5").
 """
 from __future__ import annotations
 
@@ -18,115 +23,222 @@ import time
 import numpy as np
 
 from . import synthetic as syn
-from .binding import BLK_BA, BLK_BG, BLK_POS, BLK_RHO, BLK_ROT, Estimator, PriorData
+from .binding import BLK_BA, BLK_BG, BLK_LD, BLK_POS, BLK_RHO, BLK_ROT, Estimator, PriorData
 
-KF_DT_NS = 50_000_000  # 20 Hz keyframes
-WIN_KF = 11            # keyframes per window (WINDOW_SIZE 10 + the newest one)
+KF_DT_NS = 50_000_000       # 20 Hz keyframes
+WINDOW_SIZE = 10            # visual_odometry/parameters.h:8
+WIN_KF = WINDOW_SIZE + 1    # keyframes per window
+EXTEND_NS = 40_000_000      # odometry_manager.cpp:246, 251
+# keyframe phase inside a knot interval: (offset + 40 ms) mod 50 ms > 40 ms, so that the spline's end before the
+# extension lies BEFORE the new image and InitTrajectory has IMU samples to work with (with 20 Hz images and 50 ms
+# knots any other phase leaves the predictor without data)
+C5_KF_OFFSET_NS = 7_000_000
+MARGIN_OLD, MARGIN_SECOND_NEW = 0, 1
 
 
 def config_c5_sequence(n_windows: int, seed=syn.SEED0 + 5, anchors=30, track_len=10):
     """n_windows + 10 keyframes at 20 Hz, `anchors` new landmarks per keyframe tracked over the next 10 keyframes,
     free line delay (online calibration)."""
     n_kf = n_windows + WIN_KF - 1
-    kf = syn.KF_OFFSET_NS + np.arange(n_kf, dtype=np.int64) * KF_DT_NS
+    kf = C5_KF_OFFSET_NS + np.arange(n_kf, dtype=np.int64) * KF_DT_NS
     n_knots = int((kf[-1] + 200_000_000) // syn.DT_NS) + 4
     per_frame = [anchors] * (n_kf - 1) + [0]
     return syn.make_window("C5-seq", n_knots, kf, per_frame, track_len, seed=seed, fix_ld=False)
 
 
 class StreamingRunner:
-    def __init__(self, lib, seq: "syn.Window", iters=8, device=0):
+    """One estimator engine driven through the reference's per-image cycle.
+
+    perm_seed: shuffle the order in which factors are handed to the estimator (the summation order of the CPU
+    oracle) -- used by the sensitivity tests; the window problem is mathematically unchanged.
+    second_new_every: every N-th frame is treated as a non-keyframe: when it is the second-newest frame of the window
+    the step takes the MARGIN_SECOND_NEW branch (no marginalization, the frame is dropped instead of the oldest).
+    """
+
+    def __init__(self, lib, seq: "syn.Window", iters=15, init_iters=8, device=0, second_new_every=0, perm_seed=None,
+                 predictor=True):
         from . import make_config, make_options
-        self.lib, self.seq, self.iters = lib, seq, iters
-        self.q = seq.q0.copy(); self.p = seq.p0.copy()          # global control points (solution so far / initial guess)
-        self.bias = seq.bias0.copy()                             # per keyframe
-        self.rho = seq.rho0.copy()                               # per landmark (global ids)
-        self.ld = seq.ld0
-        self.prior = None
-        self.prev_ks = None
-        self.prev_lm_global = None
-        cfg = make_config(device=device, **seq.config_kwargs())
+        self.lib, self.seq, self.iters, self.init_iters = lib, seq, iters, init_iters
+        self.predictor = predictor
+        self.second_new_every = second_new_every
+        self.rng = None if perm_seed is None else np.random.default_rng(perm_seed)
+        s = seq
+        self.frames = list(range(WIN_KF))                       # source keyframe ids in the window
+        self.next_frame = WIN_KF
+        # the spline so far: control points 0 .. ncp-1 (the initializer's output covers the first window)
+        self.ncp = self._cp_needed(int(s.kf_times[WIN_KF - 1]) + EXTEND_NS)
+        self.q = s.q0.copy(); self.p = s.p0.copy()
+        self.bias = s.bias0.copy()                              # per source keyframe
+        self.rho = s.rho0.copy()                                # per landmark (source ids)
+        self.ld = s.ld0
+        self.prior = None                                       # PriorData with GLOBAL knot / SOURCE frame / landmark ids
+        cfg = make_config(device=device, **s.config_kwargs())
         self.est = Estimator(lib, cfg)
         self._make_options = make_options
         self.records = []
+        self.step_index = 0
 
-    def _layout(self, k):
+    # -- spline bookkeeping ------------------------------------------------------------------------
+    def _cp_needed(self, t_ns):
+        """smallest control-point count with maxTimeNs() >= t_ns (se3_spline.h:201-207)."""
         s = self.seq
-        kf = s.kf_times[k:k + WIN_KF]
-        idx = lambda t: int((t - s.t0_ns) // s.dt_ns)
-        ks = max(0, idx(kf[0] - s.rs_padding_ns))
-        last = idx(kf[-1] + 80_000_000) + 4
-        return kf, ks, min(last, s.n_knots) - ks, idx(kf[0]) - ks, idx(kf[1]) - ks
+        n = 4
+        while s.t0_ns + (n - 3) * s.dt_ns < t_ns:
+            n += 1
+        return n
 
-    def step(self, k):
-        s = self.seq
-        kf, ks, nloc, nowk, later = self._layout(k)
-        # ---- host-side "tracker": slice the sequence (not timed) ----
-        w = syn.subwindow(s, k, k + WIN_KF - 1, imu_max_ns=int(kf[-1]))
-        lm_global = w.meta["lm_global"]
-        img_marg = (w.anchor_frame[w.lm] == 0).astype(np.int32)
-        imu_marg = (w.imu_t < kf[1]).astype(np.int32)
-        bias_marg = np.zeros(len(w.bf_i), np.int32); bias_marg[0] = 1
-        q = np.ascontiguousarray(self.q[ks:ks + nloc]); p = np.ascontiguousarray(self.p[ks:ks + nloc])
-        b = np.ascontiguousarray(self.bias[k:k + WIN_KF])
-        rho = np.ascontiguousarray(self.rho[lm_global])
-        prior = self._shift_prior(ks, lm_global)
-        R0 = syn.qrot(q[nowk][None], np.eye(3)).T.copy(); t0 = p[nowk].copy()
-        e = self.est
-        # ---- timed region: everything that crosses the C-ABI ----
-        t_start = time.perf_counter()
-        e.SetTimeOrigin(s.t0_ns + ks * s.dt_ns)
-        e.SetOptions(self._make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER, is_marg_state=True,
-                                        ctrl_to_be_opt_now=nowk, ctrl_to_be_opt_later=later))
-        e.SetKnots(q, p); e.SetBiases(b); e.SetInvDepths(rho); e.SetLineDelay(self.ld)
-        e.ClearFactors()
-        e.AddImageFeatureDelayAnalytic(w.ti, w.rowi, w.pi, w.tj, w.rowj, w.pj, w.lm, img_marg)
-        e.AddIMUMeasurementAnalytic(w.imu_t, w.imu_gyro, w.imu_accel, w.imu_node, imu_marg)
-        e.AddBiasFactor(w.bf_i, w.bf_j, w.bf_sqrt_info, bias_marg)
-        e.AddMarginalizationFactor(prior)
-        summ = e.Solve(self.iters)
-        e.GaugeRealign(nowk, R0, t0)
-        new_prior = e.SaveMarginalizationInfo()
-        qs, ps = e.GetKnots(); bs = e.GetBiases(); rs = e.GetInvDepths(); ld = e.GetLineDelay()
-        ms = 1e3 * (time.perf_counter() - t_start)
-        # ---- carry the solution over ----
-        # control points beyond the support of the newest IMU sample are only touched by a few high-row features with
-        # basis weights < 1e-2: they are not carried over, the front end re-initialises them (here: the generator's
-        # initial guess, standing in for the reference's IMU-propagated InitTrajectory / extendKnotsTo)
-        keep = int((kf[-1] - s.t0_ns) // s.dt_ns) - ks + 3
-        self.q[ks:ks + keep] = qs[:keep]; self.p[ks:ks + keep] = ps[:keep]
-        self.bias[k:k + WIN_KF] = bs
-        if k + WIN_KF < len(self.bias):
-            self.bias[k + WIN_KF] = bs[-1]          # the next keyframe's bias node starts from the newest estimate
-        self.rho[lm_global] = rs
-        self.ld = ld
-        self.prior, self.prev_ks, self.prev_lm_global = new_prior, ks, lm_global
-        rec = dict(window=k, ms=ms, iterations=summ.iterations, final_cost=summ.final_cost, n_obs=w.n_obs,
-                   n_knots=nloc, device_ms=summ.device_ms, prior_dim=0 if new_prior is None else new_prior.n)
-        self.records.append(rec)
-        return rec
+    def _knot_of(self, t_ns):
+        return int((t_ns - self.seq.t0_ns) // self.seq.dt_ns)
 
-    def _shift_prior(self, ks, lm_global):
-        """Block indices of the prior are relative to the window that produced it: re-index them for this window."""
+    def _perm(self, n):
+        return np.arange(n) if self.rng is None else self.rng.permutation(n)
+
+    # -- prior re-indexing (index identity <-> window-relative indices) -----------------------------
+    def _prior_to_window(self, ks, frames, lm_global):
         pr = self.prior
         if pr is None:
             return None
         out = PriorData(n=pr.n, J=pr.J, r=pr.r, blk_type=pr.blk_type.copy(), blk_index=pr.blk_index.copy(),
                         blk_col=pr.blk_col.copy(), blk_x0=pr.blk_x0)
         knots = (out.blk_type == BLK_ROT) | (out.blk_type == BLK_POS)
-        out.blk_index[knots] -= ks - self.prev_ks
+        out.blk_index[knots] -= ks
         biases = (out.blk_type == BLK_BG) | (out.blk_type == BLK_BA)
-        out.blk_index[biases] -= 1
+        if biases.any():
+            pos = np.searchsorted(frames, out.blk_index[biases])
+            assert np.all(np.asarray(frames)[np.clip(pos, 0, len(frames) - 1)] == out.blk_index[biases]), \
+                "a bias node of the prior left the window"
+            out.blk_index[biases] = pos
         isrho = out.blk_type == BLK_RHO
         if isrho.any():
-            g = self.prev_lm_global[out.blk_index[isrho]]
-            pos = np.searchsorted(lm_global, g)
-            assert np.all(lm_global[np.clip(pos, 0, len(lm_global) - 1)] == g), "a landmark of the prior left the window"
+            pos = np.searchsorted(lm_global, out.blk_index[isrho])
+            assert np.all(lm_global[np.clip(pos, 0, len(lm_global) - 1)] == out.blk_index[isrho])
             out.blk_index[isrho] = pos
         assert out.blk_index.min() >= 0
         return out
 
+    def _prior_to_global(self, pr, ks, frames, lm_global):
+        if pr is None:
+            return None
+        knots = (pr.blk_type == BLK_ROT) | (pr.blk_type == BLK_POS)
+        pr.blk_index[knots] += ks
+        biases = (pr.blk_type == BLK_BG) | (pr.blk_type == BLK_BA)
+        pr.blk_index[biases] = np.asarray(frames)[pr.blk_index[biases]]
+        isrho = pr.blk_type == BLK_RHO
+        pr.blk_index[isrho] = lm_global[pr.blk_index[isrho]]
+        return pr
+
+    # -- one image ------------------------------------------------------------------------------------
+    def step(self, k=None):
+        s = self.seq
+        first = self.step_index == 0
+        t_wall = 0.0
+        e = self.est
+        max_bef_ns = max_bef_idx = None
+        if not first:
+            # the new image joins the window (AddImageToWindow), then ExtendTrajectory
+            self.frames.append(self.next_frame)
+            self.bias[self.next_frame] = self.bias[self.frames[-2]]   # Bgs_[WINDOW_SIZE] starts from the newest estimate
+            self.next_frame += 1
+            t_img = int(s.kf_times[self.frames[-1]])
+            max_bef_ns = s.t0_ns + (self.ncp - 3) * s.dt_ns
+            max_bef_idx = self.ncp - 1
+            ncp_new = self._cp_needed(t_img + EXTEND_NS)
+            self.q[self.ncp:ncp_new] = self.q[self.ncp - 1]
+            self.p[self.ncp:ncp_new] = self.p[self.ncp - 1]
+            self.ncp = ncp_new
+        frames = np.asarray(self.frames, np.int64)
+        kf = s.kf_times[frames]
+        t_newest = int(kf[-1])
+        max_t = s.t0_ns + (self.ncp - 3) * s.dt_ns
+        ks = self._knot_of(int(kf[0]))                # min_idx of UpdateTrajectory = first control point of the window
+        nloc = self.ncp - ks
+        nowk, later = 0, self._knot_of(int(kf[1])) - ks
+        marg_flag = MARGIN_OLD
+        if self.second_new_every and (self.frames[-2] % self.second_new_every) == self.second_new_every - 1:
+            marg_flag = MARGIN_SECOND_NEW
+
+        # ---- host-side "tracker / feature manager": slice the sequence (not timed) ----
+        w = syn.subwindow_frames(s, frames, imu_max_ns=min(max_t, t_newest + 1), window_size=WINDOW_SIZE)
+        lm_global = w.meta["lm_global"]
+        rho = np.ascontiguousarray(self.rho[lm_global])
+        img_marg = ((w.anchor_frame[w.lm] == 0) & (rho[w.lm] > 0)).astype(np.int32)   # :216-218
+        imu_marg = (w.imu_t < kf[1]).astype(np.int32)                                  # :243-253
+        bias_marg = np.zeros(len(w.bf_i), np.int32); bias_marg[0] = 1                 # :256-263
+        if marg_flag != MARGIN_OLD:
+            img_marg[:] = 0; imu_marg[:] = 0; bias_marg[:] = 0
+        pi_, pm = self._perm(w.n_obs), self._perm(len(w.imu_t))
+        q = np.ascontiguousarray(self.q[ks:self.ncp]); p = np.ascontiguousarray(self.p[ks:self.ncp])
+        b = np.ascontiguousarray(self.bias[frames])
+        prior = self._prior_to_window(ks, self.frames, lm_global)
+        init_sel = None
+        if not first and self.predictor:
+            init_sel = np.nonzero((w.imu_t >= max_bef_ns) & (w.imu_t < max_t))[0]
+        h2d = 0
+
+        # ---- timed region: everything that crosses the C-ABI ----
+        t_start = time.perf_counter()
+        e.SetTimeOrigin(s.t0_ns + ks * s.dt_ns)
+        e.SetKnots(q, p); e.SetBiases(b); e.SetInvDepths(rho); e.SetLineDelay(self.ld)
+        h2d += q.nbytes + p.nbytes + b.nbytes + rho.nbytes + 8
+        init_summary = None
+        if init_sel is not None and len(init_sel) > 0:
+            # InitTrajectory: IMU only, new control points only, biases locked at the newest keyframe's estimate
+            e.SetOptions(self._make_options(fixed_knot_index=max_bef_idx - ks, lock_wb=True, lock_ab=True, fix_ld=True))
+            e.ClearFactors()
+            e.AddMarginalizationFactor(None)
+            node = np.full(len(init_sel), len(frames) - 1, np.int32)
+            e.AddIMUMeasurementAnalytic(w.imu_t[init_sel], w.imu_gyro[init_sel], w.imu_accel[init_sel], node)
+            h2d += len(init_sel) * 64
+            init_summary = e.Solve(self.init_iters)
+        # UpdateTrajectory
+        e.SetOptions(self._make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER,
+                                        is_marg_state=(marg_flag == MARGIN_OLD), ctrl_to_be_opt_now=nowk,
+                                        ctrl_to_be_opt_later=later))
+        e.ClearFactors()
+        e.AddMarginalizationFactor(prior)
+        e.AddImageFeatureDelayAnalytic(w.ti[pi_], w.rowi[pi_], w.pi[pi_], w.tj[pi_], w.rowj[pi_], w.pj[pi_], w.lm[pi_],
+                                       img_marg[pi_])
+        e.AddIMUMeasurementAnalytic(w.imu_t[pm], w.imu_gyro[pm], w.imu_accel[pm], w.imu_node[pm], imu_marg[pm])
+        e.AddBiasFactor(w.bf_i, w.bf_j, w.bf_sqrt_info, bias_marg)
+        h2d += w.n_obs * 64 + len(w.imu_t) * 64 + len(w.bf_i) * 56 + (0 if prior is None else prior.n * prior.n * 8)
+        # pre-solve pose of the window's first control point (R0, t0 of UpdateTrajectory:329-331) -- AFTER InitTrajectory
+        q_pre, p_pre = (q[nowk], p[nowk])
+        R0 = syn.qrot(q_pre[None], np.eye(3)).T.copy(); t0 = p_pre.copy()
+        summ = e.Solve(self.iters)
+        e.GaugeRealign(nowk, R0, t0)
+        new_prior = e.SaveMarginalizationInfo() if marg_flag == MARGIN_OLD else None
+        qs, ps = e.GetKnots(); bs = e.GetBiases(); rs = e.GetInvDepths(); ld = e.GetLineDelay()
+        t_wall = time.perf_counter() - t_start
+        d2h = qs.nbytes + ps.nbytes + bs.nbytes + rs.nbytes + 8 + (0 if new_prior is None else new_prior.J.nbytes)
+
+        # ---- carry the solution over (the reference updates the parameter blocks in place) ----
+        self.q[ks:self.ncp] = qs; self.p[ks:self.ncp] = ps
+        self.bias[frames] = bs
+        self.rho[lm_global] = rs
+        self.ld = ld
+        if marg_flag == MARGIN_OLD:
+            self.prior = self._prior_to_global(new_prior, ks, self.frames, lm_global)
+            self.frames.pop(0)                      # slideWindowOld
+        else:
+            self.frames.pop(-2)                     # slideWindowNew: the prior stays as it is
+        rec = dict(window=self.step_index, ms=1e3 * t_wall, iterations=summ.iterations, final_cost=summ.final_cost,
+                   initial_cost=summ.initial_cost, termination=summ.termination, n_obs=w.n_obs, n_imu=len(w.imu_t),
+                   n_knots=nloc, n_lm=len(lm_global), device_ms=summ.device_ms, marg_flag=marg_flag,
+                   init_iterations=None if init_summary is None else init_summary.iterations,
+                   init_n_imu=0 if init_sel is None else len(init_sel),
+                   init_device_ms=0.0 if init_summary is None else init_summary.device_ms,
+                   prior_dim=0 if self.prior is None else self.prior.n, h2d_bytes=h2d, d2h_bytes=d2h)
+        self.records.append(rec)
+        self.step_index += 1
+        return rec
+
     def run(self, n_windows, first=0):
-        for k in range(first, first + n_windows):
-            self.step(k)
+        for _ in range(n_windows):
+            self.step()
         return self.records
+
+    def state_error(self):
+        """RMS translation error of the optimised part of the spline against the generator's truth (sanity metric)."""
+        s = self.seq
+        ks = self._knot_of(int(s.kf_times[self.frames[0]]))
+        return float(np.sqrt(np.mean(np.sum((self.p[ks:self.ncp - 2] - s.p_gt[ks:self.ncp - 2]) ** 2, axis=1))))

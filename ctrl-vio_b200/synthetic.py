@@ -325,19 +325,7 @@ def make_window(name: str, n_knots: int, kf_times_ns, anchors_per_frame, track_l
         # bias random-walk weights (trajectory_manager.cpp:420-450): cov = sum dt_k^2 sigma^2
         bf_i = np.arange(n_kf - 1, dtype=np.int32)
         bf_j = bf_i + 1
-        si = np.zeros((n_kf - 1, 6))
-        for i in range(n_kf - 1):
-            cov_g = cov_a = 0.0
-            for idx in range(1, len(imu_t)):
-                if imu_t[idx - 1] < kf[i]:
-                    continue
-                if imu_t[idx] >= kf[i + 1]:
-                    break
-                dts = (imu_t[idx] - imu_t[idx - 1]) * 1e-9
-                cov_g += dts * dts * SIGMA_BG ** 2
-                cov_a += dts * dts * SIGMA_BA ** 2
-            si[i, :3] = 1.0 / np.sqrt(cov_g)
-            si[i, 3:] = 1.0 / np.sqrt(cov_a)
+        si = bias_sqrt_info(imu_t, kf)
         n_nodes = n_kf
     else:
         imu_t = np.zeros(0, np.int64); gyro = np.zeros((0, 3)); accel = np.zeros((0, 3)); node = np.zeros(0, np.int32)
@@ -357,6 +345,25 @@ def make_window(name: str, n_knots: int, kf_times_ns, anchors_per_frame, track_l
                   kf_times=kf, ti=ti, rowi=rowi, pi=pi, tj=tj, rowj=rowj, pj=pj, lm=lm, anchor_frame=anchor_frame,
                   obs_frame=obs_frame, imu_t=imu_t, imu_gyro=gyro, imu_accel=accel, imu_node=node, bf_i=bf_i,
                   bf_j=bf_j, bf_sqrt_info=si, meta=dict(seed=seed))
+
+
+def bias_sqrt_info(imu_t, kf):
+    """Bias random-walk weights between consecutive keyframes (trajectory_manager.cpp:420-450):
+    cov = sum dt_k^2 sigma^2 over the IMU intervals [t_{k-1}, t_k] with t_{k-1} >= kf_i and t_k < kf_{i+1}."""
+    kf = np.asarray(kf, np.int64)
+    si = np.zeros((max(len(kf) - 1, 0), 6))
+    if len(imu_t) < 2:
+        return si
+    dts = np.diff(imu_t) * 1e-9
+    csum = np.concatenate([[0.0], np.cumsum(dts * dts)])      # csum[m] = sum of the first m intervals
+    for i in range(len(kf) - 1):
+        a = np.searchsorted(imu_t, kf[i], side="left")         # first sample >= kf_i  -> interval index a (ends at a+1)
+        b = np.searchsorted(imu_t, kf[i + 1], side="left")     # first sample >= kf_{i+1}: intervals ending before it
+        s2 = csum[max(b - 1, a)] - csum[a] if b - 1 > a else 0.0
+        if s2 > 0:
+            si[i, :3] = 1.0 / np.sqrt(s2 * SIGMA_BG ** 2)
+            si[i, 3:] = 1.0 / np.sqrt(s2 * SIGMA_BA ** 2)
+    return si
 
 
 SEED0 = 0xC7A1
@@ -428,4 +435,49 @@ def subwindow(w: Window, kf_first: int, kf_last: int, imu_min_ns=None, imu_max_n
     out.bf_j = out.bf_i + 1
     out.bf_sqrt_info = w.bf_sqrt_info[kf_first:kf_last]
     out.meta = dict(w.meta, lm_global=np.nonzero(keep_lm)[0], kf_first=kf_first)
+    return out
+
+
+def subwindow_frames(w: Window, frames, imu_min_ns=None, imu_max_ns=None, window_size=None) -> Window:
+    """Restrict a sequence to an arbitrary ascending list of keyframes (the window after MARGIN_SECOND_NEW slides is
+    not contiguous in the source sequence).  Landmarks keep their anchor; landmarks anchored in a frame outside the
+    list disappear with all their observations.  window_size: apply FeatureManager::isLandmarkCandidate
+    (feature_manager.h:58-65: used_num >= 2 && start_frame < WINDOW_SIZE - 2).  Bias nodes = positions in `frames`;
+    bias random-walk weights are recomputed between consecutive listed frames."""
+    import copy
+
+    frames = np.asarray(frames, np.int64)
+    n_src = len(w.kf_times)
+    pos = -np.ones(n_src, np.int64)
+    pos[frames] = np.arange(len(frames))
+    keep_lm = pos[w.anchor_frame] >= 0
+    if window_size is not None:
+        keep_lm &= pos[w.anchor_frame] < window_size - 2
+    o = keep_lm[w.lm] & (pos[w.obs_frame] >= 0)
+    cnt = np.bincount(w.lm[o], minlength=len(w.rho_gt))
+    keep_lm &= cnt > 0          # used_num = 1 + cnt >= 2
+    o &= keep_lm[w.lm]
+    new_id = -np.ones(len(w.rho_gt), np.int64)
+    new_id[keep_lm] = np.arange(keep_lm.sum())
+    kf = w.kf_times[frames]
+    opt_min = w.t0_ns + ((kf[0] - w.t0_ns) // w.dt_ns) * w.dt_ns
+    lo = opt_min if imu_min_ns is None else imu_min_ns
+    hi = (w.t0_ns + (w.n_knots - 3) * w.dt_ns) if imu_max_ns is None else imu_max_ns
+    im = (w.imu_t >= lo) & (w.imu_t < hi)
+    node = np.clip(np.searchsorted(kf, w.imu_t[im], side="right") - 1, 0, len(kf) - 1).astype(np.int32)
+    out = copy.copy(w)
+    out.name = f"{w.name}{list(frames[[0, -1]])}"
+    out.kf_times = kf
+    out.ti, out.rowi, out.pi = w.ti[o], w.rowi[o], w.pi[o]
+    out.tj, out.rowj, out.pj = w.tj[o], w.rowj[o], w.pj[o]
+    out.lm = new_id[w.lm[o]].astype(np.int32)
+    out.obs_frame = pos[w.obs_frame[o]].astype(np.int32)
+    out.anchor_frame = pos[w.anchor_frame[keep_lm]].astype(np.int32)
+    out.rho_gt, out.rho0 = w.rho_gt[keep_lm], w.rho0[keep_lm]
+    out.imu_t, out.imu_gyro, out.imu_accel, out.imu_node = w.imu_t[im], w.imu_gyro[im], w.imu_accel[im], node
+    out.bias_gt, out.bias0 = w.bias_gt[frames], w.bias0[frames]
+    out.bf_i = np.arange(len(kf) - 1, dtype=np.int32)
+    out.bf_j = out.bf_i + 1
+    out.bf_sqrt_info = bias_sqrt_info(w.imu_t, kf)
+    out.meta = dict(w.meta, lm_global=np.nonzero(keep_lm)[0], frames=frames)
     return out

@@ -210,6 +210,18 @@ int ctvio_normal_equations(ctvio_handle h, double* Hcc, double* gc, double* hl, 
 int ctvio_query_trajectory(ctvio_handle h, int32_t n, const int64_t* t, double* q_xyzw, double* p_xyz,
                            double* omega_body, double* vel_world, double* acc_world);
 
+/* ---- front-end formats either side of the path ----
+ * replaces FeatureManager::triangulate(Rs, Ps, ric, tic) (visual_odometry/feature_manager.cpp:230-275; the
+ * identity-extrinsic overload :173-223 is the same call with ric = I, tic = 0): DLT depth of every landmark candidate
+ * (used_num >= 2 && start_frame < window_size - 2) whose depth_inout entry is <= 0; observation k of landmark l is
+ * obs_point_xyz[obs_offset[l] + k] seen from frame start_frame[l] + k; depth = V(2)/V(3) of the right singular vector
+ * of the smallest singular value, replaced by init_depth (INIT_DEPTH, parameters.cpp:44) when < 0.1.
+ * Rs: [n_frames][9] row-major body rotations, Ps: [n_frames][3]. */
+int ctvio_triangulate(ctvio_handle h, int32_t n_frames, const double* Rs_rowmajor9, const double* Ps_xyz,
+                      const double* ric_rowmajor9, const double* tic_xyz, int32_t n_landmarks,
+                      const int32_t* start_frame, const int32_t* obs_offset, const double* obs_point_xyz,
+                      int32_t window_size, double init_depth, double* depth_inout);
+
 /* ---- measurement support (bench.py roofline) ----
  * Average CUDA-event duration (ms, on the engine stream) of one launch of each stage of an LM step at the
  * current state, over `reps` launches after 3 warm-up launches.  flush_l2 != 0 writes a 256 MiB scratch

@@ -9,6 +9,7 @@
 
 #include "../include/ctvio.h"
 #include "engine.hpp"
+#include "triangulate.hpp"
 
 using namespace ctvio_oracle;
 
@@ -357,6 +358,13 @@ int ctvo_query_trajectory(void* h, int32_t n, const int64_t* t, double* q, doubl
     if (vel) { Vec3 v = RdEvaluate<1>(w.grid, w.p.data(), t[k], nullptr); vel[3 * k] = v.x; vel[3 * k + 1] = v.y; vel[3 * k + 2] = v.z; }
     if (acc) { Vec3 v = RdEvaluate<2>(w.grid, w.p.data(), t[k], nullptr); acc[3 * k] = v.x; acc[3 * k + 1] = v.y; acc[3 * k + 2] = v.z; }
   }
+  return CTVIO_OK;
+}
+
+int ctvo_triangulate(void*, int32_t n_frames, const double* Rs, const double* Ps, const double* ric, const double* tic,
+                     int32_t nl, const int32_t* start_frame, const int32_t* obs_offset, const double* obs_point,
+                     int32_t window_size, double init_depth, double* depth) {
+  triangulate(n_frames, Rs, Ps, ric, tic, nl, start_frame, obs_offset, obs_point, window_size, init_depth, depth);
   return CTVIO_OK;
 }
 
