@@ -2,20 +2,24 @@
 // kernel WITHOUT grid-wide barriers.  Replaces the factor/solve half of Ceres' SPARSE_NORMAL_CHOLESKY step
 // (estimator/trajectory_estimator.cpp:374; Ceres itself is not under /root/reference) on the Schur-reduced system.
 //
-// Owner computes: every 64x64 tile (i, j), i >= j, of the lower triangle has ONE owner CTA that keeps the tile
-// in registers from the first to the last update, so the trailing matrix is never re-read or re-written in HBM:
-//   * "column" CTA j owns the diagonal tile (j, j) AND the sub-diagonal tile (j, j-1) -- the two tiles on the
-//     critical chain  factor(j-1) -> L(j,j-1) -> update of (j,j) -> factor(j)  stay on one SM;
-//   * every other tile (i, j), i >= j + 2, has its own CTA.
-// Dependencies are point-to-point flags in global memory (release/acquire, epoch valued so they never need
-// clearing): tile_ready(i,k) "L(i,k) final and written", diag_ready(j) "Linv_j and the forward-solved x_j
-// published", x_ready(r) / bwd_ready(r,k) for the backward sweep.  Owners apply the updates k = 0..j-1 in order,
-// which is a topological order of the DAG, so no CTA ever waits on work queued behind its own (all CTAs are
-// co-resident: cooperative launch).
-// The forward substitution is folded in: the owner of (i,k) publishes L(i,k) x_k, the column CTA i sums those
-// partials in a FIXED order (bit-reproducible, required by the replicated solve of the sharded mode); the
-// backward sweep reuses the tiles still resident in shared memory: owner (r,k) publishes L(r,k)^T x_r.
-// Needs  #tiles - (nb - 1) <= #SMs ; launch_factor_solve falls back to the barrier kernel (chol_coop.cu) otherwise.
+// Owner computes: every 64x64 tile (i, j), i >= j, of the lower triangle has ONE owner CTA that keeps the tile in
+// tensor-core fragments from the first to the last update, so the trailing matrix is never re-read or re-written in HBM.
+//   * diagonal CTA j: tile (j, j).  Applies the SYRK updates of the finished tiles L(j,k), factors the block 16 columns
+//     at a time (pivot chain in one warp) WITHOUT forming its 64x64 inverse, and publishes a PACKET per 16 columns
+//     (the panel below the 16x16 diagonal block + that block's 16x16 inverse, which the pivot warp's idle lanes get for free).
+//   * tile CTA (i, j), i > j: applies its GEMM updates, then runs the right-looking triangular solve against block column
+//     j IN STEP with its factorisation (one packet = 16 columns of L(i,j)); the sub-diagonal CTA (j+1, j) streams each
+//     finished 16-column slab to diagonal CTA j+1, which applies it as a rank-16 update: when the last pivot of column j
+//     is done, one 16x16 product, one slab hop and one rank-16 update separate it from the first pivot of column j+1.
+// r2 changes vs r1 (profiles/r2/README.md has the timelines): no 64x64 inverse on the chain (was ~half of the diagonal
+// factor), solve pipelined with the factorisation, the chain's GEMM work split over two SMs per column (r1: one), and
+// the chain's messages are SELF-VALIDATING WORDS (sentinel = not yet written) instead of store + fence + flag + acquire.
+// Tiles that feed later GEMM updates still use release/acquire flags in global memory (epoch valued: never cleared).
+// The forward substitution is folded in: the owner of (i,k) publishes L(i,k) x_k, the diagonal CTA i sums those
+// partials in a FIXED order (bit-reproducible, required by the replicated solve of the sharded mode); the backward
+// sweep reuses the tiles still resident in shared memory: owner (r,k) publishes L(r,k)^T x_r.
+// Needs nb (nb + 1) / 2 <= #SMs (all CTAs co-resident: cooperative launch); launch_factor_solve falls back to the
+// barrier kernel (chol_coop.cu) otherwise.
 #include <algorithm>
 
 #include "chol_tiles.cuh"
@@ -34,6 +38,23 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// ---- self-validating words: packets of the diagonal factorisations travel WITHOUT flag + fence ----
+// A packet word is either the sentinel (a negative quiet NaN with a payload no arithmetic produces) or final data; 8-byte
+// accesses are single-copy atomic, so a consumer spins on the data itself: ONE L2 round trip per hop instead of
+// store -> fence -> flag -> acquire -> load.  Two buffers alternate by the engine's launch parity; a producer resets its
+// slots of the OTHER buffer at the end of a launch (nobody reads that buffer during this launch), so the next launch
+// finds sentinels.  (A NaN in the data - non-positive pivot - is the default qNaN, never the sentinel: no deadlock.)
+constexpr unsigned long long kSentinel = 0xFFF8C0DEC0DE0001ull;
+__device__ __forceinline__ bool is_sentinel(double v) { return static_cast<unsigned long long>(__double_as_longlong(v)) == kSentinel; }
+__device__ __forceinline__ double2 ld_relaxed2(const double* p) {
+  double2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed2(double* p, double2 v) {
+  asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
 // all threads of the CTA: wait until *flag == epoch (thread 0 spins), then make the producer's data visible
 __device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
   if (threadIdx.x == 0) {
@@ -111,19 +132,22 @@ __device__ __forceinline__ void tile_matvec(const double* Lrm, const double* v, 
 struct CholDagArgs {
   double* M;          // [npad][npad], strictly-lower tiles overwritten with L(i,j)^T (transposed inside the tile slot)
   int npad;
-  double* Linv;       // [nb][64][64]  TRANSPOSED block inverses (Linv_j^T), the B operand of the panel GEMMs
+  double* Lpub;       // this launch's packet buffer [nb][4][16][80] (self-validating words, see kSentinel)
+  double* Lpub_other; // the other parity's buffer: reset to sentinels by the producers at the end of this launch
+  double* Spub;       // [nb][4][16][64] slabs P_s^T of the sub-diagonal tiles (j, j-1) for diagonal CTA j (self-validating)
+  double* Spub_other;
   const double* rhs;  // [npad]
   double* y;          // [npad] solution
   double* yf;         // [npad] forward-solved right-hand side
   double* part;       // [2][nb][nb][64] partial products of the forward / backward sweeps
-  int* flags;         // tile_ready[nb*nb] | bwd_ready[nb*nb] | diag_ready[nb] | x_ready[nb] | fwd_ready[nb]
+  int* flags;         // tile_ready[nb*nb] | bwd_ready[nb*nb] | (4 nb unused) | x_ready[nb] | fwd_ready[nb] | fwdp_ready[nb*nb]
   int epoch;
   LmScalars* scal;
 };
 
 #ifdef CTVIO_CHOL_TIMING
 __device__ unsigned long long g_dag_stamps[32 * 16];
-#define DSTAMP(j, i) do { if (threadIdx.x == 0 && (j) < 32) { unsigned long long t_; \
+#define DSTAMP(j, i) do { if (threadIdx.x == 0 && (j) >= 0 && (j) < 32) { unsigned long long t_; \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_dag_stamps[(j) * 16 + (i)] = t_; } } while (0)
 extern "C" int ctvio_debug_fac_clk(long long* out) {
   return cudaMemcpyFromSymbol(out, g_fac_clk, sizeof(g_fac_clk)) == cudaSuccess ? 0 : -1;
@@ -135,38 +159,182 @@ extern "C" int ctvio_debug_dag_stamps(unsigned long long* out) {
 #define DSTAMP(j, i)
 #endif
 
-constexpr size_t kCholDagSmem = (6 * size_t(kTile) + 8 * kCholNB) * sizeof(double);
+// shared memory: D | S1 | S2 | Pk (4 packets) | At | Bp (2 packets) | L16t | rdiag, vec, vec2, red[4][64], x16
+constexpr size_t kCholDagSmem =
+    (3 * size_t(kTile) + 4 * size_t(kPacket) + 16 * size_t(kTS) + 2 * size_t(kPacket) + 256 + 7 * kCholNB + 16) * sizeof(double);
+
+// out[r] = sum_c St[c][r] v[c]   (St = the tile TRANSPOSED, [c][r] layout: lanes run along r, conflict free).
+// 4 partial sums per output (threads r, r + 64, ...) combined in a fixed order through red[4][64].
+__device__ __forceinline__ void tile_matvec_t(const double* St, const double* v, double* out_global, double* red, int tid,
+                                              double* out_shared = nullptr) {
+  const int r = tid & 63, part = tid >> 6;
+  double s = 0.0;
+#pragma unroll 4
+  for (int c = part; c < kCholNB; c += 4) s = fma(St[c * kTS + r], v[c], s);
+  red[part * kCholNB + r] = s;
+  __syncthreads();
+  if (tid < kCholNB) {
+    const double t = (red[tid] + red[kCholNB + tid]) + (red[2 * kCholNB + tid] + red[3 * kCholNB + tid]);
+    out_global[tid] = t;
+    if (out_shared) out_shared[tid] = t;
+  }
+}
+
+// Right-looking triangular solve of the tile held in `acc` (fragments) against block column jc, consuming the packets
+// of its diagonal-block factorisation AS THEY ARE PUBLISHED (one per 16 columns):  L(i,jc) = T L_jj^-T.
+// Result: S1 = L(i,jc)^T ([c][row] layout = the operand / publication layout).  slab_out != nullptr (sub-diagonal tile):
+// every finished 16-column slab P_s^T is streamed to the diagonal CTA of row i as self-validating words.
+__device__ __forceinline__ void trsm_pipelined(Frag& acc, const Lane& L, double* S1, double* At, double* Bp2,
+                                               const double* Lpub_col, double* slab_out, int tid, int jstamp) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  // packet words of this thread: e = tid, tid + 256, tid + 512 of the 640 double2 of a full packet (16 rows x 40); the
+  // last packet only carries the 16x16 inverse (128 double2).  Loads of packet s + 1 are IN FLIGHT while step s computes.
+  int goff[3], soff[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int e = tid + 256 * u;
+    const int r = e / 40, c = (e - r * 40) * 2;
+    goff[u] = e < 640 ? r * 80 + c : -1;
+    soff[u] = r * kPS + c;
+  }
+  const int goff3 = tid < 128 ? (tid >> 3) * 80 + 64 + (tid & 7) * 2 : -1, soff3 = (tid >> 3) * kPS + 64 + (tid & 7) * 2;
+  double2 pre[3];
+  auto issue = [&](int s) {
+    const double* src = Lpub_col + size_t(s) * kPacketG;
+    if (s < 3) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+        if (goff[u] >= 0) pre[u] = ld_relaxed2(src + goff[u]);
+    } else if (goff3 >= 0) {
+      pre[0] = ld_relaxed2(src + goff3);
+    }
+  };
+  auto commit = [&](int s, double* Bp) {
+    const double* src = Lpub_col + size_t(s) * kPacketG;
+    if (s < 3) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+        if (goff[u] >= 0) {
+          while (is_sentinel(pre[u].x) || is_sentinel(pre[u].y)) pre[u] = ld_relaxed2(src + goff[u]);
+          *reinterpret_cast<double2*>(Bp + soff[u]) = pre[u];
+        }
+    } else if (goff3 >= 0) {
+      while (is_sentinel(pre[0].x) || is_sentinel(pre[0].y)) pre[0] = ld_relaxed2(src + goff3);
+      *reinterpret_cast<double2*>(Bp + soff3) = pre[0];
+    }
+  };
+  issue(0);
+#pragma unroll 1
+  for (int s = 0; s < 4; ++s) {
+    double* Bp = Bp2 + (s & 1) * kPacket;
+    // a. the 16 columns of step s (as updated so far) -> At[k][row]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int ct = L.ct[nt];
+        if ((ct >> 1) == s) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) At[(8 * (ct & 1) + 2 * q + e) * kTS + L.row(mt)] = acc.c[mt][nt][e];
+        }
+      }
+    // b. packet of step s: every thread waits for ITS words (they are their own flags), then the next packet's loads go out
+    DSTAMP(16 + jstamp, 4 * s + 0);
+    commit(s, Bp);
+    DSTAMP(16 + jstamp, 4 * s + 1);
+    if (s < 3) issue(s + 1);
+    __syncthreads();
+    DSTAMP(jstamp, 8 + s);
+    if (s == 3) DSTAMP(jstamp, 2);
+    // c. P_s = A_s X16_s'  : warp w = row fragment w, both 8-column fragments -> S1 rows 16 s .. 16 s + 15 (transposed)
+    {
+      const double* pa = At + q * kTS + 8 * warp + g;   // A[8 w + g][k0 + q]
+      const double* pb = Bp + q * kPS + 64 + g;         // B[k0 + q][n0 + g] = X16[n0 + g][k0 + q] = XT16[k0 + q][n0 + g]
+      double2 cl = make_double2(0.0, 0.0), ch = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const double av = pa[4 * kk * kTS];
+        if (kk < 2)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(cl.x), "+d"(cl.y) : "d"(av), "d"(pb[4 * kk * kPS]));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(ch.x), "+d"(ch.y) : "d"(av), "d"(pb[4 * kk * kPS + 8]));
+      }
+      double* dst = S1 + (16 * s) * kTS + 8 * warp + g;
+      dst[(2 * q) * kTS] = cl.x;
+      dst[(2 * q + 1) * kTS] = cl.y;
+      dst[(8 + 2 * q) * kTS] = ch.x;
+      dst[(8 + 2 * q + 1) * kTS] = ch.y;
+    }
+    DSTAMP(16 + jstamp, 4 * s + 2);
+    __syncthreads();
+    if (slab_out) {  // 16 x 64 doubles = 512 double2, two per thread, straight out of S1's rows 16 s ..
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = tid + 256 * u, r = e >> 5, c = (e & 31) * 2;
+        st_relaxed2(slab_out + size_t(s) * 16 * 64 + r * 64 + c, *reinterpret_cast<const double2*>(S1 + (16 * s + r) * kTS + c));
+      }
+    }
+    // d. trailing columns of the tile:  T[:, c] -= sum_k P_s[:, k] L_jj[c][16 s + k]  for c >= 16 (s + 1)
+    if (s < 3) {
+      const double* pp = S1 + (16 * s + q) * kTS + g;   // P_s^T[k0 + q][row]
+      const double* pl = Bp + q * kPS + g;              // Pt_s[k0 + q][c]
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        double av[2], bv[4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) av[mt] = -pp[4 * kk * kTS + 8 * L.rt[mt]];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bv[nt] = pl[4 * kk * kPS + 8 * L.ct[nt]];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            if ((L.ct[nt] >> 1) > s)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(acc.c[mt][nt][0]), "+d"(acc.c[mt][nt][1]) : "d"(av[mt]), "d"(bv[nt]));
+          }
+      }
+    }
+    // (Bp is double buffered and At / S1 rows are rewritten only after the next step's barrier)
+    DSTAMP(16 + jstamp, 4 * s + 3);
+  }
+}
 
 __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   extern __shared__ __align__(16) unsigned char dag_smem[];
-  double* D = reinterpret_cast<double*>(dag_smem);  // column CTA: diagonal tile (row-major) -> scratch of the factor
-  double* Xi = D + kTile;                            // column CTA: Linv_j
-  double* XiT = Xi + kTile;                          // column CTA: Linv_j^T
-  double* S1 = XiT + kTile;                          // operand A ([k][row]); later the owned final tile, transposed
-  double* S2 = S1 + kTile;                           // operand B ([k][row]) / factor scratch
-  double* Lrm = S2 + kTile;                          // the owned off-diagonal tile once final, row-major
-  double* rdiag = Lrm + kTile;                       // [64]
+  double* D = reinterpret_cast<double*>(dag_smem);  // column CTA: diagonal tile (row-major), destroyed by the factor
+  double* S1 = D + kTile;                            // operand A ([k][row]); later the owned final tile, transposed
+  double* S2 = S1 + kTile;                           // operand B ([k][row])
+  double* Pk = S2 + kTile;                           // column CTA: the four packets of its own factorisation
+  double* At = Pk + 4 * kPacket;                     // [16][kTS] current 16-column slab of the tile being solved
+  double* Bp = At + 16 * kTS;                        // [2][16][kPS] packets being consumed (double buffered)
+  double* L16t = Bp + 2 * kPacket;                   // [16][16] scratch of the pivot chain
+  double* rdiag = L16t + 256;                        // [64]
   double* vec = rdiag + kCholNB;                     // [64]
   double* vec2 = vec + kCholNB;                      // [64]
   double* red = vec2 + kCholNB;                      // [4][64]
+  double* x16 = red + 4 * kCholNB;                   // [16]
   __shared__ int s_bad;
   const int tid = threadIdx.x;
   const Lane L = lane_of(tid);
   const int npad = a.npad, nb = npad / kCholNB, epoch = a.epoch;
   int* tile_ready = a.flags;
   int* bwd_ready = a.flags + nb * nb;
-  int* diag_ready = a.flags + 2 * nb * nb;
-  int* x_ready = diag_ready + nb;
+  int* step_ready = a.flags + 2 * nb * nb;  // [nb][4]
+  int* x_ready = step_ready + 4 * nb;
   int* fwd_ready = x_ready + nb;
+  int* fwdp_ready = fwd_ready + nb;         // [nb][nb] forward partial L(i,k) x_k written
   double* fwd_part = a.part;                          // [i][k][64] = L(i,k) x_k
   double* bwd_part = a.part + size_t(nb) * nb * kCholNB;  // [k][r][64] = L(r,k)^T x_r
 
   const int cta = blockIdx.x;
   if (cta >= nb) {
-    // ======================= off-diagonal tile (i, j), i >= j + 2 =======================
+    // ======================= tile (i, j), i > j =======================
     int t = cta - nb, j = 0;
-    while (t >= nb - 2 - j) { t -= nb - 2 - j; ++j; }
-    const int i = j + 2 + t;
+    while (t >= nb - 1 - j) { t -= nb - 1 - j; ++j; }
+    const int i = j + 1 + t;
+    const bool sub = i == j + 1;  // sub-diagonal tile: feeds the diagonal CTA of row i slab by slab
     double* slot = a.M + size_t(i) * kCholNB * npad + j * kCholNB;
     Frag acc;
     frag_load_global(acc, slot, npad, L);
@@ -178,117 +346,150 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
       tile_gemm_dmma<true>(S1, S2, acc, L);
       __syncthreads();
     }
-    // L(i,j) = T * Linv_j^T
-    frag_store_t(S1, acc, L);
-    wait_flag(diag_ready + j, epoch);
-    load_tile_cg(S2, a.Linv + size_t(j) * kCholNB * kCholNB, kCholNB, tid);
-    __syncthreads();
-    frag_zero(acc);
-    tile_gemm_dmma<false, kCholNB, kGemmLowerB>(S1, S2, acc, L);
-    __syncthreads();  // everybody is done reading S1
-    frag_store(Lrm, acc, L);
-    frag_store_t(S1, acc, L);
+    // L(i,j) = T L_jj^-T, 16 columns at a time behind the factorisation of block column j
+    trsm_pipelined(acc, L, S1, At, Bp, a.Lpub + size_t(j) * 4 * kPacketG, sub ? a.Spub + size_t(i) * 4 * 16 * 64 : nullptr, tid,
+                   sub ? i : -100);
     __syncthreads();
     store_tile_global(slot, npad, S1, tid);  // published transposed
-    wait_flag(fwd_ready + j, epoch);
-    if (tid < kCholNB) vec[tid] = __ldcg(a.yf + j * kCholNB + tid);
-    __syncthreads();
-    tile_matvec(Lrm, vec, fwd_part + (size_t(i) * nb + j) * kCholNB, tid);
-    post_flag(tile_ready + i * nb + j, epoch);
-    // backward sweep: L(i,j)^T x_i
-    wait_flag(x_ready + i, epoch);
-    if (tid < kCholNB) vec[tid] = __ldcg(a.y + i * kCholNB + tid);
-    __syncthreads();
-    tile_matvec(S1, vec, bwd_part + (size_t(j) * nb + i) * kCholNB, tid);
-    post_flag(bwd_ready + i * nb + j, epoch);
+    post_flag(tile_ready + i * nb + j, epoch);  // the tile first: the updates of row i / column i wait for it
+    if (!sub) {  // (the diagonal CTA of row i holds a copy of the sub-diagonal tile and forms these two products itself)
+      wait_flag(fwd_ready + j, epoch);
+      if (tid < kCholNB) vec[tid] = __ldcg(a.yf + j * kCholNB + tid);
+      __syncthreads();
+      tile_matvec_t(S1, vec, fwd_part + (size_t(i) * nb + j) * kCholNB, red, tid);
+      post_flag(fwdp_ready + i * nb + j, epoch);
+      // backward sweep: L(i,j)^T x_i   (S1 row-major = L^T)
+      wait_flag(x_ready + i, epoch);
+      if (tid < kCholNB) vec[tid] = __ldcg(a.y + i * kCholNB + tid);
+      __syncthreads();
+      tile_matvec(S1, vec, bwd_part + (size_t(j) * nb + i) * kCholNB, tid);
+      post_flag(bwd_ready + i * nb + j, epoch);
+    } else {  // next launch of this engine: the slab slots of the other buffer must read as "not yet written"
+      double* o = a.Spub_other + size_t(i) * 4 * 16 * 64;
+      const double sv = __longlong_as_double(static_cast<long long>(kSentinel));
+      for (int e = tid; e < 4 * 16 * 64 / 2; e += 256) *reinterpret_cast<double2*>(o + 2 * e) = make_double2(sv, sv);
+    }
     return;
   }
 
-  // ======================= column CTA j: tiles (j, j) and (j, j-1) =======================
+  // ======================= diagonal CTA j: tile (j, j) =======================
   const int j = cta;
   DSTAMP(j, 0);
-  Frag accD, accS;
+  Frag accD;
   frag_load_global(accD, a.M + size_t(j) * kCholNB * npad + j * kCholNB, npad, L);
-  double* slot = a.M + size_t(j) * kCholNB * npad + (j >= 1 ? j - 1 : 0) * kCholNB;
-  if (j >= 1) frag_load_global(accS, slot, npad, L);
   for (int k = 0; k + 1 < j; ++k) {
-    wait_flags2(tile_ready + j * nb + k, tile_ready + (j - 1) * nb + k, epoch);
-    load_tile_cg(S1, a.M + size_t(j) * kCholNB * npad + k * kCholNB, npad, tid);
-    load_tile_cg(S2, a.M + size_t(j - 1) * kCholNB * npad + k * kCholNB, npad, tid);
+    wait_flag(tile_ready + j * nb + k, epoch);
+    load_tile_cg(S2, a.M + size_t(j) * kCholNB * npad + k * kCholNB, npad, tid);
     __syncthreads();
-    tile_gemm_dmma<true, kCholNB, kGemmLowerOut>(S1, S1, accD, L);
-    tile_gemm_dmma<true>(S1, S2, accS, L);
+    tile_gemm_dmma<true, kCholNB, kGemmLowerOut>(S2, S2, accD, L);
     __syncthreads();
   }
   DSTAMP(j, 1);
-  {  // right-hand side of block j for the forward substitution: the partials of the other owners (all in by now), fixed
+  {  // right-hand side of block j for the forward substitution: the partials of the other owners, fixed
     // summation order; this CTA's own partial L(j,j-1) x_{j-1} is added after the factorisation (side job below)
+    if (tid < j - 1) {
+      const int* f = fwdp_ready + j * nb + tid;
+      while (ld_acquire(f) != epoch) {}
+    }
+    __syncthreads();
     const double sp = sum_partials(fwd_part + size_t(j) * nb * kCholNB, j >= 1 ? j - 1 : 0, kCholNB, red, tid);
     if (tid < kCholNB) vec[tid] = a.rhs[j * kCholNB + tid] - sp;
   }
   if (j >= 1) {
-    // L(j,j-1) = T * Linv_{j-1}^T, then the last update of the diagonal tile
-    frag_store_t(S1, accS, L);
-    wait_flag(diag_ready + (j - 1), epoch);
-    DSTAMP(j, 2);
-    load_tile_cg(S2, a.Linv + size_t(j - 1) * kCholNB * kCholNB, kCholNB, tid);
-    __syncthreads();
-    DSTAMP(j, 8);
-    frag_zero(accS);
-    tile_gemm_dmma<false, kCholNB, kGemmLowerB>(S1, S2, accS, L);
-    __syncthreads();  // everybody is done reading S1
-    DSTAMP(j, 9);
-    frag_store(Lrm, accS, L);
-    frag_store_t(S1, accS, L);
-    __syncthreads();
-    DSTAMP(j, 10);
-    tile_gemm_dmma<true, kCholNB, kGemmLowerOut>(S1, S1, accD, L);
+    // the sub-diagonal tile arrives 16 columns at a time from CTA (j, j-1): S1 rows 16 s .. = P_s^T, accD -= P_s P_s'
+    const double* src = a.Spub + size_t(j) * 4 * 16 * 64;
+    const int r0 = tid >> 5, c0 = (tid & 31) * 2;  // thread's two double2 of a slab: rows r0, r0 + 8
+    double2 pre[2];
+    auto issue = [&](int s) {
+      pre[0] = ld_relaxed2(src + size_t(s) * 1024 + r0 * 64 + c0);
+      pre[1] = ld_relaxed2(src + size_t(s) * 1024 + (r0 + 8) * 64 + c0);
+    };
+    issue(0);
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const double* w = src + size_t(s) * 1024 + (r0 + 8 * u) * 64 + c0;
+        while (is_sentinel(pre[u].x) || is_sentinel(pre[u].y)) pre[u] = ld_relaxed2(w);
+        *reinterpret_cast<double2*>(S1 + (16 * s + r0 + 8 * u) * kTS + c0) = pre[u];
+      }
+      if (s < 3) issue(s + 1);
+      __syncthreads();
+      DSTAMP(j, 8 + s);
+      if (s == 3) DSTAMP(j, 2);
+      const double* pp = S1 + (16 * s + L.q) * kTS + L.g;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        double av[2], dv[4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) av[mt] = -pp[4 * kk * kTS + 8 * L.rt[mt]];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dv[nt] = pp[4 * kk * kTS + 8 * L.ct[nt]];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            if (L.rt[mt] >= L.ct[nt])
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(accD.c[mt][nt][0]), "+d"(accD.c[mt][nt][1]) : "d"(av[mt]), "d"(dv[nt]));
+          }
+      }
+    }
     DSTAMP(j, 3);
   }
   frag_store(D, accD, L);
   __syncthreads();
   DSTAMP(j, 4);
-  // While warp 0 runs the pivot chain of the first two 16-column steps, warps 1..7 publish L(j,j-1) (tile store, fence,
-  // flag) and form its forward partial: ~2 us that used to sit on the critical chain between two factorisations.
-  double* own = red;  // [64] L(j,j-1) x_{j-1}
+  // While warp 0 runs the pivot chains, warps 1..7 publish the packets of this factorisation and form the forward
+  // partial of the sub-diagonal tile (a copy of L(j,j-1)^T sits in S1: the four slabs).
+  double* own = red;  // [64] L(j,j-1) x_{j-1}   (red is free until the backward sweep)
+  double* gpk = a.Lpub + size_t(j) * 4 * kPacketG;
   auto side = [&](int step) {
     if (j == 0) return;
     const int tt = tid - 32;  // 0..223
-    if (step == 0) {
-      for (int e = tt; e < kCholNB * kCholNB / 2; e += 224) {
-        const int r = e >> 5, c = (e & 31) * 2;
-        *reinterpret_cast<double2*>(slot + size_t(r) * npad + c) = *reinterpret_cast<const double2*>(S1 + r * kTS + c);
-      }
-      asm volatile("bar.sync 1, 224;" ::: "memory");
-      if (tt == 0) {
-        __threadfence();
-        st_release(tile_ready + j * nb + (j - 1), epoch);
-      }
-    } else if (step == 1 && tt < kCholNB) {
-      // x_{j-1} was published (fwd_ready) a microsecond after Linv_{j-1}: long ago by now
+    if (step == 1 && tt < kCholNB) {
+      // x_{j-1} was published (fwd_ready) shortly after the last packet of column j-1: long ago by now
       if (tt == 0) { while (ld_acquire(fwd_ready + (j - 1)) != epoch) {} }
       asm volatile("bar.sync 2, 64;" ::: "memory");
       vec2[tt] = __ldcg(a.yf + (j - 1) * kCholNB + tt);
     } else if (step == 2 && tt < 128) {
+      // own[r] = sum_c L(j,j-1)[r][c] x[c] = sum_c S1[c][r] x[c]; two lanes per row
       const int r = tt >> 1, pt = tt & 1;
       double acc = 0.0;
 #pragma unroll 8
-      for (int c = pt; c < kCholNB; c += 2) acc = fma(Lrm[r * kTS + c], vec2[c], acc);
+      for (int c = pt; c < kCholNB; c += 2) acc = fma(S1[c * kTS + r], vec2[c], acc);
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       if (pt == 0) own[r] = acc;
     }
   };
-  if (!factor_and_invert_64(D, Xi, XiT, S2, rdiag, &s_bad, side) && tid == 0) a.scal->chol_fail = 1;
+  auto pub = [&](int s) {  // warps 1..7: packet s (panel + 16x16 inverse) -> global; the words validate themselves
+    const int tt = tid - 32;
+    const double* src = Pk + s * kPacket;
+    double* dst = gpk + size_t(s) * kPacketG;
+    for (int e = tt; e < 16 * 40; e += 224) {
+      const int r = e / 40, c = (e - r * 40) * 2;
+      double2 v = *reinterpret_cast<const double2*>(src + r * kPS + c);
+      if (c < 16 * (s + 1) && c < 64) v = make_double2(0.0, 0.0);  // rows of the panel above the diagonal block: unused
+      st_relaxed2(dst + r * 80 + c, v);
+    }
+  };
+  auto pub_last = [&]() {  // all threads: the last 16x16 inverse
+    if (tid < 128) {
+      const int r = tid >> 3, c = 64 + (tid & 7) * 2;
+      st_relaxed2(gpk + size_t(3) * kPacketG + r * 80 + c, *reinterpret_cast<const double2*>(Pk + 3 * kPacket + r * kPS + c));
+    }
+  };
+  if (!factor_64_pipe(D, Pk, L16t, rdiag, &s_bad, pub, pub_last, side) && tid == 0) a.scal->chol_fail = 1;
   DSTAMP(j, 5);
-  // forward substitution of block j: x_j = Linv_j (rhs_j - sum_k L(j,k) x_k)
+  // forward substitution of block j: x_j = L_jj^-1 (rhs_j - sum_k L(j,k) x_k)
   if (j >= 1 && tid < kCholNB) vec[tid] -= own[tid];
-  store_tile_global(a.Linv + size_t(j) * kCholNB * kCholNB, kCholNB, XiT, tid);  // publish Linv_j^T first: it is what
-  post_flag(diag_ready + j, epoch);                                               // the next column's chain waits for
-  DSTAMP(j, 6);
-  tile_matvec(Xi, vec, a.yf + j * kCholNB, tid, vec2);  // x_j (forward); shared copy for the backward sweep
+  __syncthreads();
+  block_solve_packets<true>(Pk, vec, x16, tid);
+  if (tid < kCholNB) { a.yf[j * kCholNB + tid] = vec[tid]; vec2[tid] = vec[tid]; }
   post_flag(fwd_ready + j, epoch);
+  DSTAMP(j, 6);
 
-  // backward sweep: x_j = Linv_j^T (yf_j - sum_{r > j} L(r,j)^T x_r)
+  // backward sweep: x_j = L_jj^-T (yf_j - sum_{r > j} L(r,j)^T x_r)
   // all partials of this block column: one polling thread per flag (the early ones cost a single L2 round trip in
   // parallel instead of nb - 1 - j sequential ones), then one barrier
   if (tid < nb - 1 - j) {
@@ -301,12 +502,12 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     if (tid < kCholNB) vec[tid] = vec2[tid] - sp;
   }
   __syncthreads();
-  tile_matvec(XiT, vec, a.y + j * kCholNB, tid, vec2);  // XiT row-major = Linv^T
+  block_solve_packets<false>(Pk, vec, x16, tid);
+  if (tid < kCholNB) a.y[j * kCholNB + tid] = vec[tid];
   if (j >= 1) {
     // own sub-diagonal tile: L(j,j-1)^T x_j for column CTA j-1, published together with x_j (one fence for both:
     // the next column of the backward chain waits for exactly this partial)
-    __syncthreads();
-    tile_matvec(S1, vec2, bwd_part + (size_t(j - 1) * nb + j) * kCholNB, tid);  // S1 = L(j,j-1)^T
+    tile_matvec(S1, vec, bwd_part + (size_t(j - 1) * nb + j) * kCholNB, tid);  // S1 row-major = L(j,j-1)^T
   }
   __syncthreads();
   if (tid == 0) {
@@ -315,10 +516,15 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     st_release(x_ready + j, epoch);
   }
   DSTAMP(j, 7);
+  {  // next launch of this engine uses the other packet buffer: leave this column's slots there as sentinels
+    double* o = a.Lpub_other + size_t(j) * 4 * kPacketG;
+    const double sv = __longlong_as_double(static_cast<long long>(kSentinel));
+    for (int e = tid; e < 4 * kPacketG / 2; e += 256) *reinterpret_cast<double2*>(o + 2 * e) = make_double2(sv, sv);
+  }
 }
 
 // number of CTAs the DAG kernel needs for nb block columns
-static int dag_grid(int nb) { return nb + (nb >= 3 ? (nb - 1) * (nb - 2) / 2 : 0); }
+static int dag_grid(int nb) { return nb * (nb + 1) / 2; }
 
 bool chol_dag_supported(int npad, int n_sm) { return dag_grid(npad / kCholNB) <= n_sm; }
 
@@ -328,7 +534,21 @@ size_t chol_dag_part_len(int npad) {
 }
 size_t chol_dag_flags_len(int npad) {
   const size_t nb = npad / kCholNB;
-  return 2 * nb * nb + 3 * nb;
+  return 3 * nb * nb + 6 * nb;
+}
+// [barrier kernel's block inverses npad x 64 | packets parity 0 | packets parity 1 | slabs parity 0 | slabs parity 1]
+static size_t dag_pub_len(int npad) { return size_t(npad / kCholNB) * 4 * (kPacketG + 16 * 64); }
+size_t chol_dag_lpub_len(int npad) { return size_t(npad) * kCholNB + 2 * dag_pub_len(npad); }
+
+__global__ void fill_sentinel_kernel(double* p, size_t n) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = __longlong_as_double(static_cast<long long>(kSentinel));
+}
+// both packet buffers start as sentinels (call once after (re)allocating the buffer, on the engine stream)
+int launch_chol_dag_init(double* linv_buf, int npad, cudaStream_t s) {
+  const size_t n = 2 * dag_pub_len(npad);
+  fill_sentinel_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(linv_buf + size_t(npad) * kCholNB, n);
+  return 1;
 }
 
 int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
@@ -336,7 +556,16 @@ int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
   static std::atomic<unsigned> epoch_src{0};
   if (once.first()) cudaFuncSetAttribute(chol_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCholDagSmem));
   CholDagArgs a;
-  a.M = l.M; a.npad = l.npad; a.Linv = l.Linv; a.rhs = l.rhs; a.y = l.y; a.yf = l.yf;
+  const size_t half = size_t(l.npad / kCholNB) * 4 * kPacketG;
+  const unsigned parity = l.chol_seq ? ((*l.chol_seq)++ & 1u) : 0u;
+  a.M = l.M; a.npad = l.npad;
+  const size_t shalf = size_t(l.npad / kCholNB) * 4 * 16 * 64;
+  double* pk = l.Linv + size_t(l.npad) * kCholNB;
+  a.Lpub = pk + parity * half;
+  a.Lpub_other = pk + (parity ^ 1u) * half;
+  a.Spub = pk + 2 * half + parity * shalf;
+  a.Spub_other = pk + 2 * half + (parity ^ 1u) * shalf;
+  a.rhs = l.rhs; a.y = l.y; a.yf = l.yf;
   a.part = l.chol_part; a.flags = l.chol_flags; a.scal = l.scal;
   // process-wide unique, never 0 (flag buffers start zeroed); a wrap after 2^31 launches would need the flags of a
   // buffer to hold exactly the value 2^31 launches old: not a practical concern

@@ -106,6 +106,7 @@ constexpr int kX16Stride = 20;  // row stride (doubles) of the 16x16 inverse blo
 // P1 of 16-column step s (c0 = 16 s): executed by ONE full warp.  Lanes 0..15 hold the rows of the diagonal block;
 // lanes 16..31 run the SAME instruction stream on the columns of the identity, i.e. lane 16 + c forward-substitutes
 // column c of X16 = L16^-1 one pivot behind the factorisation, for free (SIMT).  XT16[m][k] = X16[k][m].
+template <int XS = kX16Stride>
 __device__ __forceinline__ void factor_p1_warp(double* D, double* L16t, double* XT16, double* rdiag, int* s_bad, int c0, int lane) {
   const int r = lane & 15;
   const bool real = lane < 16;
@@ -138,7 +139,7 @@ __device__ __forceinline__ void factor_p1_warp(double* D, double* L16t, double* 
   }
   if (!real) {
 #pragma unroll
-    for (int k = 0; k < 16; k += 2) *reinterpret_cast<double2*>(XT16 + r * kX16Stride + k) = make_double2(a[k], a[k + 1]);
+    for (int k = 0; k < 16; k += 2) *reinterpret_cast<double2*>(XT16 + r * XS + k) = make_double2(a[k], a[k + 1]);
   }
   if (bad && lane == 0) *s_bad = 1;
 }
@@ -311,6 +312,186 @@ __device__ __forceinline__ bool factor_and_invert_64(double* D, double* Xi, doub
   }
   __syncthreads();
   return *s_bad == 0;
+}
+
+// ---- factor WITHOUT the 64x64 inverse, publishing per 16-column step (tile-DAG kernel, chol_dag.cu) ----
+// Packet of step s (row stride kPS, 16 rows m = column 16 s + m of the block):
+//   cols  0..63  Pt_s[m][row] = L[row][16 s + m]  for row >= 16 (s + 1)   (the panel below the 16x16 diagonal block)
+//   cols 64..79  XT16_s[m][k] = X16_s[k][m],  X16_s = (16x16 diagonal block of L)^-1
+// Everything a consumer needs for the right-looking triangular solve of ITS tile against this block column, step by
+// step:  P_s = T[:, 16 s ..] X16_s' ;  T[:, > 16 (s + 1)] -= P_s Pt_s(rows below)' .  The 64x64 inverse of r1 (P2b and
+// half of P3 of factor_and_invert_64) is gone from the serial chain, and consumers start after the FIRST 16 columns.
+constexpr int kPS = 84;                  // packet row stride in shared memory (84 = 4 mod 16: fragment loads conflict-free)
+constexpr int kPacket = 16 * kPS;        // doubles per packet in shared memory
+constexpr int kPacketG = 16 * 80;        // doubles per packet in global memory (dense rows of 80)
+
+// pub(s): called by the threads of warps 1..7 (tid >= 32) right after the panel of step s is complete (s < 3), i.e.
+//         while warp 0 runs the look-ahead + pivot chain of step s + 1;
+// pub_last(): called by ALL threads when the last pivot chain (step 3, no panel below) is done;
+// side(s): as in factor_and_invert_64.
+template <class Pub, class PubLast, class Side>
+__device__ __forceinline__ bool factor_64_pipe(double* D, double* Pk, double* L16t, double* rdiag, int* s_bad, Pub pub,
+                                               PubLast pub_last, Side side) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  if (tid == 0) *s_bad = 0;
+  __syncthreads();
+  if (warp == 0) factor_p1_warp<kPS>(D, L16t, Pk + 64, rdiag, s_bad, 0, lane);
+  else side(0);
+  __syncthreads();
+#pragma unroll 1
+  for (int s = 0; s < 3; ++s) {
+    const int c0 = 16 * s;
+    FCLK(s, 0);
+    double* Pt = Pk + s * kPacket;        // [16][kPS]: cols 0..63 panel (transposed), cols 64..79 XT16_s
+    const double* XT16 = Pt + 64;
+    {
+      // P2a: panel rows below the diagonal block, one 8-row fragment (both 8-column fragments) per warp
+      const int n_a = (48 - c0) >> 3;
+      if (warp < n_a) {
+        const int i0 = c0 + 16 + 8 * warp;
+        const double* pa = D + (i0 + g) * kTS + c0 + q;   // A[i0 + g][k0 + q]
+        const double* pb = XT16 + q * kPS + g;            // B[k0 + q][n0 + g] = X16[n0 + g][k0 + q]
+        double2 cl = make_double2(0.0, 0.0), ch = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const double av = pa[4 * kk];
+          if (kk < 2)                                      // X16 is lower triangular: k <= n
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(cl.x), "+d"(cl.y) : "d"(av), "d"(pb[4 * kk * kPS]));
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(ch.x), "+d"(ch.y) : "d"(av), "d"(pb[4 * kk * kPS + 8]));
+        }
+        Pt[(2 * q) * kPS + i0 + g] = cl.x;
+        Pt[(2 * q + 1) * kPS + i0 + g] = cl.y;
+        Pt[(8 + 2 * q) * kPS + i0 + g] = ch.x;
+        Pt[(8 + 2 * q + 1) * kPS + i0 + g] = ch.y;
+      }
+    }
+    FCLK(s, 1);
+    __syncthreads();
+    FCLK(s, 2);
+    // P3 (D(rows >= c0+16, cols >= c0+16) -= P P', lower fragments) overlapped with the pivot chain of the next step:
+    // warp 0 updates the three fragments of the next 16x16 diagonal block first and starts P1 at once; the other warps
+    // publish the packet (consumers are waiting for it), finish the update, then run the side job.
+    const int rt0 = (c0 + 16) >> 3;
+    if (warp == 0) {
+      double* cp0 = D + (8 * rt0 + g) * kTS + 8 * rt0 + 2 * q;
+      double* cp1 = cp0 + 8 * kTS;      // (rt0 + 1, rt0)
+      double* cp2 = cp1 + 8;            // (rt0 + 1, rt0 + 1)
+      double2 v0 = *reinterpret_cast<const double2*>(cp0), v1 = *reinterpret_cast<const double2*>(cp1),
+              v2 = *reinterpret_cast<const double2*>(cp2);
+      const double* pp = Pt + q * kPS + 8 * rt0 + g;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const double p0 = pp[4 * kk * kPS], p1 = pp[4 * kk * kPS + 8];
+        const double a0 = -p0, a1 = -p1;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(v0.x), "+d"(v0.y) : "d"(a0), "d"(p0));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(v1.x), "+d"(v1.y) : "d"(a1), "d"(p0));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(v2.x), "+d"(v2.y) : "d"(a1), "d"(p1));
+      }
+      *reinterpret_cast<double2*>(cp0) = v0;
+      *reinterpret_cast<double2*>(cp1) = v1;
+      *reinterpret_cast<double2*>(cp2) = v2;
+      __syncwarp();
+      factor_p1_warp<kPS>(D, L16t, Pk + (s + 1) * kPacket + 64, rdiag, s_bad, c0 + 16, lane);
+    } else {
+      pub(s);
+      FCLK(s, 4);
+      // fragment column ct = warp (warp 7 also column 0 ... only columns >= rt0 hold D entries to update)
+      for (int ct = rt0 + (warp - 1); ct < 8; ct += 7) {
+        int first = ct;  // lower fragments: rt >= ct
+        if (ct == rt0 || ct == rt0 + 1) first = rt0 + 2;  // (rt0,rt0), (rt0+1,rt0), (rt0+1,rt0+1) are warp 0's
+        if (first >= 8) continue;
+        const double* pb = Pt + q * kPS + 8 * ct + g;
+        double bv[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) bv[kk] = pb[4 * kk * kPS];
+        for (int rt = first; rt < 8; ++rt) {
+          double* cp = D + (8 * rt + g) * kTS + 8 * ct + 2 * q;
+          double2 cv = *reinterpret_cast<const double2*>(cp);
+          const double* pa = Pt + q * kPS + 8 * rt + g;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const double a0 = -pa[4 * kk * kPS];
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(cv.x), "+d"(cv.y) : "d"(a0), "d"(bv[kk]));
+          }
+          *reinterpret_cast<double2*>(cp) = cv;
+        }
+      }
+      side(s + 1);
+    }
+    FCLK(s, 3);
+    __syncthreads();
+  }
+  FCLK(3, 0);
+  pub_last();
+  FCLK(3, 1);
+  return *s_bad == 0;
+}
+
+// x = L^-1 v (forward, FWD) or x = L^-T v (backward) for the factored 64x64 block kept as its four packets:
+// 16-wide substitution with the explicit 16x16 inverses.  v (shared, 64) is overwritten by x.  All 256 threads call.
+template <bool FWD>
+__device__ __forceinline__ void block_solve_packets(const double* Pk, double* v, double* x16, int tid) {
+  const int lane4 = tid & 3, r4 = tid >> 2;  // 4 lanes per output
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const int s = FWD ? it : 3 - it;
+    const double* Pt = Pk + s * kPacket;
+    const double* XT = Pt + 64;
+    if (tid < 64) {
+      // x_s[n] : FWD  sum_{k <= n} X16[n][k] v[16 s + k] = sum_k XT[k][n] v[..]
+      //          BWD  sum_{m >= n} X16[m][n] v[16 s + m] = sum_m XT[n][m] v[..]
+      const int n = r4;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = lane4; k < 16; k += 4) {
+        const double xe = FWD ? (k <= n ? XT[k * kPS + n] : 0.0) : (k >= n ? XT[n * kPS + k] : 0.0);
+        acc = fma(xe, v[16 * s + k], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (lane4 == 0) x16[n] = acc;
+    }
+    __syncthreads();
+    if (FWD) {
+      // v[row] -= sum_k L[row][16 s + k] x_s[k]   for row >= 16 (s + 1)
+      const int row = r4;
+      double acc = 0.0;
+      if (row >= 16 * (s + 1)) {
+#pragma unroll
+        for (int k = lane4; k < 16; k += 4) acc = fma(Pt[k * kPS + row], x16[k], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (lane4 == 0) {
+        if (row >= 16 * (s + 1)) v[row] -= acc;
+        else if (row >= 16 * s) v[row] = x16[row - 16 * s];
+      }
+    } else {
+      // v[16 s' + k] -= sum_{row in block s} L[row][16 s' + k] x_s[row - 16 s]   for every earlier block s' < s
+      // (L[row][16 s' + k] = Pt_{s'}[k][row]);  64 outputs c = 16 s' + k, 4 lanes each over the 16 rows
+      const int c = r4;
+      double acc = 0.0;
+      if (c < 16 * s) {
+        const double* Pc = Pk + (c >> 4) * kPacket + (c & 15) * kPS + 16 * s;
+#pragma unroll
+        for (int m = lane4; m < 16; m += 4) acc = fma(Pc[m], x16[m], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (lane4 == 0) {
+        if (c < 16 * s) v[c] -= acc;
+        else if (c < 16 * (s + 1)) v[c] = x16[c - 16 * s];
+      }
+    }
+    __syncthreads();
+  }
 }
 
 }  // namespace ctvio

@@ -139,7 +139,8 @@ struct ctvio_engine {
   DevBuf<double> d_M, d_Linv, d_y, d_sc, d_sl, d_hh, d_dc, d_dl, d_rho_sync, d_chol_part;
   DevBuf<int32_t> d_chol_flags;
   DevBuf<uint8_t> d_owned;
-  int npad = 0;
+  int npad = 0, linv_npad = -1;
+  unsigned chol_seq = 0;  // tile-DAG launches so far (packet buffer parity)
   DevBuf<LmScalars> d_scal;
   LmScalars* h_scal = nullptr;  // pinned
   LmPublished* h_pub = nullptr; // pinned + mapped: written by the last kernel of an LM step
@@ -159,7 +160,7 @@ struct ctvio_engine {
   struct MargWs {
     DevBuf<int32_t> pos_cam, pos_lm, prior_pos, marg_img, marg_imu;
     DevBuf<int2> bij;
-    DevBuf<double> bs, A, b, Amm, V, ev, Vs, Ainv, T, Ap, bp, Ap2, V2, ev2, vb, J, r;
+    DevBuf<double> Jrow, bs, A, b, Amm, V, ev, Vs, Ainv, T, Ap, bp, Ap2, V2, ev2, vb, J, r;
   } mws;
 
   // multi-GPU
@@ -345,7 +346,12 @@ int prepare(ctvio_engine* e) {
     for (int b = 0; b < 2; ++b) CUDA_OK(e->ne_slab[b].reserve(e->ne_slab_len));
     e->npad = ((d.np + kCholNB - 1) / kCholNB) * kCholNB;
     CUDA_OK(e->d_M.reserve(size_t(e->npad) * e->npad + 3 * size_t(e->npad)));  // M | rhs | diagA | yf (all-reduce slab)
-    CUDA_OK(e->d_Linv.reserve(size_t(e->npad) * kCholNB));
+    if (chol_dag_lpub_len(e->npad) > e->d_Linv.cap || e->linv_npad != e->npad) {
+      CUDA_OK(e->d_Linv.reserve(chol_dag_lpub_len(e->npad)));
+      e->launches += launch_chol_dag_init(e->d_Linv.p, e->npad, e->stream);  // packet buffers start as sentinels
+      e->linv_npad = e->npad;
+      e->chol_seq = 0;
+    }
     {
       // ---- K4 work items: per 64x64 tile (ti >= tj) of the reduced system the landmarks whose knot-dim range
       // [lo, hi) touches both blocks, cut into parts of `part` landmarks so that about two waves of CTAs exist
@@ -555,7 +561,7 @@ LinearLaunch linear_launch(ctvio_engine* e, int nb) {
   a.rhs = e->d_M.p + size_t(e->npad) * e->npad;
   a.diagA = a.rhs + e->npad;
   a.yf = a.diagA + e->npad;
-  a.chol_part = e->d_chol_part.p; a.chol_flags = e->d_chol_flags.p;
+  a.chol_part = e->d_chol_part.p; a.chol_flags = e->d_chol_flags.p; a.chol_seq = &e->chol_seq;
   a.sharded = e->world > 1 ? 1 : 0;
   a.hh = e->d_hh.p; a.dc = e->d_dc.p; a.dl = e->d_dl.p;
   a.npad = e->npad;
@@ -1647,27 +1653,35 @@ int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
   CUDA_OK(d_bs.upload(bs, st));
   CUDA_OK(d_A.reserve(size_t(P) * P));
   CUDA_OK(d_b.reserve(P));
-  CUDA_OK(cudaMemsetAsync(d_A.p, 0, size_t(P) * P * sizeof(double), st));
-  CUDA_OK(cudaMemsetAsync(d_b.p, 0, size_t(P) * sizeof(double), st));
   {
+    // row-compressed Jacobian of every recorded factor, then [A | b] = Jrow' Jrow in a fixed summation order
+    const int n_old = use_prior ? e->prior.n : 0;
+    const int row_img = 0, row_imu = 2 * int(marg_img.size()), row_bias = row_imu + 6 * int(marg_imu.size());
+    const int row_prior = row_bias + 6 * int(bij.size());
+    const int R = row_prior + n_old;
+    const int ldj = (P + 2) & ~1;
+    CUDA_OK(ws.Jrow.reserve(size_t(std::max(R, 1)) * ldj));
+    CUDA_OK(cudaMemsetAsync(ws.Jrow.p, 0, size_t(std::max(R, 1)) * ldj * sizeof(double), st));
     ctvio::MargImageArgs a;
     a.obs = ImageObsPtrs{e->d_img_t.p, e->d_img_pi.p, e->d_img_pj.p, e->d_img_meta.p, int32_t(e->img.size())};
     a.marg_index = d_marg_img.p; a.n_marg = int32_t(marg_img.size());
     a.st = e->x[e->cur].ptrs(); a.sp = e->sp; a.rig = e->rig; a.cauchy = e->cfg.cauchy_marg;
     a.pos_cam = d_pos_cam.p; a.pos_lm = d_pos_lm.p; a.idx_ld = d.idx_ld;
-    a.A = d_A.p; a.b = d_b.p; a.P = P; a.scal = e->d_scal.p;
+    a.Jrow = ws.Jrow.p; a.ldj = ldj; a.row0 = row_img; a.P = P; a.scal = e->d_scal.p;
     e->launches += ctvio::launch_marg_image(a, st);
     ctvio::MargImuArgs b;
     b.obs = ImuObsPtrs{e->d_imu_t.p, e->d_imu_ga.p, int32_t(e->imu.size())};
     b.marg_index = d_marg_imu.p; b.n_marg = int32_t(marg_imu.size());
     b.st = a.st; b.sp = e->sp; b.rig = e->rig; b.pos_cam = d_pos_cam.p; b.idx_bias0 = d.idx_bias0;
-    b.A = d_A.p; b.b = d_b.p; b.P = P; b.scal = e->d_scal.p;
+    b.Jrow = ws.Jrow.p; b.ldj = ldj; b.row0 = row_imu; b.P = P; b.scal = e->d_scal.p;
     e->launches += ctvio::launch_marg_imu(b, st);
     ctvio::MargSmallArgs c;
     c.bf_ij = d_bij.p; c.bf_s = d_bs.p; c.n_bias = int32_t(bij.size());
     c.prior = prior_ptrs(e); c.use_prior = use_prior ? 1 : 0; c.prior_pos = d_prior_pos.p;
-    c.st = a.st; c.pos_cam = d_pos_cam.p; c.idx_bias0 = d.idx_bias0; c.A = d_A.p; c.b = d_b.p; c.P = P;
+    c.st = a.st; c.pos_cam = d_pos_cam.p; c.idx_bias0 = d.idx_bias0;
+    c.Jrow = ws.Jrow.p; c.ldj = ldj; c.row0_bias = row_bias; c.row0_prior = row_prior; c.P = P;
     e->launches += ctvio::launch_marg_small(c, st);
+    e->launches += ctvio::launch_marg_syrk(ws.Jrow.p, R, ldj, P, d_A.p, d_b.p, st);
   }
   // ---- dense Schur complement through eigen-decompositions (marginalization_factor.cpp:240-263) ----
   const double eps = 1e-30;

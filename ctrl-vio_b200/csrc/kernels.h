@@ -222,12 +222,14 @@ struct LinearLaunch {
   double* sc;                   // [np] Jacobi scale
   double* sl;                   // [nL]
   double* M;                    // [npad][npad] reduced system, LOWER triangle of 64x64 tiles valid (diagonal tiles full)
-  double* Linv;                 // [npad/NB][NB][NB] inverses of the diagonal Cholesky blocks
+  double* Linv;                 // barrier kernel: [npad/NB][NB][NB] inverses of the diagonal Cholesky blocks;
+                                // tile-DAG kernel: the per-step packets of the diagonal factorisations (chol_dag_lpub_len)
   double* rhs;                  // [npad]
   double* y;                    // [npad]
   double* yf;                   // [npad] forward-solved right-hand side
   double* chol_part;            // workspace of the tile-DAG Cholesky (chol_dag_part_len doubles); null -> barrier kernel
   int32_t* chol_flags;          // its dependency flags (chol_dag_flags_len ints, zero-initialised once)
+  unsigned* chol_seq;           // host counter of tile-DAG launches on this engine (packet buffer parity); may be null
   double* hh;                   // [nL] damped landmark diagonals
   double* diagA;                // [npad] camera diagonal (sharded mode: all-reduced with M and rhs); may be null
   int32_t sharded;              // != 0: M is built WITHOUT damping / identity rows (they are added after the all-reduce)
@@ -246,6 +248,8 @@ int launch_factor_solve(const LinearLaunch& a, cudaStream_t s);
 bool chol_dag_supported(int npad, int n_sm);
 size_t chol_dag_part_len(int npad);
 size_t chol_dag_flags_len(int npad);
+size_t chol_dag_lpub_len(int npad);  // doubles of LinearLaunch::Linv: [block inverses of the barrier kernel | 2 packet buffers]
+int launch_chol_dag_init(double* linv_buf, int npad, cudaStream_t s);  // packet buffers <- sentinels, once per allocation
 int launch_chol_dag(const LinearLaunch& a, cudaStream_t s);
 int launch_chol_coop(const LinearLaunch& a, cudaStream_t s);
 int launch_step_vectors(const LinearLaunch& a, cudaStream_t s);

@@ -12,7 +12,10 @@
 namespace ctvio {
 
 // ------------------------------------------------------------------------------------------------
-// recorded image / IMU factors -> A, b
+// recorded factors -> rows of the compressed Jacobian  Jrow[R][ldj]  (columns = positions in the [dropped | kept]
+// ordering, last used column P = the residual), then  [A | b] = Jrow' Jrow  by ONE kernel whose threads each own an
+// output entry and run over the rows in a FIXED order: the accumulation is bit-reproducible run to run (the r1 version
+// used ~2 500 unordered fp64 atomics per factor).  Every thread below writes only its own rows.
 
 __global__ void marg_image_kernel(MargImageArgs a) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,43 +39,36 @@ __global__ void marg_image_kernel(MargImageArgs a) {
   ImageCommon cm;
   const double pixy[2] = {pi.x, pi.y}, pjxy[2] = {pj.x, pj.y};
   image_common(a.rig, pixy, pjxy, rho, ea.R, ea.p, eb.R, eb.p, a.cauchy, cm);
-  // local Jacobian: 2 x 50 (+ positions)
-  double J0[50], J1[50];
-  int pos[50];
+  double* row0 = a.Jrow + size_t(a.row0 + 2 * m) * a.ldj;
+  double* row1 = row0 + a.ldj;
+  // the two knot windows may overlap (frames closer than the spline support): contributions ADD in the thread's own rows
+  auto put = [&](int pos, double v0, double v1) {
+    if (pos < 0) return;
+    row0[pos] += v0;
+    row1[pos] += v1;
+  };
   {
     double rot[4][6], posb[4][6];
     image_side_blocks(0, cm, ea, rot, posb);
     for (int k = 0; k < 4; ++k)
       for (int c = 0; c < 3; ++c) {
-        J0[k * 6 + c] = rot[k][c]; J1[k * 6 + c] = rot[k][3 + c];
-        J0[k * 6 + 3 + c] = posb[k][c]; J1[k * 6 + 3 + c] = posb[k][3 + c];
-        pos[k * 6 + c] = a.pos_cam[6 * (si + k) + c];
-        pos[k * 6 + 3 + c] = a.pos_cam[6 * (si + k) + 3 + c];
+        put(a.pos_cam[6 * (si + k) + c], rot[k][c], rot[k][3 + c]);
+        put(a.pos_cam[6 * (si + k) + 3 + c], posb[k][c], posb[k][3 + c]);
       }
     image_side_blocks(1, cm, eb, rot, posb);
     for (int k = 0; k < 4; ++k)
       for (int c = 0; c < 3; ++c) {
-        J0[24 + k * 6 + c] = rot[k][c]; J1[24 + k * 6 + c] = rot[k][3 + c];
-        J0[24 + k * 6 + 3 + c] = posb[k][c]; J1[24 + k * 6 + 3 + c] = posb[k][3 + c];
-        pos[24 + k * 6 + c] = a.pos_cam[6 * (sj + k) + c];
-        pos[24 + k * 6 + 3 + c] = a.pos_cam[6 * (sj + k) + 3 + c];
+        put(a.pos_cam[6 * (sj + k) + c], rot[k][c], rot[k][3 + c]);
+        put(a.pos_cam[6 * (sj + k) + 3 + c], posb[k][c], posb[k][3 + c]);
       }
   }
   double t2[2];
   image_jrho(a.rig, cm, ea.R, rho, t2);
-  J0[48] = t2[0]; J1[48] = t2[1]; pos[48] = a.pos_lm[meta.z];
+  put(a.pos_lm[meta.z], t2[0], t2[1]);
   image_jld(a.rig, cm, meta.x, meta.y, ea.R, ea.omega, ea.vel, eb.R, eb.omega, eb.vel, t2);
-  J0[49] = t2[0]; J1[49] = t2[1]; pos[49] = a.pos_cam[a.idx_ld];
-  const int P = a.P;
-  for (int x = 0; x < 50; ++x) {
-    if (pos[x] < 0) continue;
-    atomicAdd(a.b + pos[x], J0[x] * cm.r[0] + J1[x] * cm.r[1]);
-    for (int y = 0; y < 50; ++y) {
-      if (pos[y] < 0) continue;
-      const double h = J0[x] * J0[y] + J1[x] * J1[y];
-      if (h != 0.0) atomicAdd(a.A + size_t(pos[x]) * P + pos[y], h);
-    }
-  }
+  put(a.pos_cam[a.idx_ld], t2[0], t2[1]);
+  row0[a.P] = cm.r[0];
+  row1[a.P] = cm.r[1];
 }
 
 __global__ void marg_imu_kernel(MargImuArgs a) {
@@ -93,45 +89,34 @@ __global__ void marg_imu_kernel(MargImuArgs a) {
   }
   ImuEvalOut o;
   eval_imu<true, kPStride>(a.sp, a.rig, a.st.q, a.st.p, a.st.tab, s, u, gyro, accel, bias, o);
-  const int P = a.P;
-  // 30 local columns: 4 knots x (rot 3 | pos 3), bg 3, ba 3
-  for (int x = 0; x < 30; ++x) {
-    const int px = x < 24 ? a.pos_cam[6 * (s + x / 6) + x % 6] : a.pos_cam[a.idx_bias0 + 6 * node + (x - 24)];
-    if (px < 0) continue;
-    double jx[6];
-    for (int r = 0; r < 6; ++r)
-      jx[r] = x < 24 ? ((x % 6) < 3 ? o.Jrot[x / 6][3 * r + x % 6] : o.Jpos[x / 6][3 * r + x % 6 - 3])
-                     : ((x - 24) == r ? a.rig.imu_info[r] : 0.0);
-    double g = 0;
-    for (int r = 0; r < 6; ++r) g += jx[r] * o.r[r];
-    atomicAdd(a.b + px, g);
-    for (int y = 0; y < 30; ++y) {
-      const int py = y < 24 ? a.pos_cam[6 * (s + y / 6) + y % 6] : a.pos_cam[a.idx_bias0 + 6 * node + (y - 24)];
-      if (py < 0) continue;
-      double h = 0;
-      for (int r = 0; r < 6; ++r) {
-        const double jy = y < 24 ? ((y % 6) < 3 ? o.Jrot[y / 6][3 * r + y % 6] : o.Jpos[y / 6][3 * r + y % 6 - 3])
-                                 : ((y - 24) == r ? a.rig.imu_info[r] : 0.0);
-        h += jx[r] * jy;
+  // 6 rows x 30 local columns: 4 knots x (rot 3 | pos 3), bg 3, ba 3
+  for (int r = 0; r < 6; ++r) {
+    double* row = a.Jrow + size_t(a.row0 + 6 * m + r) * a.ldj;
+    for (int k = 0; k < 4; ++k)
+      for (int c = 0; c < 3; ++c) {
+        const int pr = a.pos_cam[6 * (s + k) + c], pp = a.pos_cam[6 * (s + k) + 3 + c];
+        if (pr >= 0) row[pr] = o.Jrot[k][3 * r + c];
+        if (pp >= 0) row[pp] = o.Jpos[k][3 * r + c];
       }
-      if (h != 0.0) atomicAdd(a.A + size_t(px) * P + py, h);
-    }
+    const int pb = a.pos_cam[a.idx_bias0 + 6 * node + r];
+    if (pb >= 0) row[pb] = a.rig.imu_info[r];
+    row[a.P] = o.r[r];
   }
 }
 
 // bias factors flagged marg + the old prior (if recorded); one CTA
 __global__ void marg_small_kernel(MargSmallArgs a) {
   const int tid = threadIdx.x;
-  const int P = a.P;
   for (int n = tid; n < a.n_bias; n += blockDim.x) {
     const int2 ij = a.bf_ij[n];
     for (int k = 0; k < 6; ++k) {
       const double s = a.bf_s[6 * n + k];
       const double r = s * (a.st.bias[6 * ij.y + k] - a.st.bias[6 * ij.x + k]);
       const int pi = a.pos_cam[a.idx_bias0 + 6 * ij.x + k], pj = a.pos_cam[a.idx_bias0 + 6 * ij.y + k];
-      if (pi >= 0) { atomicAdd(a.b + pi, -s * r); atomicAdd(a.A + size_t(pi) * P + pi, s * s); }
-      if (pj >= 0) { atomicAdd(a.b + pj, s * r); atomicAdd(a.A + size_t(pj) * P + pj, s * s); }
-      if (pi >= 0 && pj >= 0) { atomicAdd(a.A + size_t(pi) * P + pj, -s * s); atomicAdd(a.A + size_t(pj) * P + pi, -s * s); }
+      double* row = a.Jrow + size_t(a.row0_bias + 6 * n + k) * a.ldj;
+      if (pi >= 0) row[pi] = -s;
+      if (pj >= 0) row[pj] = s;
+      row[a.P] = r;
     }
   }
   const int n = a.prior.n;
@@ -162,23 +147,43 @@ __global__ void marg_small_kernel(MargSmallArgs a) {
   for (int i = tid; i < n; i += blockDim.x) {
     double s = a.prior.r[i];
     for (int j = 0; j < n; ++j) s = fma(a.prior.J[size_t(i) * n + j], a.prior.dx[j], s);
-    a.prior.res[i] = s;
+    a.Jrow[size_t(a.row0_prior + i) * a.ldj + a.P] = s;
   }
-  __syncthreads();
-  // prior_pos[j]: position of prior column j in the new ordering
-  for (int j = tid; j < n; j += blockDim.x) {
-    const int pj = a.prior_pos[j];
-    if (pj < 0) continue;
-    double g = 0;
-    for (int i = 0; i < n; ++i) g = fma(a.prior.J[size_t(i) * n + j], a.prior.res[i], g);
-    atomicAdd(a.b + pj, g);
-  }
+  // prior_pos[j]: position of prior column j in the new ordering (distinct columns -> distinct positions)
   for (int e = tid; e < n * n; e += blockDim.x) {
-    const int x = e / n, y = e % n;
-    const int px = a.prior_pos[x], py = a.prior_pos[y];
-    if (px < 0 || py < 0) continue;
-    const double v = a.prior.JtJ[e];
-    if (v != 0.0) atomicAdd(a.A + size_t(px) * P + py, v);
+    const int i = e / n, j = e % n;
+    const int pj = a.prior_pos[j];
+    if (pj >= 0) a.Jrow[size_t(a.row0_prior + i) * a.ldj + pj] = a.prior.J[e];
+  }
+}
+
+// [A | b] = Jrow' Jrow over columns 0..P (column P = residual): C[i][j] = sum_r Jrow[r][i] Jrow[r][j], r ascending.
+// 16x16 outputs per CTA, 32 rows staged per step; the sum of every entry runs in one thread in a fixed order.
+__global__ void __launch_bounds__(256) marg_syrk_kernel(const double* __restrict__ Jrow, int R, int ldj, int P, double* A,
+                                                        double* b) {
+  __shared__ double Si[32][17], Sj[32][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i0 = blockIdx.y * 16, j0 = blockIdx.x * 16;
+  if (j0 + 15 < i0) return;  // strictly lower blocks are mirrored from the upper ones
+  const int i = i0 + ty, j = j0 + tx;
+  double acc = 0.0;
+  for (int r0 = 0; r0 < R; r0 += 32) {
+    for (int e = threadIdx.x; e < 32 * 16; e += 256) {
+      const int rr = e >> 4, c = e & 15;
+      const bool ok = r0 + rr < R;
+      Si[rr][c] = (ok && i0 + c <= P) ? Jrow[size_t(r0 + rr) * ldj + i0 + c] : 0.0;
+      Sj[rr][c] = (ok && j0 + c <= P) ? Jrow[size_t(r0 + rr) * ldj + j0 + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) acc = fma(Si[rr][ty], Sj[rr][tx], acc);
+    __syncthreads();
+  }
+  if (i > P || j > P || i == P) return;
+  if (j == P) { b[i] = acc; return; }
+  if (j >= i) {
+    A[size_t(i) * P + j] = acc;
+    A[size_t(j) * P + i] = acc;
   }
 }
 
@@ -195,6 +200,12 @@ int launch_marg_imu(const MargImuArgs& a, cudaStream_t s) {
 int launch_marg_small(const MargSmallArgs& a, cudaStream_t s) {
   if (a.n_bias <= 0 && !(a.use_prior && a.prior.n > 0)) return 0;
   marg_small_kernel<<<1, 256, 0, s>>>(a);
+  return 1;
+}
+int launch_marg_syrk(const double* Jrow, int R, int ldj, int P, double* A, double* b, cudaStream_t s) {
+  if (P <= 0) return 0;
+  const int nb = (P + 1 + 15) / 16;
+  marg_syrk_kernel<<<dim3(nb, nb), 256, 0, s>>>(Jrow, R, ldj, P, A, b);
   return 1;
 }
 
@@ -398,17 +409,162 @@ __global__ void __launch_bounds__(1024) jacobi_eig_smem_kernel(double* Ag, doubl
   for (int i = tid; i < n; i += nt) ev[i] = A[i * ld + i];
 }
 
+// Two-sided parallel Jacobi, block form.  The n/2 disjoint rotations of a round act on A as  A <- J' A J : the 2x2
+// block of rows {p_k, q_k} and columns {p_l, q_l} becomes  R_k' B R_l  and depends on NO other entry, so one thread
+// owns one (k, l) block for the whole round, in place, rows and columns in ONE phase: 2 barriers per round
+// (rotations | update) instead of the 3 + separate row pass of the kernels above, and 4 loads / 4 stores per 12 FMAs.
+// V <- V J rides in the same phase.  The (k, l) -> thread assignment does not depend on the round, so the index
+// arithmetic is hoisted out of the sweep loop.  Rotation sequence and every sum are fixed: bit-reproducible.
+// A_SMEM / V_SMEM: the matrix / the eigenvectors live in shared memory (odd row stride) or stay in global memory (L2).
+template <bool A_SMEM, bool V_SMEM>
+__global__ void __launch_bounds__(1024) jacobi_eig_block_kernel(double* Ag, double* Vg, double* ev, int n, int max_sweeps) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int ne = (n + 1) & ~1, npairs = ne / 2;
+  const int lda = A_SMEM ? (n | 1) : n, ldv = V_SMEM ? (n | 1) : n;
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  double* A = A_SMEM ? sm : Ag;
+  double* V = V_SMEM ? sm + (A_SMEM ? size_t(n) * lda : 0) : Vg;
+  double* cs = sm + (A_SMEM ? size_t(n) * lda : 0) + (V_SMEM ? size_t(n) * ldv : 0);  // [npairs][2]
+  int* pq = reinterpret_cast<int*>(cs + 2 * npairs);                                  // [npairs][2]
+  __shared__ double s_off, s_diag, s_prev;
+  for (int e = tid; e < n * n; e += nt) {
+    const int i = e / n, j = e - i * n;
+    if (A_SMEM) A[i * lda + j] = Ag[e];
+    V[i * ldv + j] = (i == j) ? 1.0 : 0.0;
+  }
+  // fixed work assignment: A blocks (k, l), k <= l (the mirror block is written by the same thread), and V row pairs
+  constexpr int kMaxBlk = 12, kMaxV = 24;
+  const int nblk_total = npairs * (npairs + 1) / 2;
+  short bk[kMaxBlk], bl[kMaxBlk];
+  int nblk = 0;
+  for (int b = tid; b < nblk_total && nblk < kMaxBlk; b += nt) {
+    // b -> (k, l) with k <= l, row-major over the upper triangle
+    int k = 0, rem = b;
+    while (rem >= npairs - k) { rem -= npairs - k; ++k; }
+    bk[nblk] = short(k); bl[nblk] = short(k + rem);
+    ++nblk;
+  }
+  __syncthreads();
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    if (tid == 0) { s_off = 0.0; s_diag = 0.0; }
+    __syncthreads();
+    double off = 0, dg = 0;
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e - i * n;
+      const double v = A[i * lda + j];
+      if (i == j) dg += v * v; else off += v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      off += __shfl_xor_sync(0xffffffffu, off, o);
+      dg += __shfl_xor_sync(0xffffffffu, dg, o);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&s_off, off); atomicAdd(&s_diag, dg); }
+    __syncthreads();
+    // converged, or stagnating at the rounding floor (the off-diagonal mass no longer halves per sweep once it is below
+    // ~(n eps)^2 of the diagonal mass).  Stopping earlier is NOT an option: the reference's eps = 1e-30 pseudo-inverse
+    // inverts the smallest eigenvalues, so their relative accuracy matters.  (shared-memory atomics of 32 warp sums:
+    // the order can differ between runs, but s_off only steers the loop count through comparisons far from any tie)
+    const double prev = sweep > 0 ? s_prev : 1e300;
+    if (s_off <= 1e-60 || s_off <= 1e-30 * s_diag || (s_off <= 1e-24 * s_diag && s_off > 0.5 * prev)) break;
+    __syncthreads();
+    if (tid == 0) s_prev = s_off;
+    for (int round = 0; round < ne - 1; ++round) {
+      // ---- phase R: the round's pairs (round-robin tournament) and their rotations ----
+      for (int k = tid; k < npairs; k += nt) {
+        int p, q;
+        if (k == 0) { p = ne - 1; q = round % (ne - 1); }
+        else { p = (round + k) % (ne - 1); q = (round + ne - 1 - k) % (ne - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, s = 0.0;
+        if (q < n) {
+          const double apq = A[p * lda + q];
+          if (apq != 0.0) {
+            const double app = A[p * lda + p], aqq = A[q * lda + q];
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = 1.0 / sqrt(t * t + 1.0);
+            s = t * c;
+          }
+        } else {
+          q = -1;  // dummy player of an odd n: the pair is idle
+        }
+        cs[2 * k] = c; cs[2 * k + 1] = s;
+        pq[2 * k] = p; pq[2 * k + 1] = q;
+      }
+      __syncthreads();
+      // ---- phase U: every 2x2 block B(k,l) <- R_k' B R_l  (and its mirror), V <- V R ----
+#pragma unroll 1
+      for (int w = 0; w < nblk; ++w) {
+        const int k = bk[w], l = bl[w];
+        const int pk = pq[2 * k], qk = pq[2 * k + 1], pl = pq[2 * l], ql = pq[2 * l + 1];
+        const double ck = cs[2 * k], sk = cs[2 * k + 1], cl = cs[2 * l], sl = cs[2 * l + 1];
+        if (qk < 0 && ql < 0) continue;
+        // entries with an idle (dummy) partner: only the real row / column exists
+        const bool hk = qk >= 0, hl = ql >= 0;
+        const double b00 = A[pk * lda + pl];
+        const double b01 = hl ? A[pk * lda + ql] : 0.0;
+        const double b10 = hk ? A[qk * lda + pl] : 0.0;
+        const double b11 = (hk && hl) ? A[qk * lda + ql] : 0.0;
+        // columns: [x_p x_q] <- [c x_p - s x_q , s x_p + c x_q] with (cl, sl); rows likewise with (ck, sk)
+        const double t00 = cl * b00 - sl * b01, t01 = sl * b00 + cl * b01;
+        const double t10 = cl * b10 - sl * b11, t11 = sl * b10 + cl * b11;
+        const double r00 = ck * t00 - sk * t10, r10 = sk * t00 + ck * t10;
+        const double r01 = ck * t01 - sk * t11, r11 = sk * t01 + ck * t11;
+        A[pk * lda + pl] = r00;
+        if (hl) A[pk * lda + ql] = r01;
+        if (hk) A[qk * lda + pl] = r10;
+        if (hk && hl) A[qk * lda + ql] = r11;
+        if (k != l) {  // mirror block (l, k) = transpose
+          A[pl * lda + pk] = r00;
+          if (hl) A[ql * lda + pk] = r01;
+          if (hk) A[pl * lda + qk] = r10;
+          if (hk && hl) A[ql * lda + qk] = r11;
+        }
+      }
+      {
+        const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+        for (int k = warp; k < npairs; k += nwarps) {
+          const int p = pq[2 * k], q = pq[2 * k + 1];
+          const double c = cs[2 * k], s = cs[2 * k + 1];
+          if (q < 0 || s == 0.0) continue;
+          for (int r = lane; r < n; r += 32) {
+            const double vp = V[r * ldv + p], vq = V[r * ldv + q];
+            V[r * ldv + p] = c * vp - s * vq;
+            V[r * ldv + q] = s * vp + c * vq;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = tid; e < n * n; e += nt) {
+    const int i = e / n, j = e - i * n;
+    if (A_SMEM) Ag[e] = A[i * lda + j];
+    if (V_SMEM) Vg[e] = V[i * ldv + j];
+  }
+  for (int i = tid; i < n; i += nt) ev[i] = A[i * lda + i];
+}
+
 int launch_jacobi_eig(double* A, double* V, double* ev, int n, cudaStream_t s) {
   if (n <= 0) return 0;
-  const size_t pairs = size_t((n + 1) / 2) * (2 * sizeof(double) + 2 * sizeof(int));
-  const size_t smem_res = 2 * size_t(n) * (n | 1) * sizeof(double) + pairs;
-  if (smem_res <= 220 * 1024) {
-    static PerDeviceOnce once;
-    if (once.first()) cudaFuncSetAttribute(jacobi_eig_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    jacobi_eig_smem_kernel<<<1, 1024, smem_res, s>>>(A, V, ev, n, 60);
+  const int ne = (n + 1) & ~1, npairs = ne / 2;
+  const size_t pairs = size_t(npairs) * (2 * sizeof(double) + 2 * sizeof(int));
+  const size_t mat = size_t(n) * (n | 1) * sizeof(double);
+  const size_t limit = 224 * 1024;
+  static PerDeviceOnce once;
+  if (once.first()) {
+    cudaFuncSetAttribute(jacobi_eig_block_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit));
+    cudaFuncSetAttribute(jacobi_eig_block_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit));
+  }
+  // per-thread block slots: npairs (npairs + 1) / 2 blocks over 1024 threads, at most 12 each -> n <= ~310
+  if (size_t(npairs) * (npairs + 1) / 2 > size_t(12) * 1024) {
+    jacobi_eig_kernel<<<1, 1024, pairs, s>>>(A, V, ev, n, 60);
     return 1;
   }
-  jacobi_eig_kernel<<<1, 1024, pairs, s>>>(A, V, ev, n, 60);
+  if (2 * mat + pairs <= limit) jacobi_eig_block_kernel<true, true><<<1, 1024, 2 * mat + pairs, s>>>(A, V, ev, n, 60);
+  else if (mat + pairs <= limit) jacobi_eig_block_kernel<true, false><<<1, 1024, mat + pairs, s>>>(A, V, ev, n, 60);
+  else jacobi_eig_block_kernel<false, false><<<1, 1024, pairs, s>>>(A, V, ev, n, 60);
   return 1;
 }
 

@@ -47,8 +47,8 @@ struct MargImageArgs {
   const int32_t* pos_cam;     // [np] camera dim -> position in [dropped | kept] ordering, -1 = not a block
   const int32_t* pos_lm;      // [nL]
   int32_t idx_ld;
-  double* A;                  // [P][P]
-  double* b;                  // [P]
+  double* Jrow;               // [R][ldj] row-compressed Jacobian, column P = residual; this factor owns rows row0 + 2 m ..
+  int32_t ldj, row0;
   int32_t P;
   LmScalars* scal;
 };
@@ -61,8 +61,8 @@ struct MargImuArgs {
   RigParams rig;
   const int32_t* pos_cam;
   int32_t idx_bias0;
-  double* A;
-  double* b;
+  double* Jrow;
+  int32_t ldj, row0;
   int32_t P;
   LmScalars* scal;
 };
@@ -76,10 +76,12 @@ struct MargSmallArgs {
   StatePtrs st;
   const int32_t* pos_cam;
   int32_t idx_bias0;
-  double* A;
-  double* b;
+  double* Jrow;
+  int32_t ldj, row0_bias, row0_prior;
   int32_t P;
 };
+// [A | b] = Jrow' Jrow, fixed summation order (A: [P][P] symmetric, b: [P])
+int launch_marg_syrk(const double* Jrow, int R, int ldj, int P, double* A, double* b, cudaStream_t s);
 int launch_marg_image(const MargImageArgs& a, cudaStream_t s);
 int launch_marg_imu(const MargImuArgs& a, cudaStream_t s);
 int launch_marg_small(const MargSmallArgs& a, cudaStream_t s);

@@ -221,7 +221,10 @@ class StreamingRunner:
             self.frames.pop(0)                      # slideWindowOld
         else:
             self.frames.pop(-2)                     # slideWindowNew: the prior stays as it is
-        rec = dict(window=self.step_index, ms=1e3 * t_wall, iterations=summ.iterations, final_cost=summ.final_cost,
+        # 0.5 |r_lin|^2 of the prior this window was solved with: the part of the cost that is set by the eps = 1e-30
+        # pseudo-inverse's noise eigen-directions (tests compare costs with this constant removed)
+        prior_const = 0.0 if prior is None else 0.5 * float(np.dot(prior.r, prior.r))
+        rec = dict(window=self.step_index, ms=1e3 * t_wall, prior_const=prior_const, iterations=summ.iterations, final_cost=summ.final_cost,
                    initial_cost=summ.initial_cost, termination=summ.termination, n_obs=w.n_obs, n_imu=len(w.imu_t),
                    n_knots=nloc, n_lm=len(lm_global), device_ms=summ.device_ms, marg_flag=marg_flag,
                    init_iterations=None if init_summary is None else init_summary.iterations,

@@ -13,17 +13,19 @@ for name in ("c2", "c4"):
     t = np.array(buf[:], dtype=np.float64).reshape(32, 16)
     nb = (6 * w.n_knots + 6 * len(w.kf_times) + 1 + 63) // 64
     t0 = t[:nb, 0].min()
-    print(name, "nb", nb, " columns: start | old-updates done | Linv(j-1) seen | diag-update gemm done | D stored + rhs | factored | diag_ready posted | x_ready posted  (us from kernel start)")
+    print(name, "nb", nb, " columns (us from kernel start): start | old updates done | packets 0 1 2 3 of col j-1 seen | trsm done | D stored | "
+          "factored (last packet posted) | fwd_ready posted | x_ready posted")
     for j in range(nb):
-        print("  col %2d: " % j + " ".join("%7.1f" % ((v - t0) / 1e3) for v in t[j, :8]))
-    j = min(3, nb - 1)
-    d = t[j]
-    print("  col %d slab detail (us): Linv^T+x loaded %.2f | slab gemm %.2f | smem stores %.2f | diagonal update gemm %.2f" % (
-        j, (d[8] - d[2]) / 1e3, (d[9] - d[8]) / 1e3, (d[10] - d[9]) / 1e3, (d[3] - d[10]) / 1e3))
+        v = t[j]
+        cols = [v[0], v[1], v[8], v[9], v[10], v[11], v[3], v[4], v[5], v[6], v[7]]
+        print("  col %2d: " % j + " ".join("%7.1f" % ((x - t0) / 1e3) if x > 0 else "      -" for x in cols))
+    for j in (1, 3):
+        v = t[16 + j]
+        print("  col %d trsm steps (us from kernel start): [step a done | commit done | c done | d done] x 4: " % j + " | ".join(" ".join("%6.2f" % ((v[4 * s_ + k] - t0) / 1e3) for k in range(4)) for s_ in range(4)))
     fc = (C.c_longlong * 256)()
     LIB.lib.ctvio_debug_fac_clk(fc)
     fc = np.array(fc[:], dtype=np.int64).reshape(8, 4, 8)
     t00 = fc[0, 0, 0]
-    print("  diag factor of column 0: arrival (cycles since start) of each warp's lane 0 BEFORE the barrier ending P1 | P2 | P3, per 16-col step")
+    print("  diag factor of column 0 (cycles since loop start), per 16-col step: loop top | P2a done | after barrier | before end barrier ; pub done (warps>0)")
     for s_ in range(4):
-        print("   step %d: " % s_ + "  ".join("w%d %5d %5d %5d" % (w_, fc[w_, s_, 1] - t00, fc[w_, s_, 3] - t00, fc[w_, s_, 5] - t00) for w_ in (0, 1, 2, 3, 7)))
+        print("   step %d: " % s_ + "  ".join("w%d %5d %5d %5d %5d p%5d" % (w_, fc[w_, s_, 0] - t00, fc[w_, s_, 1] - t00, fc[w_, s_, 2] - t00, fc[w_, s_, 3] - t00, fc[w_, s_, 4] - t00) for w_ in (0, 1, 2, 7)))
