@@ -55,6 +55,22 @@ __device__ __forceinline__ void st_relaxed2(double* p, double2 v) {
   asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+__device__ __forceinline__ double ld_relaxed1(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed1(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// spin until the word has been written (self-validating message word)
+__device__ __forceinline__ double ld_spin(const double* p) {
+  double v = ld_relaxed1(p);
+  while (is_sentinel(v)) v = ld_relaxed1(p);
+  return v;
+}
+__device__ __forceinline__ double sentinel_value() { return __longlong_as_double(static_cast<long long>(kSentinel)); }
+
 // all threads of the CTA: wait until *flag == epoch (thread 0 spins), then make the producer's data visible
 __device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
   if (threadIdx.x == 0) {
@@ -99,16 +115,21 @@ __device__ __forceinline__ void store_tile_global(double* dst, int ld, const dou
 }
 // s[tid & 63] partial: sum over q = (tid >> 6), q + 4, ... < n of part[q * stride + (tid & 63)], combined over the
 // four thread groups in a fixed order through red[4][64]; returns the total for tid < 64 (after a barrier)
+// (the partials are self-validating words: every load spins until its producer has written it)
 __device__ __forceinline__ double sum_partials(const double* part, int n, size_t stride, double* red, int tid) {
   const int c = tid & 63, g = tid >> 6;
   double s = 0.0;
   int q = g;
   for (; q + 12 < n; q += 16) {
-    const double v0 = __ldcg(part + size_t(q) * stride + c), v1 = __ldcg(part + size_t(q + 4) * stride + c);
-    const double v2 = __ldcg(part + size_t(q + 8) * stride + c), v3 = __ldcg(part + size_t(q + 12) * stride + c);
+    double v0 = ld_relaxed1(part + size_t(q) * stride + c), v1 = ld_relaxed1(part + size_t(q + 4) * stride + c);
+    double v2 = ld_relaxed1(part + size_t(q + 8) * stride + c), v3 = ld_relaxed1(part + size_t(q + 12) * stride + c);
+    while (is_sentinel(v0)) v0 = ld_relaxed1(part + size_t(q) * stride + c);
+    while (is_sentinel(v1)) v1 = ld_relaxed1(part + size_t(q + 4) * stride + c);
+    while (is_sentinel(v2)) v2 = ld_relaxed1(part + size_t(q + 8) * stride + c);
+    while (is_sentinel(v3)) v3 = ld_relaxed1(part + size_t(q + 12) * stride + c);
     s += v0; s += v1; s += v2; s += v3;
   }
-  for (; q < n; q += 4) s += __ldcg(part + size_t(q) * stride + c);
+  for (; q < n; q += 4) s += ld_spin(part + size_t(q) * stride + c);
   red[g * kCholNB + c] = s;
   __syncthreads();
   return tid < kCholNB ? (red[tid] + red[kCholNB + tid]) + (red[2 * kCholNB + tid] + red[3 * kCholNB + tid]) : 0.0;
@@ -123,11 +144,70 @@ __device__ __forceinline__ void tile_matvec(const double* Lrm, const double* v, 
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   if (pt == 0) {
-    out_global[r] = s;
+    st_relaxed1(out_global + r, s);
     if (out_shared) out_shared[r] = s;
   }
 }
 }  // namespace
+
+// ---- masked fragment products --------------------------------------------------------------------
+// f[mt][nt] -= A_frag(mt) B_frag(nt)' over nk4 k-steps of 4, for the (mt, nt) pairs of the COMPILE-TIME mask (bit 4 mt + nt).
+// Which fragments a warp has to touch is warp-uniform but only known at run time (it depends on the warp's position in
+// the folded fragment grid and on the 16-column step); a run-time predicate per mma.sync makes ptxas guard EVERY DMMA with
+// a WARPSYNC (measured: a 64x16x64 slab update took 2.3 us instead of 0.5).  So the run-time value selects one of a
+// handful of instantiations and the inner loop is branch free.
+template <unsigned MASK>
+__device__ __forceinline__ void mma_masked(Frag& f, const double* pa, int sa, const double* pb, int sb, const Lane& L, int nk4) {
+#pragma unroll 4
+  for (int kk = 0; kk < nk4; ++kk) {
+    double av[2], bv[4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+      if (MASK & (0xFu << (4 * mt))) av[mt] = -pa[4 * kk * sa + 8 * L.rt[mt]];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (MASK & (0x11u << nt)) bv[nt] = pb[4 * kk * sb + 8 * L.ct[nt]];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        if ((MASK >> (4 * mt + nt)) & 1u)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(f.c[mt][nt][0]), "+d"(f.c[mt][nt][1]) : "d"(av[mt]), "d"(bv[nt]));
+  }
+}
+__device__ __forceinline__ void mma_dispatch(unsigned mask, Frag& f, const double* pa, int sa, const double* pb, int sb,
+                                             const Lane& L, int nk4) {
+  switch (mask) {  // warp-uniform
+    case 0x33u: mma_masked<0x33u>(f, pa, sa, pb, sb, L, nk4); break;
+    case 0xCCu: mma_masked<0xCCu>(f, pa, sa, pb, sb, L, nk4); break;
+    case 0xFFu: mma_masked<0xFFu>(f, pa, sa, pb, sb, L, nk4); break;
+    case 0xF1u: mma_masked<0xF1u>(f, pa, sa, pb, sb, L, nk4); break;
+    case 0x73u: mma_masked<0x73u>(f, pa, sa, pb, sb, L, nk4); break;
+    case 0xF0u: mma_masked<0xF0u>(f, pa, sa, pb, sb, L, nk4); break;
+    default: break;
+  }
+}
+// fragments (mt, nt) with rt[mt] >= ct[nt] (lower triangle of a diagonal tile) for the folded ownership of lane_of():
+// warp (wm, wn) owns fragment rows {wm, 7 - wm} and columns {0,1,6,7} (wn = 0) / {2,3,4,5} (wn = 1)
+__device__ __forceinline__ unsigned lower_mask(int warp) {
+  const int wm = warp & 3, wn = warp >> 2;
+  if (wn == 0) return wm == 0 ? 0xF1u : wm == 1 ? 0x73u : 0x33u;
+  return wm <= 1 ? 0xF0u : wm == 2 ? 0xF1u : 0x73u;
+}
+// fragment-column pairs of a warp by 16-column slab: wn = 0: pair 0 (nt 0,1) = slab 0, pair 1 (nt 2,3) = slab 3;
+// wn = 1: pair 0 = slab 1, pair 1 = slab 2
+__device__ __forceinline__ unsigned slab_mask(int warp, int s) {
+  const int wn = warp >> 2;
+  if (wn == 0) return s == 0 ? 0x33u : s == 3 ? 0xCCu : 0u;
+  return s == 1 ? 0x33u : s == 2 ? 0xCCu : 0u;
+}
+// ... and the pairs that lie in slabs > s (trailing columns of a solve step)
+__device__ __forceinline__ unsigned trailing_mask(int warp, int s) {
+  const int wn = warp >> 2;
+  if (wn == 0) return s < 3 ? 0xCCu : 0u;
+  return s == 0 ? 0xFFu : s == 1 ? 0xCCu : 0u;
+}
 
 struct CholDagArgs {
   double* M;          // [npad][npad], strictly-lower tiles overwritten with L(i,j)^T (transposed inside the tile slot)
@@ -139,8 +219,10 @@ struct CholDagArgs {
   const double* rhs;  // [npad]
   double* y;          // [npad] solution
   double* yf;         // [npad] forward-solved right-hand side
-  double* part;       // [2][nb][nb][64] partial products of the forward / backward sweeps
-  int* flags;         // tile_ready[nb*nb] | bwd_ready[nb*nb] | (4 nb unused) | x_ready[nb] | fwd_ready[nb] | fwdp_ready[nb*nb]
+  double* part;       // messages of the two substitution sweeps, all self-validating words (this launch's parity):
+                      //   fwd_part[nb][nb][64] = L(i,k) x_k | bwd_part[nb][nb][64] = L(r,k)^T x_r | xf[nb][64] | xb[nb][64]
+  double* part_other; // the other parity (reset to sentinels by the writers at the end of this launch)
+  int* flags;         // tile_ready[nb*nb]: L(i,k) final and written (release / acquire, epoch valued)
   int epoch;
   LmScalars* scal;
 };
@@ -175,7 +257,7 @@ __device__ __forceinline__ void tile_matvec_t(const double* St, const double* v,
   __syncthreads();
   if (tid < kCholNB) {
     const double t = (red[tid] + red[kCholNB + tid]) + (red[2 * kCholNB + tid] + red[3 * kCholNB + tid]);
-    out_global[tid] = t;
+    st_relaxed1(out_global + tid, t);
     if (out_shared) out_shared[tid] = t;
   }
 }
@@ -184,8 +266,12 @@ __device__ __forceinline__ void tile_matvec_t(const double* St, const double* v,
 // of its diagonal-block factorisation AS THEY ARE PUBLISHED (one per 16 columns):  L(i,jc) = T L_jj^-T.
 // Result: S1 = L(i,jc)^T ([c][row] layout = the operand / publication layout).  slab_out != nullptr (sub-diagonal tile):
 // every finished 16-column slab P_s^T is streamed to the diagonal CTA of row i as self-validating words.
+// Ua / Ub != nullptr: the LAST GEMM update of the tile (operands L(i,j-1)^T, L(j,j-1)^T in [k][row] layout) is applied
+// lazily, 16 output columns at a time right before the step that needs them: the solve starts one quarter of a tile
+// product after its operands arrive instead of a whole one, which keeps this CTA in step with the factorisation.
 __device__ __forceinline__ void trsm_pipelined(Frag& acc, const Lane& L, double* S1, double* At, double* Bp2,
-                                               const double* Lpub_col, double* slab_out, int tid, int jstamp) {
+                                               const double* Lpub_col, double* slab_out, const double* Ua, const double* Ub,
+                                               int tid, int jstamp) {
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   // packet words of this thread: e = tid, tid + 256, tid + 512 of the 640 double2 of a full packet (16 rows x 40); the
   // last packet only carries the 16x16 inverse (128 double2).  Loads of packet s + 1 are IN FLIGHT while step s computes.
@@ -227,6 +313,12 @@ __device__ __forceinline__ void trsm_pipelined(Frag& acc, const Lane& L, double*
 #pragma unroll 1
   for (int s = 0; s < 4; ++s) {
     double* Bp = Bp2 + (s & 1) * kPacket;
+    // lazy last update, one slab AHEAD of the solve (slab 0 and 1 before the first packet is needed, slab s + 1 while
+    // packet s is in flight), so that nothing but the 16x16 product of step 3 follows the last packet
+    if (Ua) {
+      if (s == 0) mma_dispatch(slab_mask(warp, 0), acc, Ua + q * kTS + g, kTS, Ub + q * kTS + g, kTS, L, kCholNB / 4);
+      if (s < 3) mma_dispatch(slab_mask(warp, s + 1), acc, Ua + q * kTS + g, kTS, Ub + q * kTS + g, kTS, L, kCholNB / 4);
+    }
     // a. the 16 columns of step s (as updated so far) -> At[k][row]
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -276,26 +368,8 @@ __device__ __forceinline__ void trsm_pipelined(Frag& acc, const Lane& L, double*
       }
     }
     // d. trailing columns of the tile:  T[:, c] -= sum_k P_s[:, k] L_jj[c][16 s + k]  for c >= 16 (s + 1)
-    if (s < 3) {
-      const double* pp = S1 + (16 * s + q) * kTS + g;   // P_s^T[k0 + q][row]
-      const double* pl = Bp + q * kPS + g;              // Pt_s[k0 + q][c]
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        double av[2], bv[4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) av[mt] = -pp[4 * kk * kTS + 8 * L.rt[mt]];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) bv[nt] = pl[4 * kk * kPS + 8 * L.ct[nt]];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            if ((L.ct[nt] >> 1) > s)
-              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                           : "+d"(acc.c[mt][nt][0]), "+d"(acc.c[mt][nt][1]) : "d"(av[mt]), "d"(bv[nt]));
-          }
-      }
-    }
+    if (s < 3)  // A = P_s^T rows (S1), B = Pt_s (packet): K = 16
+      mma_dispatch(trailing_mask(warp, s), acc, S1 + (16 * s + q) * kTS + g, kTS, Bp + q * kPS + g, kPS, L, 4);
     // (Bp is double buffered and At / S1 rows are rewritten only after the next step's barrier)
     DSTAMP(16 + jstamp, 4 * s + 3);
   }
@@ -320,13 +394,12 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   const Lane L = lane_of(tid);
   const int npad = a.npad, nb = npad / kCholNB, epoch = a.epoch;
   int* tile_ready = a.flags;
-  int* bwd_ready = a.flags + nb * nb;
-  int* step_ready = a.flags + 2 * nb * nb;  // [nb][4]
-  int* x_ready = step_ready + 4 * nb;
-  int* fwd_ready = x_ready + nb;
-  int* fwdp_ready = fwd_ready + nb;         // [nb][nb] forward partial L(i,k) x_k written
-  double* fwd_part = a.part;                          // [i][k][64] = L(i,k) x_k
-  double* bwd_part = a.part + size_t(nb) * nb * kCholNB;  // [k][r][64] = L(r,k)^T x_r
+  const size_t nn = size_t(nb) * nb * kCholNB;
+  double* fwd_part = a.part;            // [i][k][64] = L(i,k) x_k
+  double* bwd_part = a.part + nn;       // [k][r][64] = L(r,k)^T x_r
+  double* xf_pub = a.part + 2 * nn;     // [j][64] forward-solved x_j
+  double* xb_pub = xf_pub + size_t(nb) * kCholNB;  // [j][64] solution x_j
+  const double sv = sentinel_value();
 
   const int cta = blockIdx.x;
   if (cta >= nb) {
@@ -338,7 +411,7 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     double* slot = a.M + size_t(i) * kCholNB * npad + j * kCholNB;
     Frag acc;
     frag_load_global(acc, slot, npad, L);
-    for (int k = 0; k < j; ++k) {
+    for (int k = 0; k + 1 < j; ++k) {
       wait_flags2(tile_ready + i * nb + k, tile_ready + j * nb + k, epoch);
       load_tile_cg(S1, a.M + size_t(i) * kCholNB * npad + k * kCholNB, npad, tid);
       load_tile_cg(S2, a.M + size_t(j) * kCholNB * npad + k * kCholNB, npad, tid);
@@ -346,27 +419,33 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
       tile_gemm_dmma<true>(S1, S2, acc, L);
       __syncthreads();
     }
+    if (j >= 1) {  // operands of the last update stay resident (D is unused by tile CTAs); applied lazily inside the solve
+      wait_flags2(tile_ready + i * nb + (j - 1), tile_ready + j * nb + (j - 1), epoch);
+      load_tile_cg(D, a.M + size_t(i) * kCholNB * npad + (j - 1) * kCholNB, npad, tid);
+      load_tile_cg(S2, a.M + size_t(j) * kCholNB * npad + (j - 1) * kCholNB, npad, tid);
+      __syncthreads();
+    }
     // L(i,j) = T L_jj^-T, 16 columns at a time behind the factorisation of block column j
-    trsm_pipelined(acc, L, S1, At, Bp, a.Lpub + size_t(j) * 4 * kPacketG, sub ? a.Spub + size_t(i) * 4 * 16 * 64 : nullptr, tid,
-                   sub ? i : -100);
+    trsm_pipelined(acc, L, S1, At, Bp, a.Lpub + size_t(j) * 4 * kPacketG, sub ? a.Spub + size_t(i) * 4 * 16 * 64 : nullptr,
+                   j >= 1 ? D : nullptr, S2, tid, sub ? i : -100);
     __syncthreads();
     store_tile_global(slot, npad, S1, tid);  // published transposed
-    post_flag(tile_ready + i * nb + j, epoch);  // the tile first: the updates of row i / column i wait for it
+    post_flag(tile_ready + i * nb + j, epoch);  // the updates of row i / column i wait for it
     if (!sub) {  // (the diagonal CTA of row i holds a copy of the sub-diagonal tile and forms these two products itself)
-      wait_flag(fwd_ready + j, epoch);
-      if (tid < kCholNB) vec[tid] = __ldcg(a.yf + j * kCholNB + tid);
+      if (tid < kCholNB) vec[tid] = ld_spin(xf_pub + j * kCholNB + tid);
       __syncthreads();
       tile_matvec_t(S1, vec, fwd_part + (size_t(i) * nb + j) * kCholNB, red, tid);
-      post_flag(fwdp_ready + i * nb + j, epoch);
       // backward sweep: L(i,j)^T x_i   (S1 row-major = L^T)
-      wait_flag(x_ready + i, epoch);
-      if (tid < kCholNB) vec[tid] = __ldcg(a.y + i * kCholNB + tid);
+      if (tid < kCholNB) vec[tid] = ld_spin(xb_pub + i * kCholNB + tid);
       __syncthreads();
       tile_matvec(S1, vec, bwd_part + (size_t(j) * nb + i) * kCholNB, tid);
-      post_flag(bwd_ready + i * nb + j, epoch);
-    } else {  // next launch of this engine: the slab slots of the other buffer must read as "not yet written"
+      // next launch of this engine: this CTA's message slots of the other buffer must read as "not yet written"
+      if (tid < kCholNB) {
+        a.part_other[(size_t(i) * nb + j) * kCholNB + tid] = sv;
+        a.part_other[nn + (size_t(j) * nb + i) * kCholNB + tid] = sv;
+      }
+    } else {
       double* o = a.Spub_other + size_t(i) * 4 * 16 * 64;
-      const double sv = __longlong_as_double(static_cast<long long>(kSentinel));
       for (int e = tid; e < 4 * 16 * 64 / 2; e += 256) *reinterpret_cast<double2*>(o + 2 * e) = make_double2(sv, sv);
     }
     return;
@@ -381,17 +460,12 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     wait_flag(tile_ready + j * nb + k, epoch);
     load_tile_cg(S2, a.M + size_t(j) * kCholNB * npad + k * kCholNB, npad, tid);
     __syncthreads();
-    tile_gemm_dmma<true, kCholNB, kGemmLowerOut>(S2, S2, accD, L);
+    mma_dispatch(lower_mask(tid >> 5), accD, S2 + L.q * kTS + L.g, kTS, S2 + L.q * kTS + L.g, kTS, L, kCholNB / 4);
     __syncthreads();
   }
   DSTAMP(j, 1);
   {  // right-hand side of block j for the forward substitution: the partials of the other owners, fixed
     // summation order; this CTA's own partial L(j,j-1) x_{j-1} is added after the factorisation (side job below)
-    if (tid < j - 1) {
-      const int* f = fwdp_ready + j * nb + tid;
-      while (ld_acquire(f) != epoch) {}
-    }
-    __syncthreads();
     const double sp = sum_partials(fwd_part + size_t(j) * nb * kCholNB, j >= 1 ? j - 1 : 0, kCholNB, red, tid);
     if (tid < kCholNB) vec[tid] = a.rhs[j * kCholNB + tid] - sp;
   }
@@ -417,23 +491,7 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
       __syncthreads();
       DSTAMP(j, 8 + s);
       if (s == 3) DSTAMP(j, 2);
-      const double* pp = S1 + (16 * s + L.q) * kTS + L.g;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        double av[2], dv[4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) av[mt] = -pp[4 * kk * kTS + 8 * L.rt[mt]];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dv[nt] = pp[4 * kk * kTS + 8 * L.ct[nt]];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            if (L.rt[mt] >= L.ct[nt])
-              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                           : "+d"(accD.c[mt][nt][0]), "+d"(accD.c[mt][nt][1]) : "d"(av[mt]), "d"(dv[nt]));
-          }
-      }
+      mma_dispatch(lower_mask(tid >> 5), accD, S1 + (16 * s + L.q) * kTS + L.g, kTS, S1 + (16 * s + L.q) * kTS + L.g, kTS, L, 4);
     }
     DSTAMP(j, 3);
   }
@@ -448,10 +506,8 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     if (j == 0) return;
     const int tt = tid - 32;  // 0..223
     if (step == 1 && tt < kCholNB) {
-      // x_{j-1} was published (fwd_ready) shortly after the last packet of column j-1: long ago by now
-      if (tt == 0) { while (ld_acquire(fwd_ready + (j - 1)) != epoch) {} }
-      asm volatile("bar.sync 2, 64;" ::: "memory");
-      vec2[tt] = __ldcg(a.yf + (j - 1) * kCholNB + tt);
+      // x_{j-1} was published shortly after the last packet of column j-1: long ago by now
+      vec2[tt] = ld_spin(xf_pub + (j - 1) * kCholNB + tt);
     } else if (step == 2 && tt < 128) {
       // own[r] = sum_c L(j,j-1)[r][c] x[c] = sum_c S1[c][r] x[c]; two lanes per row
       const int r = tt >> 1, pt = tt & 1;
@@ -485,41 +541,39 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   if (j >= 1 && tid < kCholNB) vec[tid] -= own[tid];
   __syncthreads();
   block_solve_packets<true>(Pk, vec, x16, tid);
-  if (tid < kCholNB) { a.yf[j * kCholNB + tid] = vec[tid]; vec2[tid] = vec[tid]; }
-  post_flag(fwd_ready + j, epoch);
-  DSTAMP(j, 6);
-
-  // backward sweep: x_j = L_jj^-T (yf_j - sum_{r > j} L(r,j)^T x_r)
-  // all partials of this block column: one polling thread per flag (the early ones cost a single L2 round trip in
-  // parallel instead of nb - 1 - j sequential ones), then one barrier
-  if (tid < nb - 1 - j) {
-    const int* f = bwd_ready + (j + 1 + tid) * nb + j;
-    while (ld_acquire(f) != epoch) {}
+  if (tid < kCholNB) {
+    st_relaxed1(xf_pub + j * kCholNB + tid, vec[tid]);  // the tile owners of column j spin on these words
+    a.yf[j * kCholNB + tid] = vec[tid];
+    vec2[tid] = vec[tid];
   }
-  __syncthreads();
+  DSTAMP(j, 6);
+  // explicit inverse of the diagonal block (into D, free since the factorisation): off the critical chain for every
+  // column but the last - the backward sweep arrives here much later - and it turns the backward solve of this block
+  // into one 64x64 product
+  inverse_from_packets(Pk, D, tid);
+
+  // backward sweep: x_j = L_jj^-T (yf_j - sum_{r > j} L(r,j)^T x_r); the partials are self-validating words
   {
     const double sp = sum_partials(bwd_part + (size_t(j) * nb + j + 1) * kCholNB, nb - 1 - j, kCholNB, red, tid);
     if (tid < kCholNB) vec[tid] = vec2[tid] - sp;
   }
   __syncthreads();
-  block_solve_packets<false>(Pk, vec, x16, tid);
-  if (tid < kCholNB) a.y[j * kCholNB + tid] = vec[tid];
-  if (j >= 1) {
-    // own sub-diagonal tile: L(j,j-1)^T x_j for column CTA j-1, published together with x_j (one fence for both:
-    // the next column of the backward chain waits for exactly this partial)
-    tile_matvec(S1, vec, bwd_part + (size_t(j - 1) * nb + j) * kCholNB, tid);  // S1 row-major = L(j,j-1)^T
-  }
+  tile_matvec_t(D, vec, xb_pub + j * kCholNB, red, tid, vec2);  // x_j = Xi^T v ; tile owners (j, k) spin on xb_pub
   __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    if (j >= 1) st_release(bwd_ready + j * nb + (j - 1), epoch);
-    st_release(x_ready + j, epoch);
+  if (j >= 1) {
+    // own sub-diagonal tile: L(j,j-1)^T x_j for diagonal CTA j-1, the next link of the backward chain
+    tile_matvec(S1, vec2, bwd_part + (size_t(j - 1) * nb + j) * kCholNB, tid);  // S1 row-major = L(j,j-1)^T
   }
+  if (tid < kCholNB) a.y[j * kCholNB + tid] = vec2[tid];
   DSTAMP(j, 7);
-  {  // next launch of this engine uses the other packet buffer: leave this column's slots there as sentinels
+  {  // next launch of this engine uses the other buffers: leave this CTA's slots there as sentinels
     double* o = a.Lpub_other + size_t(j) * 4 * kPacketG;
-    const double sv = __longlong_as_double(static_cast<long long>(kSentinel));
     for (int e = tid; e < 4 * kPacketG / 2; e += 256) *reinterpret_cast<double2*>(o + 2 * e) = make_double2(sv, sv);
+    if (tid < kCholNB) {
+      a.part_other[2 * nn + size_t(j) * kCholNB + tid] = sv;
+      a.part_other[2 * nn + size_t(nb + j) * kCholNB + tid] = sv;
+      if (j >= 1) a.part_other[nn + (size_t(j - 1) * nb + j) * kCholNB + tid] = sv;
+    }
   }
 }
 
@@ -528,13 +582,14 @@ static int dag_grid(int nb) { return nb * (nb + 1) / 2; }
 
 bool chol_dag_supported(int npad, int n_sm) { return dag_grid(npad / kCholNB) <= n_sm; }
 
-size_t chol_dag_part_len(int npad) {
+static size_t dag_part_half(int npad) {
   const size_t nb = npad / kCholNB;
-  return 2 * nb * nb * kCholNB;
+  return (2 * nb * nb + 2 * nb) * kCholNB;
 }
+size_t chol_dag_part_len(int npad) { return 2 * dag_part_half(npad); }
 size_t chol_dag_flags_len(int npad) {
   const size_t nb = npad / kCholNB;
-  return 3 * nb * nb + 6 * nb;
+  return nb * nb;
 }
 // [barrier kernel's block inverses npad x 64 | packets parity 0 | packets parity 1 | slabs parity 0 | slabs parity 1]
 static size_t dag_pub_len(int npad) { return size_t(npad / kCholNB) * 4 * (kPacketG + 16 * 64); }
@@ -545,10 +600,11 @@ __global__ void fill_sentinel_kernel(double* p, size_t n) {
   if (i < n) p[i] = __longlong_as_double(static_cast<long long>(kSentinel));
 }
 // both packet buffers start as sentinels (call once after (re)allocating the buffer, on the engine stream)
-int launch_chol_dag_init(double* linv_buf, int npad, cudaStream_t s) {
-  const size_t n = 2 * dag_pub_len(npad);
+int launch_chol_dag_init(double* linv_buf, double* part_buf, int npad, cudaStream_t s) {
+  const size_t n = 2 * dag_pub_len(npad), m = chol_dag_part_len(npad);
   fill_sentinel_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(linv_buf + size_t(npad) * kCholNB, n);
-  return 1;
+  fill_sentinel_kernel<<<unsigned((m + 255) / 256), 256, 0, s>>>(part_buf, m);
+  return 2;
 }
 
 int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
@@ -565,8 +621,10 @@ int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
   a.Lpub_other = pk + (parity ^ 1u) * half;
   a.Spub = pk + 2 * half + parity * shalf;
   a.Spub_other = pk + 2 * half + (parity ^ 1u) * shalf;
+  a.part = l.chol_part + parity * dag_part_half(l.npad);
+  a.part_other = l.chol_part + (parity ^ 1u) * dag_part_half(l.npad);
   a.rhs = l.rhs; a.y = l.y; a.yf = l.yf;
-  a.part = l.chol_part; a.flags = l.chol_flags; a.scal = l.scal;
+  a.flags = l.chol_flags; a.scal = l.scal;
   // process-wide unique, never 0 (flag buffers start zeroed); a wrap after 2^31 launches would need the flags of a
   // buffer to hold exactly the value 2^31 launches old: not a practical concern
   a.epoch = int(epoch_src.fetch_add(1, std::memory_order_relaxed) % 0x7ffffffeu) + 1;

@@ -494,4 +494,38 @@ __device__ __forceinline__ void block_solve_packets(const double* Pk, double* v,
   }
 }
 
+// Xi = L^-1 (lower triangular, row-major, row stride kTS, upper part zeroed) of the factored 64x64 block kept as its four
+// packets.  16x16 blocks: X[s][s] = X16_s ;  X[s][s'] = -X16_s * sum_{t = s'}^{s-1} L[s][t] X[t][s']  (s' < s), thread
+// (a, b) = one entry of a 16x16 block.  Not on the factorisation's critical chain (see the caller).
+__device__ __forceinline__ void inverse_from_packets(const double* Pk, double* Xi, int tid) {
+  const int a = tid >> 4, b = tid & 15;
+  for (int e = tid; e < kTile; e += 256) Xi[e] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < 4; ++s) Xi[(16 * s + a) * kTS + 16 * s + b] = b <= a ? Pk[s * kPacket + b * kPS + 64 + a] : 0.0;  // X16_s[a][b] = XT16_s[b][a]
+  __syncthreads();
+  __shared__ double W[16][17];
+#pragma unroll 1
+  for (int s = 1; s < 4; ++s)
+#pragma unroll 1
+    for (int sp = s - 1; sp >= 0; --sp) {
+      // W[a][b] = sum_{t = sp}^{s-1} sum_k L[16 s + a][16 t + k] X[16 t + k][16 sp + b] ;  L[row][16 t + k] = Pt_t[k][row]
+      double w = 0.0;
+      for (int t = sp; t < s; ++t) {
+        const double* Pt = Pk + t * kPacket;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) w = fma(Pt[k * kPS + 16 * s + a], Xi[(16 * t + k) * kTS + 16 * sp + b], w);
+      }
+      W[a][b] = w;
+      __syncthreads();
+      // X[s][sp][a][b] = -sum_{k <= a} X16_s[a][k] W[k][b]
+      const double* XT = Pk + s * kPacket + 64;
+      double x = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x = fma(k <= a ? XT[k * kPS + a] : 0.0, W[k][b], x);
+      Xi[(16 * s + a) * kTS + 16 * sp + b] = -x;
+      __syncthreads();
+    }
+}
+
 }  // namespace ctvio

@@ -346,9 +346,10 @@ int prepare(ctvio_engine* e) {
     for (int b = 0; b < 2; ++b) CUDA_OK(e->ne_slab[b].reserve(e->ne_slab_len));
     e->npad = ((d.np + kCholNB - 1) / kCholNB) * kCholNB;
     CUDA_OK(e->d_M.reserve(size_t(e->npad) * e->npad + 3 * size_t(e->npad)));  // M | rhs | diagA | yf (all-reduce slab)
-    if (chol_dag_lpub_len(e->npad) > e->d_Linv.cap || e->linv_npad != e->npad) {
+    if (chol_dag_lpub_len(e->npad) > e->d_Linv.cap || chol_dag_part_len(e->npad) > e->d_chol_part.cap || e->linv_npad != e->npad) {
       CUDA_OK(e->d_Linv.reserve(chol_dag_lpub_len(e->npad)));
-      e->launches += launch_chol_dag_init(e->d_Linv.p, e->npad, e->stream);  // packet buffers start as sentinels
+      CUDA_OK(e->d_chol_part.reserve(chol_dag_part_len(e->npad)));
+      e->launches += launch_chol_dag_init(e->d_Linv.p, e->d_chol_part.p, e->npad, e->stream);  // message words start as sentinels
       e->linv_npad = e->npad;
       e->chol_seq = 0;
     }
@@ -394,7 +395,6 @@ int prepare(ctvio_engine* e) {
       CUDA_OK(e->d_lis.reserve(e->nL));
       CUDA_OK(e->d_lc.reserve(e->nL));
     }
-    CUDA_OK(e->d_chol_part.reserve(chol_dag_part_len(e->npad)));
     if (chol_dag_flags_len(e->npad) > e->d_chol_flags.cap) {
       CUDA_OK(e->d_chol_flags.reserve(chol_dag_flags_len(e->npad)));
       CUDA_OK(cudaMemsetAsync(e->d_chol_flags.p, 0, e->d_chol_flags.cap * sizeof(int32_t), e->stream));

@@ -249,7 +249,7 @@ bool chol_dag_supported(int npad, int n_sm);
 size_t chol_dag_part_len(int npad);
 size_t chol_dag_flags_len(int npad);
 size_t chol_dag_lpub_len(int npad);  // doubles of LinearLaunch::Linv: [block inverses of the barrier kernel | 2 packet buffers]
-int launch_chol_dag_init(double* linv_buf, int npad, cudaStream_t s);  // packet buffers <- sentinels, once per allocation
+int launch_chol_dag_init(double* linv_buf, double* part_buf, int npad, cudaStream_t s);  // message buffers <- sentinels, once per allocation
 int launch_chol_dag(const LinearLaunch& a, cudaStream_t s);
 int launch_chol_coop(const LinearLaunch& a, cudaStream_t s);
 int launch_step_vectors(const LinearLaunch& a, cudaStream_t s);
