@@ -168,6 +168,58 @@ def algorithmic_bytes_visual(w):
     return 72 * w.n_obs + 408 * len(w.rho0) + (n_p * n_p + n_p) * 8
 
 
+VISUAL_KFLOP = 11.1  # ~6.0 kflop residual + analytic Jacobians (with the line-delay column) + ~5.1 kflop J'J
+
+
+def roofline_k1_fp64(w_n_obs, visual_ms, fp64_tflops):
+    """SURVEY 8(d) asks for K1's fp64 fraction next to its (by design tiny) HBM fraction: algorithmic flops of one
+    launch = 11.1 kflop per visual block, over the kernel's CUDA-event time, against the fp64 rate measured in-run."""
+    ach = VISUAL_KFLOP * 1e3 * w_n_obs / (visual_ms * 1e-3) / 1e12
+    return {"bound": "fp64", "achieved": ach, "peak": fp64_tflops, "unit": "TFLOP/s", "frac": ach / fp64_tflops,
+            "algorithmic_flops": VISUAL_KFLOP * 1e3 * w_n_obs, "kernel_ms": visual_ms, "kernel": "visual_kernel<true> (K1)"}
+
+
+def best_thread_count(lib, est, candidates, solve):
+    """The port's threaded residual assembly stops scaling well before the core count on small windows: calibrate."""
+    import ctypes as C
+    best = (float("inf"), 1)
+    for cand in candidates:
+        lib.raw("set_num_threads")(est.h, C.c_int32(cand))
+        est.RestoreState()
+        t0 = time.perf_counter()
+        solve()
+        best = min(best, (time.perf_counter() - t0, cand))
+    return best[1]
+
+
+def run_c3(lib, device, reps, is_oracle=False, threads=1):
+    """BASELINE configs[2]: the C2-scale window with the line delay free: solve(15), 4-DoF re-alignment, marginalization
+    of keyframe 0 (2 control points, bias node 0, the 100 landmarks anchored in it) into the next prior.  Wall-clock ms of
+    the two C-ABI calls, state resident (SaveState / RestoreState between repetitions)."""
+    import ctypes as C
+    st = importlib.import_module("ctrl-vio_b200.streaming")
+    e, seq, wa, nowk = st.c3_window_a(lib, device=device)
+    if is_oracle:
+        lib.raw("set_num_threads")(e.h, C.c_int32(threads))
+    R0 = syn.qrot(wa.q0[nowk][None], np.eye(3)).T.copy(); t0 = wa.p0[nowk].copy()
+    e.SaveState()
+    t_solve, t_marg, dev, n = [], [], [], None
+    for it in range(reps + (0 if is_oracle else 2)):
+        e.RestoreState()
+        a = time.perf_counter()
+        s = e.Solve(MAX_ITERS)
+        b = time.perf_counter()
+        e.GaugeRealign(nowk, R0, t0)
+        pr = e.SaveMarginalizationInfo()
+        c = time.perf_counter()
+        if is_oracle or it >= 2:
+            t_solve.append(b - a); t_marg.append(c - b); dev.append(s.device_ms)
+        n = pr.n
+    return {"solve_ms": 1e3 * float(np.mean(t_solve)), "marginalize_ms": 1e3 * float(np.mean(t_marg)),
+            "solve_device_ms": float(np.mean(dev)), "iterations": s.iterations, "prior_dim": n, "reps": len(t_solve),
+            "n_obs": wa.n_obs}
+
+
 def shard_window(w, rank, world):
     """Landmark-sharded view of a window: contiguous landmark ranges, global landmark ids kept (every rank holds the
     full inverse-depth array); IMU / bias factors stay on rank 0 (ctvio_comm_init contract)."""
@@ -176,7 +228,7 @@ def shard_window(w, rank, world):
     return (w.lm >= lo) & (w.lm < hi)
 
 
-def run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch):
+def run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch, fp64_tflops=None):
     """BASELINE configs[3]: C4 with residuals sharded by landmark over `world` GPUs; one NCCL all-reduce of the
     reduced camera system [M | rhs | diag] per LM step + one of 6 scalars per evaluation."""
     w4 = syn.config_c4()
@@ -211,33 +263,88 @@ def run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch):
            "unit": "evals/s", "lm_iters_per_s": iters / tot_s, "solve_ms": 1e3 * tot_s / len(ms),
            "ms_per_lm_iter": 1e3 * tot_s / iters, "final_cost": s4.final_cost,
            "parallelism": f"landmark shards x{world}, NCCL all-reduce of the reduced system per LM step"}
+    # K1 on this rank's shard (every N): algorithmic bytes / flops of the shard over the kernel's CUDA-event time
+    n_shard = int(sel.sum())
     if world == 1:
         prof4 = est.ProfileKernels(reps=10, flush_l2=True)
-        peaks, how = measured_peaks()
-        ach4 = algorithmic_bytes_visual(w4) / (prof4["visual"] * 1e-3) / 1e9
         out["stage_ms"] = prof4
-        out["roofline_visual"] = {"bound": "hbm", "achieved": ach4, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                  "frac": ach4 / peaks["hbm_gbs"], "algorithmic_bytes": algorithmic_bytes_visual(w4)}
+        vis_ms = prof4["visual"]
+    else:
+        vis_ms = est.ProfileVisual(reps=10, flush_l2=True)
+    peaks, how = measured_peaks()
+    n_p = 6 * w4.n_knots + 6 * len(w4.kf_times) + 1
+    lm_shard = len(np.unique(w4.lm[sel]))
+    alg = 72 * n_shard + 408 * lm_shard + (n_p * n_p + n_p) * 8
+    ach4 = alg / (vis_ms * 1e-3) / 1e9
+    out["roofline_visual"] = {"bound": "hbm", "achieved": ach4, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                              "frac": ach4 / peaks["hbm_gbs"], "algorithmic_bytes": alg, "kernel_ms": vis_ms,
+                              "obs_on_this_rank": n_shard, "rank": rank}
+    out["roofline_visual_fp64"] = roofline_k1_fp64(n_shard, vis_ms, fp64_tflops) if fp64_tflops else None
     del est
     return out
 
 
-def run_c5_streaming(lib, n_windows, device):
-    """BASELINE configs[4]: streaming sliding window at 20 Hz keyframes, end-to-end ms per window through the public
-    API with host buffers (state + factors + prior re-uploaded every window like the reference rebuilds its problem;
-    solve(8) -> gauge re-alignment -> marginalization -> state read-back all inside the timed region)."""
+def cpu_c4_baseline(budget_s):
+    """Oracle on the full C4 window: one solve(15) single-threaded (the reference's num_threads = 1) and one at the best
+    thread count (bounded sample: the solve takes seconds)."""
+    import ctypes as C
+    w4 = syn.config_c4()
+    lib = oracle_lib()
+    est = pkg.setup_estimator(lib, w4)
+    est.SaveState()
+    out = {}
+    ncpu = os.cpu_count() or 1
+    for label, threads in (("threads_1", 1), ("threads_best", None)):
+        if threads is None:
+            threads = best_thread_count(lib, est, [c for c in (4, 8, 16, 32) if c <= ncpu] or [1], lambda: est.Solve(2))
+        lib.raw("set_num_threads")(est.h, C.c_int32(threads))
+        est.RestoreState()
+        t0 = time.perf_counter()
+        s = est.Solve(MAX_ITERS)
+        dt = time.perf_counter() - t0
+        out[label] = {"cores": threads, "solve_ms": 1e3 * dt, "value": w4.n_residual_blocks * s.num_jacobian_evals / dt,
+                      "unit": "evals/s", "iterations": s.iterations, "final_cost": s.final_cost}
+    out["kind"] = "port"
+    out["sample"] = "1 x solve(15) of the full C4 window per thread count"
+    return out
+
+
+def c5_summary(records, skip):
+    r = records[skip:]
+    ms = np.array([x["ms"] for x in r])
+    f = lambda k: float(np.mean([x[k] for x in r]))
+    return {"windows": len(r), "ms_per_window_mean": float(ms.mean()), "ms_per_window_p50": float(np.median(ms)),
+            "ms_per_window_p99": float(np.percentile(ms, 99)), "ms_build_and_predict_mean": f("ms_build_and_predict"),
+            "ms_solve_mean": f("ms_solve"), "ms_realign_marginalize_mean": f("ms_realign_marginalize"),
+            "ms_readback_mean": f("ms_readback"), "solve_device_ms_mean": f("device_ms"),
+            "init_device_ms_mean": f("init_device_ms"), "lm_iterations_mean": f("iterations"),
+            "h2d_bytes_per_window": f("h2d_bytes"), "d2h_bytes_per_window": f("d2h_bytes")}
+
+
+def run_c5_streaming(lib, n_windows, device, cpu_windows):
+    """BASELINE configs[4]: streaming sliding window at 20 Hz keyframes through the reference's per-image cycle
+    (ExtendTrajectory -> InitTrajectory Solve(8) with fixed control points -> UpdateTrajectory Solve(15) -> 4-DoF
+    re-alignment -> marginalization of the oldest keyframe -> slide), end-to-end ms per window through the public API with
+    host buffers, everything that crosses the C-ABI inside the timed region.  The CPU oracle runs the IDENTICAL cycle on
+    the first `cpu_windows` windows of the same sequence (bounded sample), single-threaded like the reference."""
     st = importlib.import_module("ctrl-vio_b200.streaming")
     seq = st.config_c5_sequence(n_windows)
-    r = st.StreamingRunner(lib, seq, iters=8, device=device)
+    r = st.StreamingRunner(lib, seq, device=device)
     r.run(n_windows)
-    ms = np.array([x["ms"] for x in r.records[3:]])  # the first windows include allocation / module load
-    dev = np.array([x["device_ms"] for x in r.records[3:]])
-    return {"workload": f"C5: {n_windows} windows of 11 keyframes @20 Hz, {r.records[-1]['n_obs']} RS obs, "
-                        f"{r.records[-1]['n_knots']} ctrl pts, prior dim {r.records[-1]['prior_dim']}, solve(8) + re-align + marginalize",
-            "ms_per_window_mean": float(ms.mean()), "ms_per_window_median": float(np.median(ms)),
-            "ms_per_window_p99": float(np.percentile(ms, 99)), "solve_device_ms_mean": float(dev.mean()),
-            "windows_per_s": float(1e3 / ms.mean()), "realtime_factor_at_20hz": float(50.0 / ms.mean()),
-            "final_cost_last": r.records[-1]["final_cost"]}
+    last = r.records[-1]
+    out = {"workload": f"C5: {n_windows} windows of 11 keyframes @20 Hz, ~{last['n_obs']} RS obs, {last['n_imu']} IMU samples, "
+                       f"{last['n_knots']} ctrl pts, prior dim {last['prior_dim']}; per window: IMU-only predictor solve(8) + "
+                       f"solve({MAX_ITERS}) + re-align + marginalize + slide",
+           "gpu": c5_summary(r.records, min(5, n_windows // 2)), "final_cost_last": last["final_cost"],
+           "rms_translation_error_vs_truth_m": r.state_error()}
+    out["gpu"]["realtime_factor_at_20hz"] = 50.0 / out["gpu"]["ms_per_window_mean"]
+    if cpu_windows > 0:
+        ro = st.StreamingRunner(oracle_lib(), seq)
+        ro.run(min(cpu_windows, n_windows))
+        out["cpu_baseline"] = dict(c5_summary(ro.records, 1), cores=1, kind="port",
+                                   sample=f"the first {len(ro.records)} windows of the same sequence, identical cycle")
+        out["speedup_ms_per_window"] = out["cpu_baseline"]["ms_per_window_mean"] / out["gpu"]["ms_per_window_mean"]
+    return out
 
 
 def run_reference(args, rank, world):
@@ -295,7 +402,9 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--c5-windows", type=int, default=60)
+    ap.add_argument("--c5-windows", type=int, default=1000)
+    ap.add_argument("--c5-cpu-windows", type=int, default=40)
+    ap.add_argument("--no-c3", action="store_true")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ctvio", choices=["ctvio", "reference"])
@@ -394,10 +503,23 @@ def main():
     # ---------------- kernel stage timings + roofline of the dominant kernel ----------------
     prof = est.ProfileKernels(reps=20, flush_l2=True) if rank == 0 else None
     fp64_tflops = est.MeasureFp64Tflops() if rank == 0 else None
+    if world > 1:  # every rank needs the measured fp64 rate for its shard's K1 fraction
+        fp64_tflops = est.MeasureFp64Tflops()
     c4 = None
+    c4_clocks = None
     if not args.no_c4:
-        c4 = run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch)
-    c5 = run_c5_streaming(lib, args.c5_windows, local_rank) if (rank == 0 and args.c5_windows > 0) else None
+        s4 = ClockSampler(local_rank); s4.start()
+        c4 = run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch, fp64_tflops)
+        c4_clocks = s4.stop()
+        c4["clocks"] = c4_clocks
+    c3 = c5 = None
+    if rank == 0 and not args.no_c3:
+        c3 = {"workload": "C3: C2-scale window (30 ctrl pts, 2700 RS obs, 270 IMU), line delay free, solve(15) + re-align + "
+                          "marginalize keyframe 0", "gpu": run_c3(lib, local_rank, 10)}
+    if rank == 0 and args.c5_windows > 0:
+        s5 = ClockSampler(local_rank); s5.start()
+        c5 = run_c5_streaming(lib, args.c5_windows, local_rank, args.c5_cpu_windows if world == 1 else 0)
+        c5["clocks"] = s5.stop()
 
     # ---------------- reduce over ranks ----------------
     t = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64, device="cuda")
@@ -419,11 +541,13 @@ def main():
         ach_tf = chol_flops / (prof["cholesky_solve"] * 1e-3) / 1e12
         alg = algorithmic_bytes_visual(w)
         ach = alg / (prof["visual"] * 1e-3) / 1e9
-        traffic, traffic_k1 = None, None
+        traffic, traffic_k1, traffic_src = None, None, None
         try:
             with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
                 tj = json.load(f)
                 traffic, traffic_k1 = tj.get("c2_chol_dag_dram_bytes_per_launch"), tj.get("c2_visual_dram_bytes_per_launch")
+                traffic_src = "STATIC: dram__bytes_read+write per launch from the committed ncu --set full capture " + \
+                              str(tj.get("source", "profiles/kernel_traffic.json")) + " (not re-measured in this run)"
         except Exception:
             pass
         cpu1 = cpu_solve_rate(w, 1, args.cpu_budget_s) if world == 1 else None
@@ -442,15 +566,18 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": fp64_tflops, "unit": "TFLOP/s",
-                         "frac": ach_tf / fp64_tflops, "traffic": traffic, "kernel": "chol_dag_kernel (K5)",
+                         "frac": ach_tf / fp64_tflops, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "chol_dag_kernel (K5)",
                          "peak_source": "fp64 DFMA/DMMA rate measured in this run (ctvio_measure_fp64_tflops); "
                                         "MEASURED_PEAKS.json has no fp64 figure",
                          "algorithmic_flops": chol_flops, "kernel_ms": prof["cholesky_solve"],
                          "note": "serial pivot chain of an n=%d factorisation: latency bound, not pipe bound "
-                                 "(floor ~126 cycles per column, see DESIGN.md)" % n_p},
+                                 "(floor ~126 cycles per column = %.1f us, see DESIGN.md)" % (n_p, n_p * 126 / 1.965e3)},
             "roofline_k1": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": ach / peaks["hbm_gbs"], "traffic": traffic_k1, "kernel": "visual_kernel<true> (K1)",
-                            "peak_source": how, "algorithmic_bytes": alg, "kernel_ms": prof["visual"]},
+                            "peak_source": how, "algorithmic_bytes": alg, "kernel_ms": prof["visual"],
+                            "traffic_source": traffic_src},
+            "roofline_k1_fp64": roofline_k1_fp64(w.n_obs, prof["visual"], fp64_tflops),
             "stage_ms": prof,
             "fp64_peak_tflops_measured": fp64_tflops,
             "solver": {"iterations": summ.iterations, "jacobian_passes": summ.num_jacobian_evals,
@@ -467,7 +594,15 @@ def main():
                                     "multi_thread": {"cores": nmt, "value": cpu_all["evals_per_s"],
                                                   "solve_ms": cpu_all["solve_ms"]}}
         if c4 is not None:
+            if world == 1:
+                c4["cpu_baseline"] = cpu_c4_baseline(args.cpu_budget_s)
             line["c4"] = c4
+        if c3 is not None:
+            if world == 1:
+                c3["cpu_baseline"] = dict(run_c3(oracle_lib(), 0, 3, is_oracle=True, threads=1), cores=1, kind="port")
+                c3["speedup_solve"] = c3["cpu_baseline"]["solve_ms"] / c3["gpu"]["solve_ms"]
+                c3["speedup_marginalize"] = c3["cpu_baseline"]["marginalize_ms"] / c3["gpu"]["marginalize_ms"]
+            line["c3"] = c3
         if c5 is not None:
             line["c5"] = c5
         print(json.dumps(line), flush=True)

@@ -379,6 +379,12 @@ class Estimator:
         names = ["visual", "imu", "small", "reduced_schur", "cholesky_solve", "step_vectors", "apply_table", "visual_cost"]
         return dict(zip(names, out.tolist()))
 
+    def ProfileVisual(self, reps=20, flush_l2=True):
+        """K1 only (sharded engines: the other stages involve collectives)."""
+        out = np.zeros(8)
+        self.lib.call("profile_kernels", self.h, C.c_int32(-reps), C.c_int32(int(flush_l2)), _dp(out))
+        return float(out[0])
+
     def SelfcheckSolver(self, reps=50):
         """(bitwise mismatches over `reps` repeated solves of the same reduced system, relative residual)."""
         mm, res = C.c_int32(), C.c_double()

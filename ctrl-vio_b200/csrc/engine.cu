@@ -160,7 +160,7 @@ struct ctvio_engine {
   struct MargWs {
     DevBuf<int32_t> pos_cam, pos_lm, prior_pos, marg_img, marg_imu;
     DevBuf<int2> bij;
-    DevBuf<double> Jrow, bs, A, b, Amm, V, ev, Vs, Ainv, T, Ap, bp, Ap2, V2, ev2, vb, J, r;
+    DevBuf<double> eig_scratch, Jrow, bs, A, b, Amm, V, ev, Vs, Ainv, T, Ap, bp, Ap2, V2, ev2, vb, J, r;
   } mws;
 
   // multi-GPU
@@ -1403,7 +1403,9 @@ int ctvio_triangulate(ctvio_handle e, int32_t n_frames, const double* Rs, const 
 }
 
 int ctvio_profile_kernels(ctvio_handle e, int32_t reps, int32_t flush_l2, double* out) {
-  if (!e || !out || reps <= 0) return fail(CTVIO_ERR_INVALID, "bad argument");
+  if (!e || !out || reps == 0) return fail(CTVIO_ERR_INVALID, "bad argument");
+  const bool visual_only = reps < 0;  // reps < 0: only out_ms[0] (K1) - usable on a sharded engine (no collectives)
+  if (visual_only) reps = -reps;
   cudaSetDevice(e->cfg.device);
   int rc = prepare(e);
   if (rc) return rc;
@@ -1413,6 +1415,25 @@ int ctvio_profile_kernels(ctvio_handle e, int32_t reps, int32_t flush_l2, double
   DevBuf<unsigned char> flush;
   const size_t flush_bytes = size_t(256) << 20;
   if (flush_l2) CUDA_OK(flush.reserve(flush_bytes));
+  if (visual_only) {
+    for (int k = 0; k < 8; ++k) out[k] = 0.0;
+    double total = 0;
+    for (int it = -3; it < reps; ++it) {
+      if (flush_l2) cudaMemsetAsync(flush.p, it & 0xff, flush_bytes, st);
+      cudaMemsetAsync(e->ne_slab[cur].p, 0, e->ne_slab_len * sizeof(double), st);
+      cudaEventRecord(e->ev0, st);
+      launch_visual(visual_launch(e, cur, cur, e->cfg.cauchy_solve), true, st);
+      cudaEventRecord(e->ev1, st);
+      if (cudaEventSynchronize(e->ev1) != cudaSuccess) return fail(CTVIO_ERR_CUDA, "kernel failed while profiling");
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+      if (it >= 0) total += ms;
+    }
+    out[0] = total / reps;
+    cudaMemsetAsync(&e->d_scal.p->error_flags, 0, sizeof(int32_t), st);
+    CUDA_OK(cudaStreamSynchronize(st));
+    return CTVIO_OK;
+  }
   // a valid linearisation + step so that every stage has meaningful inputs
   evaluate(e, cur, cur, true);
   LinearLaunch lin = linear_launch(e, cur);
@@ -1696,7 +1717,8 @@ int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
     CUDA_OK(d_Amm.reserve(size_t(m) * m)); CUDA_OK(d_V.reserve(size_t(m) * m)); CUDA_OK(d_ev.reserve(m));
     CUDA_OK(d_Vs.reserve(size_t(m) * m)); CUDA_OK(d_Ainv.reserve(size_t(m) * m)); CUDA_OK(d_T.reserve(size_t(n) * m));
     e->launches += ctvio::launch_marg_elementwise(0, m, P, d_A.p, d_Amm.p, nullptr, nullptr, nullptr, eps, st);
-    e->launches += ctvio::launch_jacobi_eig(d_Amm.p, d_V.p, d_ev.p, m, st);
+    CUDA_OK(ws.eig_scratch.reserve(ctvio::jacobi_log_bytes(std::max(m, n), 40) / sizeof(double) + 1));
+    e->launches += ctvio::launch_jacobi_eig(d_Amm.p, d_V.p, d_ev.p, m, ws.eig_scratch.p, st);
     e->launches += ctvio::launch_marg_elementwise(1, m, m, d_V.p, d_Vs.p, d_ev.p, nullptr, nullptr, eps, st);
     e->launches += ctvio::launch_dense_gemm(m, m, m, 1.0, d_Vs.p, m, false, d_V.p, m, true, 0.0, d_Ainv.p, m, st);
     // T = Arm * Amm_inv ; A' = Arr - T * Amr ; b' = brr - T * bmm
@@ -1707,7 +1729,8 @@ int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
   CUDA_OK(d_Ap2.reserve(size_t(n) * n)); CUDA_OK(d_V2.reserve(size_t(n) * n)); CUDA_OK(d_ev2.reserve(n));
   CUDA_OK(d_vb.reserve(n)); CUDA_OK(d_J.reserve(size_t(n) * n)); CUDA_OK(d_r.reserve(n));
   e->launches += ctvio::launch_marg_elementwise(2, n, n, d_Ap.p, d_Ap2.p, nullptr, nullptr, nullptr, eps, st);
-  e->launches += ctvio::launch_jacobi_eig(d_Ap2.p, d_V2.p, d_ev2.p, n, st);
+  CUDA_OK(ws.eig_scratch.reserve(ctvio::jacobi_log_bytes(n, 40) / sizeof(double) + 1));
+  e->launches += ctvio::launch_jacobi_eig(d_Ap2.p, d_V2.p, d_ev2.p, n, ws.eig_scratch.p, st);
   e->launches += ctvio::launch_dense_gemm(n, 1, n, 1.0, d_V2.p, n, true, d_bp.p, 1, false, 0.0, d_vb.p, 1, st);
   e->launches += ctvio::launch_marg_elementwise(3, n, n, d_V2.p, d_J.p, d_ev2.p, d_vb.p, d_r.p, eps, st);
   rc = read_scalars(e);

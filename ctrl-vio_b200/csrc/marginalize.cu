@@ -416,30 +416,62 @@ __global__ void __launch_bounds__(1024) jacobi_eig_smem_kernel(double* Ag, doubl
 // V <- V J rides in the same phase.  The (k, l) -> thread assignment does not depend on the round, so the index
 // arithmetic is hoisted out of the sweep loop.  Rotation sequence and every sum are fixed: bit-reproducible.
 // A_SMEM / V_SMEM: the matrix / the eigenvectors live in shared memory (odd row stride) or stay in global memory (L2).
-template <bool A_SMEM, bool V_SMEM>
-__global__ void __launch_bounds__(1024) jacobi_eig_block_kernel(double* Ag, double* Vg, double* ev, int n, int max_sweeps) {
+__device__ int g_jacobi_dbg[8];  // [0] sweeps, [1] n of the last eigen-decomposition (tools/marg_timing.py)
+extern "C" int ctvio_debug_jacobi(int* out8) { return cudaMemcpyFromSymbol(out8, g_jacobi_dbg, sizeof(g_jacobi_dbg)) == cudaSuccess ? 0 : -1; }
+
+// full-precision 1/x and 1/sqrt(x) from the hardware seeds + Newton steps: the rotation parameters sit on the serial
+// part of every round (43 threads compute, 1000 wait), IEEE division / sqrt sequences are 3x longer
+__device__ __forceinline__ double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-(y * y), x, 1.0);
+  y = fma(fma(e, 0.375, 0.5), y * e, y);
+  e = fma(-(y * y), x, 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+
+// Rotation log entry of one pair of one round: V <- V J is NOT done inside the eigenvalue kernel.  Every row of V
+// transforms independently of the others (row r: (v_p, v_q) <- (c v_p - s v_q, s v_p + c v_q) for the pairs of the round),
+// so the eigenvalue kernel (one CTA, A only: half the shared-memory traffic and instructions per round) just logs
+// (p, q, c, s), and a second kernel with one CTA PER ROW of V replays the log on a row of the identity - n SMs instead of
+// one for the eigenvector half of the work, ~50 us for the n = 85 prior of a streaming window.
+struct JacobiRot {
+  int p, q;
+  double c, s;
+};
+
+template <bool A_SMEM>
+__global__ void __launch_bounds__(1024) jacobi_eig_block_kernel(double* Ag, double* ev, JacobiRot* log, int* log_rounds, int n,
+                                                                int max_sweeps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int ne = (n + 1) & ~1, npairs = ne / 2;
-  const int lda = A_SMEM ? (n | 1) : n, ldv = V_SMEM ? (n | 1) : n;
+  const int lda = A_SMEM ? (n | 1) : n;
   double* sm = reinterpret_cast<double*>(smem_raw);
   double* A = A_SMEM ? sm : Ag;
-  double* V = V_SMEM ? sm + (A_SMEM ? size_t(n) * lda : 0) : Vg;
-  double* cs = sm + (A_SMEM ? size_t(n) * lda : 0) + (V_SMEM ? size_t(n) * ldv : 0);  // [npairs][2]
-  int* pq = reinterpret_cast<int*>(cs + 2 * npairs);                                  // [npairs][2]
+  double* cs = sm + (A_SMEM ? size_t(n) * lda : 0);   // [npairs][2]
+  int* pq = reinterpret_cast<int*>(cs + 2 * npairs);  // [npairs][2]
   __shared__ double s_off, s_diag, s_prev;
-  for (int e = tid; e < n * n; e += nt) {
-    const int i = e / n, j = e - i * n;
-    if (A_SMEM) A[i * lda + j] = Ag[e];
-    V[i * ldv + j] = (i == j) ? 1.0 : 0.0;
-  }
-  // fixed work assignment: A blocks (k, l), k <= l (the mirror block is written by the same thread), and V row pairs
-  constexpr int kMaxBlk = 12, kMaxV = 24;
+  int sweeps_done = 0, rounds_done = 0;
+  if (A_SMEM)
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e - i * n;
+      A[i * lda + j] = Ag[e];
+    }
+  // fixed work assignment: A blocks (k, l), k <= l (the mirror block is written by the same thread)
+  constexpr int kMaxBlk = 12;
   const int nblk_total = npairs * (npairs + 1) / 2;
   short bk[kMaxBlk], bl[kMaxBlk];
   int nblk = 0;
   for (int b = tid; b < nblk_total && nblk < kMaxBlk; b += nt) {
-    // b -> (k, l) with k <= l, row-major over the upper triangle
     int k = 0, rem = b;
     while (rem >= npairs - k) { rem -= npairs - k; ++k; }
     bk[nblk] = short(k); bl[nblk] = short(k + rem);
@@ -469,8 +501,9 @@ __global__ void __launch_bounds__(1024) jacobi_eig_block_kernel(double* Ag, doub
     if (s_off <= 1e-60 || s_off <= 1e-30 * s_diag || (s_off <= 1e-24 * s_diag && s_off > 0.5 * prev)) break;
     __syncthreads();
     if (tid == 0) s_prev = s_off;
+    ++sweeps_done;
     for (int round = 0; round < ne - 1; ++round) {
-      // ---- phase R: the round's pairs (round-robin tournament) and their rotations ----
+      // ---- phase R: the round's pairs (round-robin tournament), their rotations, the log entry ----
       for (int k = tid; k < npairs; k += nt) {
         int p, q;
         if (k == 0) { p = ne - 1; q = round % (ne - 1); }
@@ -481,27 +514,31 @@ __global__ void __launch_bounds__(1024) jacobi_eig_block_kernel(double* Ag, doub
           const double apq = A[p * lda + q];
           if (apq != 0.0) {
             const double app = A[p * lda + p], aqq = A[q * lda + q];
-            const double theta = (aqq - app) / (2.0 * apq);
-            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            c = 1.0 / sqrt(t * t + 1.0);
-            s = t * c;
+            const double theta = 0.5 * (aqq - app) * rcp_fast(apq);
+            const double h = fma(theta, theta, 1.0);
+            if (isfinite(h)) {
+              const double t = copysign(1.0, theta) * rcp_fast(fabs(theta) + h * rsqrt_fast(h));
+              c = rsqrt_fast(fma(t, t, 1.0));
+              s = t * c;
+            }  // |theta| ~ 1e154+: the rotation is the identity to working precision
           }
         } else {
           q = -1;  // dummy player of an odd n: the pair is idle
         }
         cs[2 * k] = c; cs[2 * k + 1] = s;
         pq[2 * k] = p; pq[2 * k + 1] = q;
+        log[size_t(rounds_done) * npairs + k] = JacobiRot{p, q, c, s};
       }
+      ++rounds_done;
       __syncthreads();
-      // ---- phase U: every 2x2 block B(k,l) <- R_k' B R_l  (and its mirror), V <- V R ----
+      // ---- phase A: every 2x2 block B(k,l) <- R_k' B R_l  (and its mirror) ----
 #pragma unroll 1
       for (int w = 0; w < nblk; ++w) {
         const int k = bk[w], l = bl[w];
         const int pk = pq[2 * k], qk = pq[2 * k + 1], pl = pq[2 * l], ql = pq[2 * l + 1];
         const double ck = cs[2 * k], sk = cs[2 * k + 1], cl = cs[2 * l], sl = cs[2 * l + 1];
         if (qk < 0 && ql < 0) continue;
-        // entries with an idle (dummy) partner: only the real row / column exists
-        const bool hk = qk >= 0, hl = ql >= 0;
+        const bool hk = qk >= 0, hl = ql >= 0;  // an idle (dummy) partner: only the real row / column exists
         const double b00 = A[pk * lda + pl];
         const double b01 = hl ? A[pk * lda + ql] : 0.0;
         const double b10 = hk ? A[qk * lda + pl] : 0.0;
@@ -522,50 +559,86 @@ __global__ void __launch_bounds__(1024) jacobi_eig_block_kernel(double* Ag, doub
           if (hk && hl) A[ql * lda + qk] = r11;
         }
       }
-      {
-        const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
-        for (int k = warp; k < npairs; k += nwarps) {
-          const int p = pq[2 * k], q = pq[2 * k + 1];
-          const double c = cs[2 * k], s = cs[2 * k + 1];
-          if (q < 0 || s == 0.0) continue;
-          for (int r = lane; r < n; r += 32) {
-            const double vp = V[r * ldv + p], vq = V[r * ldv + q];
-            V[r * ldv + p] = c * vp - s * vq;
-            V[r * ldv + q] = s * vp + c * vq;
-          }
+      __syncthreads();
+    }
+  }
+  if (A_SMEM)
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e - i * n;
+      Ag[e] = A[i * lda + j];
+    }
+  for (int i = tid; i < n; i += nt) ev[i] = A[i * lda + i];
+  if (tid == 0) {
+    *log_rounds = rounds_done;
+    g_jacobi_dbg[0] = sweeps_done; g_jacobi_dbg[1] = n; g_jacobi_dbg[2] = int(-log10(fmax(s_off / fmax(s_diag, 1e-300), 1e-300)));
+  }
+}
+
+// V = product of the logged rotations, one CTA per row of V (= row of the identity pushed through the log): thread k
+// applies pair k of every round to the row held in shared memory; the pairs of a round are disjoint.  The log is staged
+// through shared memory in chunks of kLogChunk rounds (coalesced bulk loads: one L2 round trip per chunk, not per round).
+constexpr int kLogChunk = 16;
+__global__ void __launch_bounds__(128) jacobi_apply_log_kernel(const JacobiRot* __restrict__ log, const int* log_rounds, int n,
+                                                               double* Vg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int npairs = ((n + 1) & ~1) / 2;
+  double* row = reinterpret_cast<double*>(smem_raw);                                    // [n]
+  JacobiRot* stage = reinterpret_cast<JacobiRot*>(row + ((n + 1) & ~1));                // [kLogChunk][npairs]
+  const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  for (int j = tid; j < n; j += nt) row[j] = j == r ? 1.0 : 0.0;
+  const int rounds = *log_rounds;
+  for (int t0 = 0; t0 < rounds; t0 += kLogChunk) {
+    const int nr = min(kLogChunk, rounds - t0);
+    __syncthreads();
+    {  // JacobiRot = 24 bytes = 3 doubles: straight copy as doubles
+      const double* src = reinterpret_cast<const double*>(log + size_t(t0) * npairs);
+      double* dst = reinterpret_cast<double*>(stage);
+      for (int e = tid; e < nr * npairs * 3; e += nt) dst[e] = src[e];
+    }
+    __syncthreads();
+    for (int t = 0; t < nr; ++t) {
+      for (int k = tid; k < npairs; k += nt) {
+        const JacobiRot g = stage[t * npairs + k];
+        if (g.q >= 0 && g.s != 0.0) {
+          const double vp = row[g.p], vq = row[g.q];
+          row[g.p] = g.c * vp - g.s * vq;
+          row[g.q] = g.s * vp + g.c * vq;
         }
       }
       __syncthreads();
     }
   }
-  for (int e = tid; e < n * n; e += nt) {
-    const int i = e / n, j = e - i * n;
-    if (A_SMEM) Ag[e] = A[i * lda + j];
-    if (V_SMEM) Vg[e] = V[i * ldv + j];
-  }
-  for (int i = tid; i < n; i += nt) ev[i] = A[i * lda + i];
+  for (int j = tid; j < n; j += nt) Vg[size_t(r) * n + j] = row[j];
 }
 
-int launch_jacobi_eig(double* A, double* V, double* ev, int n, cudaStream_t s) {
+size_t jacobi_log_bytes(int n, int max_sweeps) {
+  const int ne = (n + 1) & ~1;
+  return size_t(max_sweeps) * (ne - 1) * (ne / 2) * sizeof(JacobiRot) + 64;
+}
+
+int launch_jacobi_eig(double* A, double* V, double* ev, int n, void* log_buf, cudaStream_t s) {
   if (n <= 0) return 0;
+  constexpr int kMaxSweeps = 40;
   const int ne = (n + 1) & ~1, npairs = ne / 2;
   const size_t pairs = size_t(npairs) * (2 * sizeof(double) + 2 * sizeof(int));
   const size_t mat = size_t(n) * (n | 1) * sizeof(double);
   const size_t limit = 224 * 1024;
-  static PerDeviceOnce once;
-  if (once.first()) {
-    cudaFuncSetAttribute(jacobi_eig_block_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit));
-    cudaFuncSetAttribute(jacobi_eig_block_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit));
-  }
-  // per-thread block slots: npairs (npairs + 1) / 2 blocks over 1024 threads, at most 12 each -> n <= ~310
-  if (size_t(npairs) * (npairs + 1) / 2 > size_t(12) * 1024) {
+  // per-thread block slots: npairs (npairs + 1) / 2 blocks over 1024 threads, at most 12 each (n <= ~310); 2 pairs per
+  // thread in the replay kernel (n <= 512)
+  if (size_t(npairs) * (npairs + 1) / 2 > size_t(12) * 1024 || !log_buf) {
     jacobi_eig_kernel<<<1, 1024, pairs, s>>>(A, V, ev, n, 60);
     return 1;
   }
-  if (2 * mat + pairs <= limit) jacobi_eig_block_kernel<true, true><<<1, 1024, 2 * mat + pairs, s>>>(A, V, ev, n, 60);
-  else if (mat + pairs <= limit) jacobi_eig_block_kernel<true, false><<<1, 1024, mat + pairs, s>>>(A, V, ev, n, 60);
-  else jacobi_eig_block_kernel<false, false><<<1, 1024, pairs, s>>>(A, V, ev, n, 60);
-  return 1;
+  static PerDeviceOnce once;
+  if (once.first())
+    cudaFuncSetAttribute(jacobi_eig_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit));
+  int* rounds = reinterpret_cast<int*>(log_buf);
+  JacobiRot* log = reinterpret_cast<JacobiRot*>(reinterpret_cast<unsigned char*>(log_buf) + 64);
+  if (mat + pairs <= limit) jacobi_eig_block_kernel<true><<<1, 1024, mat + pairs, s>>>(A, ev, log, rounds, n, kMaxSweeps);
+  else jacobi_eig_block_kernel<false><<<1, 1024, pairs, s>>>(A, ev, log, rounds, n, kMaxSweeps);
+  jacobi_apply_log_kernel<<<n, 128, size_t((n + 1) & ~1) * sizeof(double) + size_t(kLogChunk) * npairs * sizeof(JacobiRot), s>>>(
+      log, rounds, n, V);
+  return 2;
 }
 
 // ------------------------------------------------------------------------------------------------

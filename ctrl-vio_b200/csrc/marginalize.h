@@ -86,7 +86,10 @@ int launch_marg_image(const MargImageArgs& a, cudaStream_t s);
 int launch_marg_imu(const MargImuArgs& a, cudaStream_t s);
 int launch_marg_small(const MargSmallArgs& a, cudaStream_t s);
 // symmetric eigen-decomposition (parallel cyclic Jacobi): A overwritten, V <- eigenvectors (columns), ev <- eigenvalues
-int launch_jacobi_eig(double* A, double* V, double* ev, int n, cudaStream_t s);
+// log_buf: jacobi_log_bytes(n, 40) bytes of global scratch for the rotation log (eigenvalues by one CTA, eigenvectors
+// by a replay kernel with one CTA per row)
+size_t jacobi_log_bytes(int n, int max_sweeps);
+int launch_jacobi_eig(double* A, double* V, double* ev, int n, void* log_buf, cudaStream_t s);
 int launch_dense_gemm(int m, int n, int k, double alpha, const double* A, int lda, bool ta, const double* B, int ldb,
                       bool tb, double beta, double* C, int ldc, cudaStream_t s);
 int launch_marg_elementwise(int mode, int n, int ld, const double* src, double* dst, const double* ev, const double* vb,

@@ -204,9 +204,12 @@ class StreamingRunner:
         # pre-solve pose of the window's first control point (R0, t0 of UpdateTrajectory:329-331) -- AFTER InitTrajectory
         q_pre, p_pre = (q[nowk], p[nowk])
         R0 = syn.qrot(q_pre[None], np.eye(3)).T.copy(); t0 = p_pre.copy()
+        t_built = time.perf_counter()
         summ = e.Solve(self.iters)
+        t_solved = time.perf_counter()
         e.GaugeRealign(nowk, R0, t0)
         new_prior = e.SaveMarginalizationInfo() if marg_flag == MARGIN_OLD else None
+        t_marged = time.perf_counter()
         qs, ps = e.GetKnots(); bs = e.GetBiases(); rs = e.GetInvDepths(); ld = e.GetLineDelay()
         t_wall = time.perf_counter() - t_start
         d2h = qs.nbytes + ps.nbytes + bs.nbytes + rs.nbytes + 8 + (0 if new_prior is None else new_prior.J.nbytes)
@@ -224,7 +227,9 @@ class StreamingRunner:
         # 0.5 |r_lin|^2 of the prior this window was solved with: the part of the cost that is set by the eps = 1e-30
         # pseudo-inverse's noise eigen-directions (tests compare costs with this constant removed)
         prior_const = 0.0 if prior is None else 0.5 * float(np.dot(prior.r, prior.r))
-        rec = dict(window=self.step_index, ms=1e3 * t_wall, prior_const=prior_const, iterations=summ.iterations, final_cost=summ.final_cost,
+        rec = dict(window=self.step_index, ms=1e3 * t_wall, prior_const=prior_const,
+                   ms_build_and_predict=1e3 * (t_built - t_start), ms_solve=1e3 * (t_solved - t_built),
+                   ms_realign_marginalize=1e3 * (t_marged - t_solved), ms_readback=1e3 * (t_start + t_wall - t_marged), iterations=summ.iterations, final_cost=summ.final_cost,
                    initial_cost=summ.initial_cost, termination=summ.termination, n_obs=w.n_obs, n_imu=len(w.imu_t),
                    n_knots=nloc, n_lm=len(lm_global), device_ms=summ.device_ms, marg_flag=marg_flag,
                    init_iterations=None if init_summary is None else init_summary.iterations,
@@ -245,3 +250,31 @@ class StreamingRunner:
         s = self.seq
         ks = self._knot_of(int(s.kf_times[self.frames[0]]))
         return float(np.sqrt(np.mean(np.sum((self.p[ks:self.ncp - 2] - s.p_gt[ks:self.ncp - 2]) ** 2, axis=1))))
+
+
+def c3_window_a(lib, perm_seed=None, device=0):
+    """BASELINE config 3, window A: the C3 source sequence restricted to keyframes 0..10 with the line delay free and
+    the factors of keyframe 0 flagged for marginalization (trajectory_manager.cpp:206-263).  perm_seed shuffles the order
+    in which factors are handed over (sensitivity tests).  Returns (estimator, sequence, window, first control point)."""
+    from . import make_options, setup_estimator
+    seq = syn.config_c3_sequence()
+    wa = syn.subwindow(seq, 0, 10)
+    later = int((wa.kf_times[1] - wa.t0_ns) // wa.dt_ns)
+    nowk = int((wa.kf_times[0] - wa.t0_ns) // wa.dt_ns)
+    img_marg = (wa.anchor_frame[wa.lm] == 0).astype(np.int32)
+    imu_marg = (wa.imu_t < wa.kf_times[1]).astype(np.int32)
+    bias_marg = np.zeros(len(wa.bf_i), np.int32); bias_marg[0] = 1
+    if perm_seed is not None:
+        rng = np.random.default_rng(perm_seed)
+        pm = rng.permutation(wa.n_obs)
+        for f in ("ti", "rowi", "pi", "tj", "rowj", "pj", "lm"):
+            setattr(wa, f, np.ascontiguousarray(getattr(wa, f)[pm]))
+        img_marg = img_marg[pm]
+        pi = rng.permutation(len(wa.imu_t))
+        for f in ("imu_t", "imu_gyro", "imu_accel", "imu_node"):
+            setattr(wa, f, np.ascontiguousarray(getattr(wa, f)[pi]))
+        imu_marg = imu_marg[pi]
+    opt = make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER, is_marg_state=True,
+                       ctrl_to_be_opt_now=nowk, ctrl_to_be_opt_later=later)
+    e = setup_estimator(lib, wa, image_marg=img_marg, imu_marg=imu_marg, bias_marg=bias_marg, options=opt, device=device)
+    return e, seq, wa, nowk

@@ -169,27 +169,8 @@ def triangulate_numpy(c, init_depth=5.0):
 # ---- chained runs (solve -> marginalize -> next window) and the oracle's own summation-order sensitivity ----------
 
 def c3_window_a(lib, perm_seed=None):
-    seq = syn.config_c3_sequence()
-    wa = syn.subwindow(seq, 0, 10)
-    later = int((wa.kf_times[1] - wa.t0_ns) // wa.dt_ns)
-    nowk = int((wa.kf_times[0] - wa.t0_ns) // wa.dt_ns)
-    img_marg = (wa.anchor_frame[wa.lm] == 0).astype(np.int32)
-    imu_marg = (wa.imu_t < wa.kf_times[1]).astype(np.int32)
-    bias_marg = np.zeros(len(wa.bf_i), np.int32); bias_marg[0] = 1
-    if perm_seed is not None:
-        rng = np.random.default_rng(perm_seed)
-        pm = rng.permutation(wa.n_obs)
-        for f in ("ti", "rowi", "pi", "tj", "rowj", "pj", "lm"):
-            setattr(wa, f, np.ascontiguousarray(getattr(wa, f)[pm]))
-        img_marg = img_marg[pm]
-        pi = rng.permutation(len(wa.imu_t))
-        for f in ("imu_t", "imu_gyro", "imu_accel", "imu_node"):
-            setattr(wa, f, np.ascontiguousarray(getattr(wa, f)[pi]))
-        imu_marg = imu_marg[pi]
-    opt = pkg.make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER, is_marg_state=True,
-                           ctrl_to_be_opt_now=nowk, ctrl_to_be_opt_later=later)
-    e = pkg.setup_estimator(lib, wa, image_marg=img_marg, imu_marg=imu_marg, bias_marg=bias_marg, options=opt)
-    return e, seq, wa, nowk
+    import importlib
+    return importlib.import_module("ctrl-vio_b200.streaming").c3_window_a(lib, perm_seed)
 
 
 def run_c3_sequence(lib, perm_seed=None):
