@@ -133,7 +133,7 @@ def oracle_lib():
     so = os.path.join(ROOT, "oracle", "liboracle.so")
     if not os.path.exists(so):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
-    return pkg.CtvioLib(so, "ctvo_", optional=("nccl_unique_id", "comm_init"))
+    return pkg.CtvioLib(so, "ctvo_", optional=pkg.binding.DEVICE_ONLY_SYMBOLS)
 
 
 def cpu_solve_rate(w, threads, budget_s):
@@ -228,10 +228,11 @@ def shard_window(w, rank, world):
     return (w.lm >= lo) & (w.lm < hi)
 
 
-def run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch, fp64_tflops=None):
-    """BASELINE configs[3]: C4 with residuals sharded by landmark over `world` GPUs; one NCCL all-reduce of the
-    reduced camera system [M | rhs | diag] per LM step + one of 6 scalars per evaluation."""
-    w4 = syn.config_c4()
+def run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch, fp64_tflops=None, n_landmarks=10_000, check_parity=True):
+    """BASELINE configs[3]: C4 with residuals sharded by landmark over `world` GPUs; per LM step ONE NCCL all-reduce of the
+    lower-triangular tiles of the reduced camera system (+ rhs + diagonal) and ONE all-gather of 8 scalars per rank.
+    n_landmarks = 100 000 gives the 1 M-observation variant "c4x" (same control points: where sharding pays)."""
+    w4 = syn.config_c4(n_landmarks=n_landmarks)
     sel = shard_window(w4, rank, world)
     est = pkg.Estimator(lib, pkg.make_config(device=local_rank, **w4.config_kwargs()))
     est.SetOptions(pkg.make_options(fix_ld=w4.fix_ld, ld_lower=w4.ld_lower, ld_upper=w4.ld_upper))
@@ -245,6 +246,7 @@ def run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch, fp64_tflops
         dist.broadcast_object_list(ids, src=0)
         est.CommInit(rank, world, ids[0])
     est.SaveState()
+    w4_npad = ((6 * w4.n_knots + 6 * len(w4.kf_times) + 1 + 63) // 64) * 64
     ms, iters, passes = [], 0, 0
     for it in range(2 + 3):
         est.RestoreState()
@@ -262,7 +264,24 @@ def run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch, fp64_tflops
     out = {"workload": workload_desc(w4), "n_gpus": world, "value": w4.n_residual_blocks * passes / tot_s,
            "unit": "evals/s", "lm_iters_per_s": iters / tot_s, "solve_ms": 1e3 * tot_s / len(ms),
            "ms_per_lm_iter": 1e3 * tot_s / iters, "final_cost": s4.final_cost,
-           "parallelism": f"landmark shards x{world}, NCCL all-reduce of the reduced system per LM step"}
+           "parallelism": f"landmark shards x{world}; per LM step one NCCL all-reduce of the packed lower-triangular reduced "
+                          f"system ({8 * (w4_npad // 64) * (w4_npad // 64 + 1) // 2 * 4096 / 1e6:.1f} MB) + one all-gather of 8 scalars"}
+    if world > 1 and check_parity:
+        # in-bench parity of the sharded solve (the driver's GPU test box has one GPU): the same window solved by ONE
+        # engine on rank 0 without sharding; state compared after the same number of LM steps
+        qs, ps = est.GetKnots()
+        diff = None
+        if rank == 0:
+            ref = pkg.setup_estimator(lib, w4, device=local_rank)
+            sr = ref.Solve(MAX_ITERS)
+            qr, pr = ref.GetKnots()
+            dq = syn.qmul(syn.qconj(qr), qs)
+            diff = {"iterations": [int(s4.iterations), int(sr.iterations)], "termination": [int(s4.termination), int(sr.termination)],
+                    "final_cost_rel": abs(s4.final_cost - sr.final_cost) / sr.final_cost,
+                    "max_translation_rel": float(np.abs(ps - pr).max() / np.abs(pr).max()),
+                    "max_rotation_rad": float((2 * np.arctan2(np.linalg.norm(dq[:, :3], axis=1), np.abs(dq[:, 3]))).max())}
+            del ref
+        out["parity_vs_single_gpu"] = diff
     # K1 on this rank's shard (every N): algorithmic bytes / flops of the shard over the kernel's CUDA-event time
     n_shard = int(sel.sum())
     if world == 1:
@@ -328,9 +347,11 @@ def run_c5_streaming(lib, n_windows, device, cpu_windows):
     host buffers, everything that crosses the C-ABI inside the timed region.  The CPU oracle runs the IDENTICAL cycle on
     the first `cpu_windows` windows of the same sequence (bounded sample), single-threaded like the reference."""
     st = importlib.import_module("ctrl-vio_b200.streaming")
-    seq = st.config_c5_sequence(n_windows)
+    seq = st.quantize_wire(st.config_c5_sequence(n_windows))  # bearings as the tracker's float32 PointCloud carries them
     r = st.StreamingRunner(lib, seq, device=device)
     r.run(n_windows)
+    rr = st.ResidentRunner(lib, seq, device=device)   # SURVEY 8f-1 / 8f-4: the window lives in HBM, wire formats go up as they are
+    rr.run(n_windows)
     last = r.records[-1]
     out = {"workload": f"C5: {n_windows} windows of 11 keyframes @20 Hz, ~{last['n_obs']} RS obs, {last['n_imu']} IMU samples, "
                        f"{last['n_knots']} ctrl pts, prior dim {last['prior_dim']}; per window: IMU-only predictor solve(8) + "
@@ -338,12 +359,21 @@ def run_c5_streaming(lib, n_windows, device, cpu_windows):
            "gpu": c5_summary(r.records, min(5, n_windows // 2)), "final_cost_last": last["final_cost"],
            "rms_translation_error_vs_truth_m": r.state_error()}
     out["gpu"]["realtime_factor_at_20hz"] = 50.0 / out["gpu"]["ms_per_window_mean"]
+    out["gpu"]["path"] = "host buffers: state, factors and prior re-uploaded every window through the Add* calls"
+    out["gpu_resident"] = c5_summary(rr.records, min(5, n_windows // 2))
+    out["gpu_resident"]["path"] = ("device-resident window: PointCloud / IMUData ingested as they are, control points extended / "
+                                   "dropped on the device, prior handed over device-to-device, factor payload gathered from "
+                                   "resident tables (index tables + the new frame cross the boundary)")
+    out["gpu_resident"]["realtime_factor_at_20hz"] = 50.0 / out["gpu_resident"]["ms_per_window_mean"]
+    out["gpu_resident"]["max_abs_translation_difference_to_host_buffer_path_m"] = float(
+        np.abs(r.p[:r.ncp] - rr.p[:rr.ncp]).max())
     if cpu_windows > 0:
         ro = st.StreamingRunner(oracle_lib(), seq)
         ro.run(min(cpu_windows, n_windows))
         out["cpu_baseline"] = dict(c5_summary(ro.records, 1), cores=1, kind="port",
                                    sample=f"the first {len(ro.records)} windows of the same sequence, identical cycle")
         out["speedup_ms_per_window"] = out["cpu_baseline"]["ms_per_window_mean"] / out["gpu"]["ms_per_window_mean"]
+        out["speedup_ms_per_window_resident"] = out["cpu_baseline"]["ms_per_window_mean"] / out["gpu_resident"]["ms_per_window_mean"]
     return out
 
 
@@ -405,6 +435,7 @@ def main():
     ap.add_argument("--c5-windows", type=int, default=1000)
     ap.add_argument("--c5-cpu-windows", type=int, default=40)
     ap.add_argument("--no-c3", action="store_true")
+    ap.add_argument("--no-c4x", action="store_true")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ctvio", choices=["ctvio", "reference"])
@@ -512,6 +543,9 @@ def main():
         c4 = run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch, fp64_tflops)
         c4_clocks = s4.stop()
         c4["clocks"] = c4_clocks
+        if not args.no_c4x:
+            c4["c4x"] = run_c4_sharded(lib, rank, world, local_rank, flush, dist, torch, fp64_tflops, n_landmarks=100_000,
+                                       check_parity=False)
     c3 = c5 = None
     if rank == 0 and not args.no_c3:
         c3 = {"workload": "C3: C2-scale window (30 ctrl pts, 2700 RS obs, 270 IMU), line delay free, solve(15) + re-align + "

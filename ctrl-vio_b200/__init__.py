@@ -18,7 +18,7 @@ import sys
 
 import numpy as np
 
-from . import synthetic
+from . import binding, synthetic
 from .binding import (ABI_SYMBOLS, BLK_BA, BLK_BG, BLK_LD, BLK_POS, BLK_RHO, BLK_ROT, Config, CtvioError, CtvioLib,
                       Estimator, Options, PriorData, Summary)
 

@@ -100,8 +100,17 @@ ABI_SYMBOLS = [
     "solve", "gauge_realign", "marginalize", "get_prior", "adopt_prior",
     "save_state", "restore_state",
     "eval_image_factors", "eval_imu_factors", "eval_cost", "normal_equations",
-    "query_trajectory", "triangulate", "profile_kernels", "measure_fp64_tflops", "selfcheck_solver", "nccl_unique_id", "comm_init",
+    "query_trajectory", "triangulate",
+    "extend_knots_to", "slide_window", "remap_landmarks", "enable_prior", "ingest_feature_cloud", "add_image_features_from_slots",
+    "ingest_imu", "add_imu_from_table", "transfer_stats", "profile_kernels", "measure_fp64_tflops", "selfcheck_solver", "nccl_unique_id", "comm_init",
 ]
+
+
+# entry points a checker library (the CPU oracle mirrors the ABI under `ctvo_`) need not provide: multi-GPU plumbing and
+# the device-residency / wire-format calls, which have no CPU meaning
+DEVICE_ONLY_SYMBOLS = ("nccl_unique_id", "comm_init", "enable_prior", "extend_knots_to", "slide_window", "remap_landmarks", "enable_prior",
+                       "ingest_feature_cloud", "add_image_features_from_slots", "ingest_imu", "add_imu_from_table",
+                       "transfer_stats")
 
 
 def _dp(a):
@@ -372,6 +381,64 @@ class Estimator:
                       C.c_int32(start_frame.shape[0]), _ip(start_frame), _ip(obs_offset), _dp(obs_point),
                       C.c_int32(window_size), C.c_double(init_depth), _dp(depth))
         return depth
+
+    # --- device-resident window / wire formats ---------------------
+    def ExtendKnotsTo(self, t_ns) -> int:
+        n = C.c_int32()
+        self.lib.call("extend_knots_to", self.h, C.c_int64(int(t_ns)), C.byref(n))
+        self.n_knots = n.value
+        return n.value
+
+    def SlideWindow(self, n_drop_knots, n_drop_bias, n_new_bias):
+        self.lib.call("slide_window", self.h, C.c_int32(n_drop_knots), C.c_int32(n_drop_bias), C.c_int32(n_new_bias))
+        self.n_knots -= n_drop_knots
+        self.n_bias += n_new_bias - n_drop_bias
+
+    def EnablePrior(self, on: bool):
+        self.lib.call("enable_prior", self.h, C.c_int32(int(on)))
+
+    def RemapLandmarks(self, old_index, init_inv_depth):
+        old_index = _i32(old_index); init = _f64(init_inv_depth, (-1,))
+        assert old_index.shape[0] == init.shape[0]
+        self.lib.call("remap_landmarks", self.h, C.c_int32(old_index.shape[0]), _ip(old_index), _dp(init))
+        self.n_lm = old_index.shape[0]
+
+    def IngestFeatureCloud(self, frame_slot, t_ns, points_xyz, ch_id, ch_u, ch_v, ch_vx, ch_vy):
+        """sensor_msgs::PointCloud of the tracker as it is: float32 point triples + five float32 channels."""
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        pts = f32(points_xyz).reshape(-1, 3); ch = [f32(x).reshape(-1) for x in (ch_id, ch_u, ch_v, ch_vx, ch_vy)]
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        self.lib.call("ingest_feature_cloud", self.h, C.c_int32(frame_slot), C.c_int64(int(t_ns)), C.c_int32(pts.shape[0]),
+                      fp(pts), *[fp(x) for x in ch])
+
+    def AddImageFeaturesFromSlots(self, slot_i, idx_i, slot_j, idx_j, landmark, marg=None):
+        a = [_i32(x) for x in (slot_i, idx_i, slot_j, idx_j, landmark)]
+        marg = _i32(marg) if marg is not None else None
+        n = a[0].shape[0]
+        self.lib.call("add_image_features_from_slots", self.h, C.c_int32(n), *[_ip(x) for x in a], _ip(marg))
+        self.n_img += n
+
+    def IngestImu(self, records: np.ndarray, off_gyro, off_accel, drop_before_ns=0):
+        """packed IMUData records (structured / byte array, one record per row)."""
+        rec = np.ascontiguousarray(records)
+        n = rec.shape[0]
+        stride = rec.strides[0] if n else rec.dtype.itemsize
+        self.lib.call("ingest_imu", self.h, C.c_int32(n), rec.ctypes.data_as(C.c_void_p), C.c_int32(stride),
+                      C.c_int32(off_gyro), C.c_int32(off_accel), C.c_int64(int(drop_before_ns)))
+
+    def AddImuFromTable(self, t_min_ns, t_max_ns, kf_times=None, fixed_node=-1, marg_before_ns=-(1 << 62)) -> int:
+        kf = _i64(kf_times) if kf_times is not None else None
+        n = C.c_int32()
+        self.lib.call("add_imu_from_table", self.h, C.c_int64(int(t_min_ns)), C.c_int64(int(t_max_ns)),
+                      C.c_int32(0 if kf is None else kf.shape[0]), _lp(kf), C.c_int32(fixed_node),
+                      C.c_int64(int(marg_before_ns)), C.byref(n))
+        self.n_imu += n.value
+        return n.value
+
+    def TransferStats(self, reset=True):
+        a, b = C.c_int64(), C.c_int64()
+        self.lib.call("transfer_stats", self.h, C.byref(a), C.byref(b), C.c_int32(int(reset)))
+        return a.value, b.value
 
     def ProfileKernels(self, reps=20, flush_l2=True):
         out = np.zeros(8)

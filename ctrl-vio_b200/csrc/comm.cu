@@ -25,6 +25,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   std::string load_error;
   bool ok = false;
@@ -56,6 +57,7 @@ NcclApi& nccl_api() {
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
     api.ok = api.load_error.empty();
   });
@@ -106,6 +108,12 @@ void comm_destroy(void* comm) {
 bool comm_allreduce_sum(void* comm, double* buf, size_t n, cudaStream_t s, std::string* err) {
   ncclResult_t r = nccl_api().AllReduce(buf, buf, n, ncclDouble, ncclSum, static_cast<ncclComm_t>(comm), s);
   if (r != ncclSuccess) return fail(err, "ncclAllReduce", r);
+  return true;
+}
+
+bool comm_allgather(void* comm, const double* send, double* recv, size_t n_per_rank, cudaStream_t s, std::string* err) {
+  ncclResult_t r = nccl_api().AllGather(send, recv, n_per_rank, ncclDouble, static_cast<ncclComm_t>(comm), s);
+  if (r != ncclSuccess) return fail(err, "ncclAllGather", r);
   return true;
 }
 

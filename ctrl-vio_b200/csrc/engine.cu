@@ -44,6 +44,8 @@ int fail(int code, const std::string& msg) {
       return fail(CTVIO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
   } while (0)
 
+thread_local size_t g_upload_bytes = 0;  // bytes moved by DevBuf::upload (index tables etc.), see ctvio_transfer_stats
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -61,6 +63,7 @@ struct DevBuf {
   cudaError_t upload(const std::vector<T>& h, cudaStream_t s) {
     cudaError_t e = reserve(h.size());
     if (e != cudaSuccess || h.empty()) return e;
+    g_upload_bytes += h.size() * sizeof(T);
     return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
   }
 };
@@ -139,6 +142,7 @@ struct ctvio_engine {
   DevBuf<double> d_M, d_Linv, d_y, d_sc, d_sl, d_hh, d_dc, d_dl, d_rho_sync, d_chol_part;
   DevBuf<int32_t> d_chol_flags;
   DevBuf<uint8_t> d_owned;
+  DevBuf<double> d_shard_pack, d_shard_scal;  // sharded mode: packed all-reduce buffer, scalar all-gather buffer
   int npad = 0, linv_npad = -1;
   unsigned chol_seq = 0;  // tile-DAG launches so far (packet buffer parity)
   DevBuf<LmScalars> d_scal;
@@ -153,6 +157,26 @@ struct ctvio_engine {
   DevBuf<double> d_prior_J, d_prior_r, d_prior_JtJ, d_prior_x0, d_prior_dx, d_prior_res;
   DevBuf<int32_t> d_prior_type, d_prior_index, d_prior_col, d_prior_col2g;
   bool prior_dirty = true;
+  bool prior_enabled = true;      // ctvio_enable_prior: estimators without the prior (InitTrajectory) keep it resident
+  bool prior_on_device = false;   // the active prior's J / r / x0 / J'J were adopted device-to-device (host vectors empty)
+  bool new_prior_on_host = false; // ctvio_get_prior has fetched the freshly marginalized prior's J / r / x0
+  DevBuf<double> d_newprior_x0;
+  // wire-format ingestion (frontend.cu): resident per-frame feature tables, resident IMU table
+  static constexpr int kFrameSlots = 16, kFrameCap = 1024;
+  DevBuf<ctvio::FrameFeature> d_frames;   // [kFrameSlots][kFrameCap]
+  DevBuf<int64_t> d_frame_t;              // [kFrameSlots]
+  DevBuf<float> d_cloud_stage;            // staging for one message (5 floats per point... points 3 + id + v)
+  int64_t h_frame_t[16] = {0};
+  int32_t h_frame_n[16] = {0};
+  std::vector<ctvio::FactorDesc> img_desc;  // parallel to img when the factors came from the resident tables
+  DevBuf<ctvio::FactorDesc> d_img_desc;
+  DevBuf<longlong2> d_imu_tab_t;           // resident IMU table {t, 0}
+  DevBuf<double2> d_imu_tab_ga;            // [cap][3]
+  DevBuf<unsigned char> d_imu_raw;
+  std::vector<int64_t> h_imu_tab_t;        // host mirror: timestamps only
+  std::vector<int32_t> imu_src;            // parallel to imu when the samples came from the resident table (table index)
+  DevBuf<int2> d_imu_src;
+  size_t h2d_bytes = 0, d2h_bytes = 0;     // bytes moved by the C-ABI calls since ctvio_transfer_stats(reset)
 
   DevBuf<double> d_tmp;  // scratch (gauge inputs, probe outputs)
   DevBuf<int32_t> d_tri_idx;  // ctvio_triangulate: start frames | observation offsets
@@ -207,6 +231,7 @@ bool knot_window(const ctvio_engine* e, int64_t t, int& first, int& last) {
 }
 
 int prepare_prior(ctvio_engine* e);
+int fetch_new_prior(ctvio_engine* e);
 
 // Build every host-side structure that depends on the factor set / sizes and upload it.
 int prepare(ctvio_engine* e) {
@@ -269,10 +294,24 @@ int prepare(ctvio_engine* e) {
       k = end;
     }
     e->n_items = int(items.size());
-    CUDA_OK(e->d_img_t.upload(ht, st));
-    CUDA_OK(e->d_img_pi.upload(hpi, st));
-    CUDA_OK(e->d_img_pj.upload(hpj, st));
-    CUDA_OK(e->d_img_meta.upload(hm, st));
+    if (!e->img_desc.empty()) {
+      // factors added from the resident frame tables: only the sorted 16-byte descriptors go up, the SoA payload is
+      // gathered on the device
+      std::vector<ctvio::FactorDesc> sd(n);
+      for (int k = 0; k < n; ++k) sd[k] = e->img_desc[e->img_order[k]];
+      CUDA_OK(e->d_img_desc.upload(sd, st));
+      CUDA_OK(e->d_img_t.reserve(n)); CUDA_OK(e->d_img_pi.reserve(n)); CUDA_OK(e->d_img_pj.reserve(n)); CUDA_OK(e->d_img_meta.reserve(n));
+      ctvio::GatherFactorsArgs ga;
+      ga.n = n; ga.desc = e->d_img_desc.p; ga.table = e->d_frames.p; ga.frame_t = e->d_frame_t.p;
+      ga.frame_cap = ctvio_engine::kFrameCap;
+      ga.t = e->d_img_t.p; ga.pi = e->d_img_pi.p; ga.pj = e->d_img_pj.p; ga.meta = e->d_img_meta.p;
+      e->launches += ctvio::launch_gather_factors(ga, st);
+    } else {
+      CUDA_OK(e->d_img_t.upload(ht, st));
+      CUDA_OK(e->d_img_pi.upload(hpi, st));
+      CUDA_OK(e->d_img_pj.upload(hpj, st));
+      CUDA_OK(e->d_img_meta.upload(hm, st));
+    }
     CUDA_OK(e->d_img_orig.upload(e->img_order, st));
     CUDA_OK(e->d_items.upload(items, st));
 
@@ -321,8 +360,17 @@ int prepare(ctvio_engine* e) {
     e->n_imu_items = int(imu_items.size());
     CUDA_OK(e->d_imu_items.upload(imu_items, st));
     CUDA_OK(e->d_imu_orig.upload(imu_order, st));
-    CUDA_OK(e->d_imu_t.upload(it, st));
-    CUDA_OK(e->d_imu_ga.upload(iga, st));
+    if (!e->imu_src.empty()) {
+      // samples taken from the resident IMU table: (table index, bias node) pairs go up, the payload is gathered
+      std::vector<int2> src(ni);
+      for (int k = 0; k < ni; ++k) src[k] = make_int2(e->imu_src[imu_order[k]], e->imu[imu_order[k]].node);
+      CUDA_OK(e->d_imu_src.upload(src, st));
+      CUDA_OK(e->d_imu_t.reserve(ni)); CUDA_OK(e->d_imu_ga.reserve(3 * size_t(ni)));
+      e->launches += ctvio::launch_gather_imu(e->d_imu_src.p, ni, e->d_imu_tab_t.p, e->d_imu_tab_ga.p, e->d_imu_t.p, e->d_imu_ga.p, st);
+    } else {
+      CUDA_OK(e->d_imu_t.upload(it, st));
+      CUDA_OK(e->d_imu_ga.upload(iga, st));
+    }
     const int nb = int(e->biasf.size());
     std::vector<int2> bij(nb);
     std::vector<double> bs(6 * size_t(nb));
@@ -439,7 +487,7 @@ int prepare(ctvio_engine* e) {
     }
     for (const HostBias& o : e->biasf)
       for (int c = 0; c < 6; ++c) touched[d.idx_bias0 + 6 * o.i + c] = touched[d.idx_bias0 + 6 * o.j + c] = 1;
-    if (e->prior.n > 0)
+    if (e->prior.n > 0 && e->prior_enabled)
       for (size_t b = 0; b < e->prior.type.size(); ++b) {
         const int g = ctvio::prior_block_base(e->prior.type[b], e->prior.index[b], d.nK, d.nB);
         const int ls = (e->prior.type[b] == CTVIO_BLK_LD || e->prior.type[b] == CTVIO_BLK_RHO) ? 1 : 3;
@@ -475,9 +523,11 @@ int prepare_prior(ctvio_engine* e) {
     for (int c = 0; c < ls; ++c)
       if (!e->h_cmask[g + c]) col2g[pr.col[b] + c] = g + c;
   }
-  CUDA_OK(e->d_prior_J.upload(pr.J, st));
-  CUDA_OK(e->d_prior_r.upload(pr.r, st));
-  CUDA_OK(e->d_prior_x0.upload(pr.x0, st));
+  if (!e->prior_on_device) {
+    CUDA_OK(e->d_prior_J.upload(pr.J, st));
+    CUDA_OK(e->d_prior_r.upload(pr.r, st));
+    CUDA_OK(e->d_prior_x0.upload(pr.x0, st));
+  }
   CUDA_OK(e->d_prior_type.upload(pr.type, st));
   CUDA_OK(e->d_prior_index.upload(pr.index, st));
   CUDA_OK(e->d_prior_col.upload(pr.col, st));
@@ -490,10 +540,27 @@ int prepare_prior(ctvio_engine* e) {
   return CTVIO_OK;
 }
 
+// make sure the host copy of the freshly marginalized prior exists (ctvio_get_prior; the device-to-device hand-over of
+// ctvio_adopt_prior never needs it)
+int fetch_new_prior(ctvio_engine* e) {
+  ctvio::PriorHost& np_ = e->new_prior;
+  if (e->new_prior_on_host || np_.n <= 0) return CTVIO_OK;
+  np_.J.resize(size_t(np_.n) * np_.n);
+  np_.r.resize(np_.n);
+  np_.x0.resize(4 * np_.type.size());
+  CUDA_OK(cudaMemcpyAsync(np_.J.data(), e->mws.J.p, np_.J.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_OK(cudaMemcpyAsync(np_.r.data(), e->mws.r.p, np_.r.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_OK(cudaMemcpyAsync(np_.x0.data(), e->d_newprior_x0.p, np_.x0.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->d2h_bytes += (np_.J.size() + np_.r.size() + np_.x0.size()) * sizeof(double);
+  e->new_prior_on_host = true;
+  return CTVIO_OK;
+}
+
 PriorPtrs prior_ptrs(ctvio_engine* e) {
   PriorPtrs p;
   std::memset(&p, 0, sizeof(p));
-  p.n = e->prior.n;
+  p.n = e->prior_enabled ? e->prior.n : 0;
   if (p.n <= 0) return p;
   p.n_blocks = int(e->prior.type.size());
   p.J = e->d_prior_J.p; p.r = e->d_prior_r.p; p.JtJ = e->d_prior_JtJ.p;
@@ -569,13 +636,17 @@ LinearLaunch linear_launch(ctvio_engine* e, int nb) {
   return a;
 }
 
-// sharded mode: sum the per-step scalars over the landmark shards (NCCL, on the engine stream)
-int allreduce_scalars(ctvio_engine* e) {
+// sharded mode: ONE all-gather of every rank's 8 scalars (sums AND maxima travel together), reduced in a fixed rank
+// order by a one-thread kernel that also publishes the common block to mapped host memory (no copy + stream synchronise)
+int allreduce_scalars(ctvio_engine* e, bool publish = false) {
   if (e->world <= 1) return CTVIO_OK;
-  e->launches += ctvio::launch_flags_to_double(e->d_scal.p, e->stream);
+  CUDA_OK(e->d_shard_scal.reserve(8 + 8 * size_t(e->world)));
+  e->launches += ctvio::launch_shard_scalars_pack(e->d_scal.p, e->d_shard_scal.p, e->stream);
   std::string err;
-  if (!ctvio::comm_allreduce_sum(e->nccl_comm, &e->d_scal.p->cost_eval, kLmSumScalars, e->stream, &err))
+  if (!ctvio::comm_allgather(e->nccl_comm, e->d_shard_scal.p, e->d_shard_scal.p + 8, 8, e->stream, &err))
     return fail(CTVIO_ERR_NCCL, err);
+  e->launches += ctvio::launch_shard_scalars_reduce(e->d_shard_scal.p + 8, e->world, e->d_scal.p, publish ? e->h_pub : nullptr,
+                                                    publish ? ++e->pub_seq : 0, e->stream);
   return CTVIO_OK;
 }
 
@@ -626,10 +697,13 @@ int lm_step(ctvio_engine* e, int nb, double radius, const ApplyLaunch* fused_app
   cudaStream_t st = e->stream;
   e->launches += launch_reduced_system(lin, radius, st);
   if (e->world > 1) {
+    // one all-reduce of the lower-triangular tiles + rhs + diagonal (half the bytes of the dense slab), damping after it
     std::string err;
-    const size_t count = size_t(e->npad) * e->npad + 2 * size_t(e->npad);
-    if (!ctvio::comm_allreduce_sum(e->nccl_comm, lin.M, count, st, &err)) return fail(CTVIO_ERR_NCCL, err);
-    e->launches += launch_add_damping(lin, radius, st);
+    const size_t count = ctvio::shard_pack_len(e->npad);
+    CUDA_OK(e->d_shard_pack.reserve(count));
+    e->launches += ctvio::launch_shard_pack(lin, e->d_shard_pack.p, st);
+    if (!ctvio::comm_allreduce_sum(e->nccl_comm, e->d_shard_pack.p, count, st, &err)) return fail(CTVIO_ERR_NCCL, err);
+    e->launches += ctvio::launch_shard_unpack(lin, e->d_shard_pack.p, radius, st);
   }
   e->launches += launch_factor_solve(lin, st);
   if (fused_apply) e->launches += launch_step_and_apply(lin, *fused_apply, st);
@@ -652,7 +726,7 @@ void evaluate(ctvio_engine* e, int xb, int nb, bool full, bool reset_cost = true
   if (reset_cost) cudaMemsetAsync(&e->d_scal.p->cost_eval, 0, sizeof(double), st);
   // fork: the (latency-bound) IMU + bias + prior kernels overlap the visual kernel on a second stream
   // sharded mode: IMU / bias / prior factors live on rank 0 only (every rank holds its own landmark shard)
-  const bool fork = (e->rank == 0) && (!e->imu.empty() || !e->biasf.empty() || e->prior.n > 0);
+  const bool fork = (e->rank == 0) && (!e->imu.empty() || !e->biasf.empty() || (e->prior.n > 0 && e->prior_enabled));
   if (fork) {
     cudaEventRecord(e->ev_fork, st);
     cudaStreamWaitEvent(e->stream2, e->ev_fork, 0);
@@ -806,6 +880,7 @@ int ctvio_set_knots(ctvio_handle e, int32_t n, const double* q, const double* p)
   CUDA_OK(cudaMemcpyAsync(e->x[e->cur].q.p, q, 4 * size_t(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   CUDA_OK(cudaMemcpyAsync(e->x[e->cur].p.p, p4.data(), p4.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));  // p4 is a stack-lifetime staging buffer
+  e->h2d_bytes += size_t(n) * 56;
   e->have_knots = true;
   e->table_valid = false;
   return CTVIO_OK;
@@ -819,6 +894,7 @@ int ctvio_set_biases(ctvio_handle e, int32_t n, const double* b) {
   for (int k = 0; k < 2; ++k) CUDA_OK(e->x[k].bias.reserve(6 * size_t(std::max(n, 1))));
   if (n > 0) CUDA_OK(cudaMemcpyAsync(e->x[e->cur].bias.p, b, 6 * size_t(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->h2d_bytes += size_t(n) * 48;
   e->have_bias = true;
   return CTVIO_OK;
 }
@@ -831,6 +907,7 @@ int ctvio_set_inv_depths(ctvio_handle e, int32_t n, const double* r) {
   for (int k = 0; k < 2; ++k) CUDA_OK(e->x[k].rho.reserve(size_t(std::max(n, 1))));
   if (n > 0) CUDA_OK(cudaMemcpyAsync(e->x[e->cur].rho.p, r, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->h2d_bytes += size_t(n) * 8;
   e->have_rho = true;
   return CTVIO_OK;
 }
@@ -865,6 +942,7 @@ int ctvio_get_knots(ctvio_handle e, double* q, double* p) {
   }
   CUDA_OK(cudaStreamSynchronize(e->stream));
   if (p) for (int k = 0; k < e->nK; ++k) for (int c = 0; c < 3; ++c) p[3 * k + c] = p4[kPStride * k + c];
+  e->d2h_bytes += size_t(e->nK) * ((q ? 32 : 0) + (p ? 32 : 0));
   return CTVIO_OK;
 }
 int ctvio_get_biases(ctvio_handle e, double* b) {
@@ -872,6 +950,7 @@ int ctvio_get_biases(ctvio_handle e, double* b) {
   cudaSetDevice(e->cfg.device);
   if (e->nB > 0) CUDA_OK(cudaMemcpyAsync(b, e->x[e->cur].bias.p, 6 * size_t(e->nB) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->d2h_bytes += size_t(e->nB) * 48;
   return CTVIO_OK;
 }
 int ctvio_get_inv_depths(ctvio_handle e, double* r) {
@@ -879,6 +958,7 @@ int ctvio_get_inv_depths(ctvio_handle e, double* r) {
   cudaSetDevice(e->cfg.device);
   if (e->nL > 0) CUDA_OK(cudaMemcpyAsync(r, e->x[e->cur].rho.p, size_t(e->nL) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->d2h_bytes += size_t(e->nL) * 8;
   return CTVIO_OK;
 }
 int ctvio_get_line_delay(ctvio_handle e, double* ld) {
@@ -892,6 +972,7 @@ int ctvio_get_line_delay(ctvio_handle e, double* ld) {
 int ctvio_clear_factors(ctvio_handle e) {
   if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
   e->img.clear(); e->imu.clear(); e->biasf.clear();
+  e->img_desc.clear(); e->imu_src.clear();
   e->structure_dirty = true;
   return CTVIO_OK;
 }
@@ -901,6 +982,7 @@ int ctvio_add_image_features(ctvio_handle e, int32_t n, const int64_t* ti, const
                              const int32_t* marg) {
   if (!e || n < 0 || (n > 0 && (!ti || !rowi || !pi || !tj || !rowj || !pj || !lm)))
     return fail(CTVIO_ERR_INVALID, "null argument");
+  if (!e->img_desc.empty()) return fail(CTVIO_ERR_STATE, "image factors from the resident tables are already present");
   e->img.reserve(e->img.size() + n);
   for (int k = 0; k < n; ++k) {
     HostImage o{ti[k], tj[k], rowi[k], rowj[k], {pi[2 * k], pi[2 * k + 1]}, {pj[2 * k], pj[2 * k + 1]}, lm[k],
@@ -913,6 +995,7 @@ int ctvio_add_image_features(ctvio_handle e, int32_t n, const int64_t* ti, const
 int ctvio_add_imu_measurements(ctvio_handle e, int32_t n, const int64_t* t, const double* gyro, const double* accel,
                                const int32_t* node, const int32_t* marg) {
   if (!e || n < 0 || (n > 0 && (!t || !gyro || !accel || !node))) return fail(CTVIO_ERR_INVALID, "null argument");
+  if (!e->imu_src.empty()) return fail(CTVIO_ERR_STATE, "IMU factors from the resident table are already present");
   for (int k = 0; k < n; ++k) {
     HostImu o{t[k], {gyro[3 * k], gyro[3 * k + 1], gyro[3 * k + 2]}, {accel[3 * k], accel[3 * k + 1], accel[3 * k + 2]},
               node[k], marg ? marg[k] : 0};
@@ -938,6 +1021,7 @@ int ctvio_set_prior(ctvio_handle e, int32_t n, const double* J, const double* r,
   if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
   e->prior = ctvio::PriorHost();
   e->prior_dirty = true;
+  e->prior_on_device = false;
   e->masks_dirty = true;  // the prior's blocks count as touched parameters
   if (n <= 0) return CTVIO_OK;
   if (!J || !r || nb <= 0 || !type || !index || !col || !x0) return fail(CTVIO_ERR_INVALID, "null argument");
@@ -1018,9 +1102,7 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
   rc = read_scalars(e);
   if (rc) return rc;
   double x_cost = e->h_scal->cost_eval;
-  // sharded mode: the gradient max-norm is only known per shard; the 1e-10 gradient tolerance is not tested
-  // there (every rank must take identical control decisions)
-  double gmax = sharded ? 1e300 : e->h_scal->gmax;
+  double gmax = e->h_scal->gmax;  // sharded: the all-gathered maximum
   sum.initial_cost = x_cost;
   sum.num_successful_steps = 1;
 
@@ -1065,15 +1147,19 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     evaluate(e, cand, cand, true, false);
     sum.num_jacobian_evals++;
     LinearLaunch linc = linear_launch(e, cand);
-    const bool publish = !sharded;  // sharded: the scalars still have to go through the all-reduce
-    e->launches += launch_gradient_norm(linc, e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st, false,
-                                        publish ? e->h_pub : nullptr, ++e->pub_seq);
-    rc = allreduce_scalars(e);
-    if (rc) return rc;
-    rc = read_scalars(e, publish);
+    // single GPU: the gradient-norm kernel publishes the block; sharded: the reduction kernel behind the all-gather does
+    if (!sharded) {
+      e->launches += launch_gradient_norm(linc, e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st, false,
+                                          e->h_pub, ++e->pub_seq);
+    } else {
+      e->launches += launch_gradient_norm(linc, e->x[cand].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st, false,
+                                          nullptr, 0);
+      rc = allreduce_scalars(e, true);
+      if (rc) return rc;
+    }
+    rc = read_scalars(e, true);
     if (rc) return rc;
     LmScalars sc = *e->h_scal;
-    if (sharded) { sc.gmax = 1e300; sc.dir_max = 1e300; }
     const double model_cost_change = -sc.gd - 0.5 * sc.dHd;
     const bool valid = !sc.chol_fail && std::isfinite(model_cost_change) && model_cost_change > 0.0;
     if (!valid) {
@@ -1147,7 +1233,7 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
         if (rc) return rc;
       }
       cand_cost = e->h_scal->cost_eval;
-      cand_gmax = sharded ? 1e300 : e->h_scal->gmax;
+      cand_gmax = e->h_scal->gmax;
       step_norm2 = e->h_scal->step_norm2;
       x_norm2 = e->h_scal->x_norm2;
     }
@@ -1736,35 +1822,24 @@ int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
   rc = read_scalars(e);
   if (rc) return rc;
 
-  // ---- the new prior: kept blocks with the current state as linearisation point ----
+  // ---- the new prior: kept blocks with the current state as linearisation point; J_lin / r_lin / x0 STAY in HBM
+  //      (ctvio_adopt_prior hands them over device-to-device, ctvio_get_prior fetches them on demand) ----
   ctvio::PriorHost& np_ = e->new_prior;
   np_.n = n;
-  np_.J.resize(size_t(n) * n);
-  np_.r.resize(n);
-  CUDA_OK(cudaMemcpy(np_.J.data(), d_J.p, np_.J.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  CUDA_OK(cudaMemcpy(np_.r.data(), d_r.p, np_.r.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  std::vector<double> hq(4 * size_t(e->nK)), hp(kPStride * size_t(e->nK)), hb(6 * size_t(std::max(e->nB, 1)));
-  double hld = 0;
-  CUDA_OK(cudaMemcpy(hq.data(), e->x[e->cur].q.p, hq.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  CUDA_OK(cudaMemcpy(hp.data(), e->x[e->cur].p.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  if (e->nB) CUDA_OK(cudaMemcpy(hb.data(), e->x[e->cur].bias.p, 6 * size_t(e->nB) * sizeof(double), cudaMemcpyDeviceToHost));
-  CUDA_OK(cudaMemcpy(&hld, e->x[e->cur].ld.p, sizeof(double), cudaMemcpyDeviceToHost));
+  e->new_prior_on_host = false;
   for (const auto& kv : blocks) {
     if (kv.second.dropped) continue;
     np_.type.push_back(kv.first.type);
     np_.index.push_back(kv.first.index);
     np_.col.push_back(kv.second.pos - m);
-    double x0[4] = {0, 0, 0, 0};
-    const int i = kv.first.index;
-    switch (kv.first.type) {
-      case CTVIO_BLK_ROT: for (int c = 0; c < 4; ++c) x0[c] = hq[4 * i + c]; break;
-      case CTVIO_BLK_POS: for (int c = 0; c < 3; ++c) x0[c] = hp[kPStride * i + c]; break;
-      case CTVIO_BLK_BG: for (int c = 0; c < 3; ++c) x0[c] = hb[6 * i + c]; break;
-      case CTVIO_BLK_BA: for (int c = 0; c < 3; ++c) x0[c] = hb[6 * i + 3 + c]; break;
-      case CTVIO_BLK_LD: x0[0] = hld; break;
-      default: break;
-    }
-    for (int c = 0; c < 4; ++c) np_.x0.push_back(x0[c]);
+  }
+  {
+    DevBuf<int32_t>&d_t = ws.pos_cam, &d_i = ws.pos_lm;  // free again: reuse as block type / index uploads
+    CUDA_OK(d_t.upload(np_.type, st));
+    CUDA_OK(d_i.upload(np_.index, st));
+    CUDA_OK(e->d_newprior_x0.reserve(4 * np_.type.size()));
+    e->launches += ctvio::launch_prior_x0(e->x[e->cur].ptrs(), d_t.p, d_i.p, int(np_.type.size()), e->d_newprior_x0.p, st);
+    CUDA_OK(cudaStreamSynchronize(st));  // the uploads above come from host vectors that are reused by the next call
   }
   *n_out = n;
   *nb_out = int32_t(np_.type.size());
@@ -1772,8 +1847,13 @@ int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
 }
 int ctvio_get_prior(ctvio_handle e, double* J, double* r, int32_t* type, int32_t* index, int32_t* col, double* x0) {
   if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  if (e->new_prior.n <= 0) return fail(CTVIO_ERR_STATE, "no prior has been produced");
+  cudaSetDevice(e->cfg.device);
+  {
+    const int rc = fetch_new_prior(e);
+    if (rc) return rc;
+  }
   const ctvio::PriorHost& p = e->new_prior;
-  if (p.n <= 0) return fail(CTVIO_ERR_STATE, "no prior has been produced");
   if (J) std::memcpy(J, p.J.data(), p.J.size() * sizeof(double));
   if (r) std::memcpy(r, p.r.data(), p.r.size() * sizeof(double));
   if (type) std::memcpy(type, p.type.data(), p.type.size() * sizeof(int32_t));
@@ -1784,9 +1864,253 @@ int ctvio_get_prior(ctvio_handle e, double* J, double* r, int32_t* type, int32_t
 }
 int ctvio_adopt_prior(ctvio_handle e) {
   if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
-  e->prior = e->new_prior;
+  if (e->new_prior.n <= 0) return fail(CTVIO_ERR_STATE, "no prior has been produced");
+  cudaSetDevice(e->cfg.device);
+  // device-to-device: the buffers of the marginalization workspace BECOME the active prior (pointer swap), only the
+  // block bookkeeping (a few dozen ints) lives on the host
+  e->prior.n = e->new_prior.n;
+  e->prior.type = e->new_prior.type; e->prior.index = e->new_prior.index; e->prior.col = e->new_prior.col;
+  e->prior.J.clear(); e->prior.r.clear(); e->prior.x0.clear();
+  std::swap(e->d_prior_J.p, e->mws.J.p); std::swap(e->d_prior_J.cap, e->mws.J.cap);
+  std::swap(e->d_prior_r.p, e->mws.r.p); std::swap(e->d_prior_r.cap, e->mws.r.cap);
+  std::swap(e->d_prior_x0.p, e->d_newprior_x0.p); std::swap(e->d_prior_x0.cap, e->d_newprior_x0.cap);
+  e->prior_on_device = true;
+  e->new_prior = ctvio::PriorHost();  // its device buffers are gone
   e->prior_dirty = true;
   e->masks_dirty = true;
+  return CTVIO_OK;
+}
+
+int ctvio_enable_prior(ctvio_handle e, int32_t on) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  if (e->prior_enabled != (on != 0)) e->masks_dirty = true;
+  e->prior_enabled = on != 0;
+  return CTVIO_OK;
+}
+
+// ---- device-resident sliding window -------------------------------------------------
+int ctvio_extend_knots_to(ctvio_handle e, int64_t t_ns, int32_t* n_out) {
+  if (!e || !e->have_knots) return fail(CTVIO_ERR_STATE, "knots have not been set");
+  cudaSetDevice(e->cfg.device);
+  int n = e->nK;
+  while (n < 4 || e->cfg.t0_ns + int64_t(n - 3) * e->cfg.dt_ns < t_ns) ++n;  // se3_spline.h:201-207
+  if (n != e->nK) {
+    const int old = e->nK;
+    // grow both state buffers, keeping the current contents (reserve() reallocates without copying)
+    for (int b = 0; b < 2; ++b) {
+      DevState& x = e->x[b];
+      if (x.q.cap < 4 * size_t(n) || x.p.cap < kPStride * size_t(n) || x.tab.cap < size_t(n)) {
+        DevBuf<double> nq, np_;
+        DevBuf<KnotPair> nt;
+        CUDA_OK(nq.reserve(4 * size_t(n) + 64)); CUDA_OK(np_.reserve(kPStride * size_t(n) + 64)); CUDA_OK(nt.reserve(size_t(n) + 16));
+        if (b == e->cur) {
+          CUDA_OK(cudaMemcpyAsync(nq.p, x.q.p, 4 * size_t(old) * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+          CUDA_OK(cudaMemcpyAsync(np_.p, x.p.p, kPStride * size_t(old) * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+        }
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+        std::swap(x.q.p, nq.p); std::swap(x.q.cap, nq.cap);
+        std::swap(x.p.p, np_.p); std::swap(x.p.cap, np_.cap);
+        std::swap(x.tab.p, nt.p); std::swap(x.tab.cap, nt.cap);
+      }
+    }
+    e->launches += ctvio::launch_extend_knots(e->x[e->cur].ptrs(), old, n, e->stream);
+    e->nK = n;
+    e->sp.n_knots = n;
+    e->structure_dirty = true;
+    e->table_valid = false;
+  }
+  if (n_out) *n_out = n;
+  return CTVIO_OK;
+}
+
+int ctvio_slide_window(ctvio_handle e, int32_t drop_knots, int32_t drop_bias, int32_t new_bias) {
+  if (!e || !e->have_knots) return fail(CTVIO_ERR_STATE, "knots have not been set");
+  if (drop_knots < 0 || drop_bias < 0 || new_bias < 0 || e->nK - drop_knots < 4 || drop_bias > e->nB)
+    return fail(CTVIO_ERR_INVALID, "slide out of range");
+  cudaSetDevice(e->cfg.device);
+  const int nB_new = e->nB - drop_bias + new_bias;
+  for (int b = 0; b < 2; ++b)
+    if (e->x[b].bias.cap < 6 * size_t(std::max(nB_new, 1))) {
+      DevBuf<double> nb;
+      CUDA_OK(nb.reserve(6 * size_t(nB_new) + 96));
+      if (b == e->cur && e->nB) CUDA_OK(cudaMemcpyAsync(nb.p, e->x[b].bias.p, 6 * size_t(e->nB) * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+      CUDA_OK(cudaStreamSynchronize(e->stream));
+      std::swap(e->x[b].bias.p, nb.p); std::swap(e->x[b].bias.cap, nb.cap);
+    }
+  // the shift runs in a scratch copy (overlapping ranges), all on the device
+  CUDA_OK(e->d_tmp.reserve(size_t(8) * e->nK + 6 * size_t(std::max(e->nB, 1)) + 16));
+  e->launches += ctvio::launch_slide_state(e->x[e->cur].ptrs(), e->nK, e->nB, drop_knots, drop_bias, new_bias, e->d_tmp.p, e->stream);
+  e->nK -= drop_knots;
+  e->sp.n_knots = e->nK;
+  e->nB = nB_new;
+  e->cfg.t0_ns += int64_t(drop_knots) * e->cfg.dt_ns;
+  e->sp.t0_ns = e->cfg.t0_ns;
+  // the active prior's blocks follow the window: knot / bias-node indices are window relative
+  for (size_t b = 0; b < e->prior.type.size(); ++b) {
+    const int t = e->prior.type[b];
+    if (t == CTVIO_BLK_ROT || t == CTVIO_BLK_POS) e->prior.index[b] -= drop_knots;
+    else if (t == CTVIO_BLK_BG || t == CTVIO_BLK_BA) e->prior.index[b] -= drop_bias;
+    if ((t <= CTVIO_BLK_BA) && e->prior.index[b] < 0) return fail(CTVIO_ERR_STATE, "a block of the active prior left the window");
+  }
+  e->prior_dirty = true;
+  e->masks_dirty = true;
+  e->structure_dirty = true;
+  e->table_valid = false;
+  return CTVIO_OK;
+}
+
+int ctvio_remap_landmarks(ctvio_handle e, int32_t n_new, const int32_t* old_index, const double* init_rho) {
+  if (!e || n_new < 0 || (n_new > 0 && (!old_index || !init_rho))) return fail(CTVIO_ERR_INVALID, "bad argument");
+  cudaSetDevice(e->cfg.device);
+  for (int k = 0; k < n_new; ++k)
+    if (old_index[k] >= e->nL) return fail(CTVIO_ERR_INVALID, "old landmark index out of range");
+  cudaStream_t st = e->stream;
+  CUDA_OK(e->d_tmp.reserve(size_t(n_new) + 8));
+  CUDA_OK(e->d_tri_idx.reserve(size_t(n_new) + 1));
+  const int other = e->cur ^ 1;
+  for (int b = 0; b < 2; ++b) CUDA_OK(e->x[b].rho.reserve(size_t(std::max(n_new, e->nL)) + 1) == cudaSuccess ? cudaSuccess : cudaErrorMemoryAllocation);
+  if (n_new) {
+    CUDA_OK(cudaMemcpyAsync(e->d_tmp.p, init_rho, size_t(n_new) * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(e->d_tri_idx.p, old_index, size_t(n_new) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    e->h2d_bytes += size_t(n_new) * 12;
+    // gather into the other state buffer's array, then swap the pointers (no aliasing)
+    e->launches += ctvio::launch_remap_rho(e->x[e->cur].rho.p, e->d_tri_idx.p, e->d_tmp.p, n_new, e->x[other].rho.p, st);
+    CUDA_OK(cudaStreamSynchronize(st));
+    std::swap(e->x[e->cur].rho.p, e->x[other].rho.p);
+    std::swap(e->x[e->cur].rho.cap, e->x[other].rho.cap);
+  }
+  if (n_new != e->nL) e->structure_dirty = true;
+  e->nL = n_new;
+  e->have_rho = true;
+  return CTVIO_OK;
+}
+
+// ---- wire-format ingestion ----------------------------------------------------------
+int ctvio_ingest_feature_cloud(ctvio_handle e, int32_t slot, int64_t t_ns, int32_t n, const float* points, const float* ch_id,
+                               const float* ch_u, const float* ch_v, const float* ch_vx, const float* ch_vy) {
+  (void)ch_u; (void)ch_vx; (void)ch_vy;  // carried by the message, not used by the estimator's factors
+  if (!e || slot < 0 || slot >= ctvio_engine::kFrameSlots || n < 0 || n > ctvio_engine::kFrameCap ||
+      (n > 0 && (!points || !ch_id || !ch_v)))
+    return fail(CTVIO_ERR_INVALID, "bad feature cloud");
+  cudaSetDevice(e->cfg.device);
+  cudaStream_t st = e->stream;
+  CUDA_OK(e->d_frames.reserve(size_t(ctvio_engine::kFrameSlots) * ctvio_engine::kFrameCap));
+  CUDA_OK(e->d_frame_t.reserve(ctvio_engine::kFrameSlots));
+  CUDA_OK(e->d_cloud_stage.reserve(5 * size_t(ctvio_engine::kFrameCap)));
+  e->h_frame_t[slot] = t_ns;
+  e->h_frame_n[slot] = n;
+  CUDA_OK(cudaMemcpyAsync(e->d_frame_t.p + slot, &e->h_frame_t[slot], sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (n) {
+    // the message arrays go up AS THEY ARE (packed float32 triples + float32 channels); conversion happens on the device
+    CUDA_OK(cudaMemcpyAsync(e->d_cloud_stage.p, points, 3 * size_t(n) * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(e->d_cloud_stage.p + 3 * size_t(n), ch_id, size_t(n) * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(e->d_cloud_stage.p + 4 * size_t(n), ch_v, size_t(n) * sizeof(float), cudaMemcpyHostToDevice, st));
+    e->h2d_bytes += 5 * size_t(n) * sizeof(float) + 8;
+    ctvio::UnpackCloudArgs a;
+    a.n = n; a.points = e->d_cloud_stage.p; a.ch_id = e->d_cloud_stage.p + 3 * size_t(n); a.ch_v = e->d_cloud_stage.p + 4 * size_t(n);
+    a.out = e->d_frames.p + size_t(slot) * ctvio_engine::kFrameCap;
+    e->launches += ctvio::launch_unpack_cloud(a, st);
+  }
+  CUDA_OK(cudaStreamSynchronize(st));  // the caller's message buffers may go away
+  return CTVIO_OK;
+}
+
+int ctvio_add_image_features_from_slots(ctvio_handle e, int32_t n, const int32_t* slot_i, const int32_t* idx_i,
+                                        const int32_t* slot_j, const int32_t* idx_j, const int32_t* lm, const int32_t* marg) {
+  if (!e || n < 0 || (n > 0 && (!slot_i || !idx_i || !slot_j || !idx_j || !lm))) return fail(CTVIO_ERR_INVALID, "null argument");
+  if (!e->img.empty() && e->img_desc.empty()) return fail(CTVIO_ERR_STATE, "image factors with host payload are already present");
+  for (int k = 0; k < n; ++k) {
+    const int si = slot_i[k], sj = slot_j[k];
+    if (si < 0 || si >= ctvio_engine::kFrameSlots || sj < 0 || sj >= ctvio_engine::kFrameSlots || idx_i[k] < 0 ||
+        idx_i[k] >= e->h_frame_n[si] || idx_j[k] < 0 || idx_j[k] >= e->h_frame_n[sj])
+      return fail(CTVIO_ERR_INVALID, "feature slot / index out of range");
+    HostImage o{e->h_frame_t[si], e->h_frame_t[sj], 0, 0, {0, 0}, {0, 0}, lm[k], marg ? marg[k] : 0};
+    e->img.push_back(o);
+    e->img_desc.push_back(ctvio::FactorDesc{si * ctvio_engine::kFrameCap + idx_i[k], sj * ctvio_engine::kFrameCap + idx_j[k], lm[k],
+                                            marg ? marg[k] : 0});
+  }
+  e->structure_dirty = true;
+  return CTVIO_OK;
+}
+
+int ctvio_ingest_imu(ctvio_handle e, int32_t n, const void* records, int32_t stride, int32_t off_gyro, int32_t off_accel,
+                     int64_t drop_before_ns) {
+  if (!e || n < 0 || (n > 0 && !records) || stride < 56 || off_gyro < 8 || off_accel < 8 || off_gyro + 24 > stride ||
+      off_accel + 24 > stride)
+    return fail(CTVIO_ERR_INVALID, "bad IMU record layout");
+  cudaSetDevice(e->cfg.device);
+  cudaStream_t st = e->stream;
+  // retire samples older than drop_before_ns (RemoveIMUData, trajectory_manager.cpp:472-475): a device-side shift
+  size_t keep_from = 0;
+  while (keep_from < e->h_imu_tab_t.size() && e->h_imu_tab_t[keep_from] < drop_before_ns) ++keep_from;
+  const size_t kept = e->h_imu_tab_t.size() - keep_from, total = kept + size_t(n);
+  if (e->d_imu_tab_t.cap < total) {
+    DevBuf<longlong2> nt;
+    DevBuf<double2> ng;
+    CUDA_OK(nt.reserve(2 * total + 256)); CUDA_OK(ng.reserve(3 * (2 * total + 256)));
+    if (kept) {
+      CUDA_OK(cudaMemcpyAsync(nt.p, e->d_imu_tab_t.p + keep_from, kept * sizeof(longlong2), cudaMemcpyDeviceToDevice, st));
+      CUDA_OK(cudaMemcpyAsync(ng.p, e->d_imu_tab_ga.p + 3 * keep_from, 3 * kept * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+    std::swap(e->d_imu_tab_t.p, nt.p); std::swap(e->d_imu_tab_t.cap, nt.cap);
+    std::swap(e->d_imu_tab_ga.p, ng.p); std::swap(e->d_imu_tab_ga.cap, ng.cap);
+  } else if (keep_from > 0 && kept > 0) {
+    CUDA_OK(e->d_tmp.reserve(8 * kept));
+    e->launches += ctvio::launch_shift_imu_table(e->d_imu_tab_t.p, e->d_imu_tab_ga.p, int(keep_from), int(kept), e->d_tmp.p, st);
+  }
+  e->h_imu_tab_t.erase(e->h_imu_tab_t.begin(), e->h_imu_tab_t.begin() + keep_from);
+  if (n) {
+    CUDA_OK(e->d_imu_raw.reserve(size_t(n) * stride));
+    CUDA_OK(cudaMemcpyAsync(e->d_imu_raw.p, records, size_t(n) * stride, cudaMemcpyHostToDevice, st));  // records as they are
+    e->h2d_bytes += size_t(n) * stride;
+    ctvio::UnpackImuArgs a;
+    a.n = n; a.raw = e->d_imu_raw.p; a.stride = stride; a.off_gyro = off_gyro; a.off_accel = off_accel;
+    a.kf_t = nullptr; a.n_kf = 0; a.dst0 = int(kept); a.t_node = e->d_imu_tab_t.p; a.ga = e->d_imu_tab_ga.p;
+    e->launches += ctvio::launch_unpack_imu(a, st);
+    const unsigned char* rec = static_cast<const unsigned char*>(records);
+    for (int k = 0; k < n; ++k) {
+      int64_t t;
+      std::memcpy(&t, rec + size_t(k) * stride, sizeof(t));
+      e->h_imu_tab_t.push_back(t);
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return CTVIO_OK;
+}
+
+int ctvio_add_imu_from_table(ctvio_handle e, int64_t t_min, int64_t t_max, int32_t n_kf, const int64_t* kf_t, int32_t fixed_node,
+                             int64_t marg_before_ns, int32_t* n_added) {
+  if (!e || (fixed_node < 0 && (n_kf <= 0 || !kf_t))) return fail(CTVIO_ERR_INVALID, "bad argument");
+  if (!e->imu.empty() && e->imu_src.empty()) return fail(CTVIO_ERR_STATE, "IMU factors with host payload are already present");
+  int added = 0;
+  for (size_t k = 0; k < e->h_imu_tab_t.size(); ++k) {
+    const int64_t t = e->h_imu_tab_t[k];
+    if (t < t_min) continue;      // trajectory_manager.cpp:391-394
+    if (t >= t_max) break;
+    int node = fixed_node;
+    if (node < 0) {               // bias index of the sample (:396-412)
+      if (t < kf_t[0]) node = 0;
+      else if (t >= kf_t[n_kf - 1]) node = n_kf - 1;
+      else
+        for (int i = 1; i < n_kf; ++i)
+          if (t >= kf_t[i - 1] && t < kf_t[i]) { node = i - 1; break; }
+    }
+    HostImu o{t, {0, 0, 0}, {0, 0, 0}, node, t < marg_before_ns ? 1 : 0};
+    e->imu.push_back(o);
+    e->imu_src.push_back(int32_t(k));
+    ++added;
+  }
+  if (n_added) *n_added = added;
+  e->structure_dirty = true;
+  return CTVIO_OK;
+}
+
+int ctvio_transfer_stats(ctvio_handle e, int64_t* h2d_bytes, int64_t* d2h_bytes, int32_t reset) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  if (h2d_bytes) *h2d_bytes = int64_t(e->h2d_bytes + g_upload_bytes);
+  if (d2h_bytes) *d2h_bytes = int64_t(e->d2h_bytes);
+  if (reset) { e->h2d_bytes = e->d2h_bytes = 0; g_upload_bytes = 0; }
   return CTVIO_OK;
 }
 

@@ -16,6 +16,8 @@
 // one-sided Jacobi SVD on the 4x4 R: same conditioning as the reference (no A'A squaring), no local-memory arrays.
 #include "frontend.h"
 
+#include <algorithm>
+
 namespace ctvio {
 
 namespace {
@@ -203,6 +205,81 @@ __global__ void gather_factors_kernel(GatherFactorsArgs a) {
   a.meta[k] = make_int4(fi.row, fj.row, d.lm, d.marg);
 }
 
+// ---- device-resident window bookkeeping: nothing below touches the host ---------------------------
+__global__ void extend_knots_kernel(StatePtrs st, int old_n, int new_n) {
+  const int k = old_n + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= new_n) return;
+  // trajectory_manager.cpp:114-115: extendKnotsTo(max_time, last_knot)
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    st.q[4 * k + c] = st.q[4 * (old_n - 1) + c];
+    st.p[kPStride * k + c] = st.p[kPStride * (old_n - 1) + c];
+  }
+}
+__global__ void slide_copy_kernel(StatePtrs st, int nK, int nB, double* tmp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4 * nK) tmp[i] = st.q[i];
+  if (i < kPStride * nK) tmp[4 * nK + i] = st.p[i];
+  if (i < 6 * nB) tmp[8 * nK + i] = st.bias[i];
+}
+__global__ void slide_shift_kernel(StatePtrs st, int nK, int nB, int dk, int db, int new_bias, const double* tmp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4 * (nK - dk)) st.q[i] = tmp[4 * dk + i];
+  if (i < kPStride * (nK - dk)) st.p[i] = tmp[4 * nK + kPStride * dk + i];
+  const int keepb = nB - db;
+  if (i < 6 * (keepb + new_bias)) {
+    const int b = i / 6, c = i - 6 * b;
+    // kept nodes move down; appended nodes start from the newest estimate (Bgs_[WINDOW_SIZE] after slideWindow)
+    const int srcb = b < keepb ? b + db : nB - 1;
+    st.bias[i] = nB > 0 ? tmp[8 * nK + 6 * srcb + c] : 0.0;
+  }
+}
+__global__ void remap_rho_kernel(const double* old_rho, const int32_t* old_index, const double* init_rho, int n, double* out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n) return;
+  out[l] = old_index[l] >= 0 ? old_rho[old_index[l]] : init_rho[l];
+}
+__global__ void shift_imu_copy_kernel(const longlong2* t, const double2* ga, int from, int count, double* tmp) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  longlong2* tt = reinterpret_cast<longlong2*>(tmp);
+  double2* tg = reinterpret_cast<double2*>(tmp + 2 * size_t(count));
+  tt[k] = t[from + k];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) tg[3 * k + c] = ga[3 * size_t(from + k) + c];
+}
+__global__ void shift_imu_back_kernel(longlong2* t, double2* ga, int count, const double* tmp) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const longlong2* tt = reinterpret_cast<const longlong2*>(tmp);
+  const double2* tg = reinterpret_cast<const double2*>(tmp + 2 * size_t(count));
+  t[k] = tt[k];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) ga[3 * size_t(k) + c] = tg[3 * k + c];
+}
+__global__ void gather_imu_kernel(const int2* src, int n, const longlong2* tab_t, const double2* tab_ga, longlong2* out_t,
+                                  double2* out_ga) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int2 s = src[k];
+  out_t[k] = make_longlong2(tab_t[s.x].x, s.y);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out_ga[3 * size_t(k) + c] = tab_ga[3 * size_t(s.x) + c];
+}
+// linearisation point of the kept blocks of a fresh prior (keep_block_data, marginalization_factor.cpp:223-236)
+__global__ void prior_x0_kernel(StatePtrs st, const int32_t* type, const int32_t* index, int nb, double* x0) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int t = type[b], i = index[b];
+  double v[4] = {0, 0, 0, 0};
+  if (t == 0) { for (int c = 0; c < 4; ++c) v[c] = st.q[4 * i + c]; }
+  else if (t == 1) { for (int c = 0; c < 3; ++c) v[c] = st.p[kPStride * i + c]; }
+  else if (t == 2) { for (int c = 0; c < 3; ++c) v[c] = st.bias[6 * i + c]; }
+  else if (t == 3) { for (int c = 0; c < 3; ++c) v[c] = st.bias[6 * i + 3 + c]; }
+  else if (t == 4) v[0] = *st.ld;
+  for (int c = 0; c < 4; ++c) x0[4 * b + c] = v[c];
+}
+
 }  // namespace
 
 int launch_triangulate(const TriangulateArgs& a, cudaStream_t s) {
@@ -223,6 +300,40 @@ int launch_unpack_imu(const UnpackImuArgs& a, cudaStream_t s) {
 int launch_gather_factors(const GatherFactorsArgs& a, cudaStream_t s) {
   if (a.n <= 0) return 0;
   gather_factors_kernel<<<(a.n + 127) / 128, 128, 0, s>>>(a);
+  return 1;
+}
+
+int launch_extend_knots(const StatePtrs& st, int old_n, int new_n, cudaStream_t s) {
+  if (new_n <= old_n) return 0;
+  extend_knots_kernel<<<(new_n - old_n + 63) / 64, 64, 0, s>>>(st, old_n, new_n);
+  return 1;
+}
+int launch_slide_state(const StatePtrs& st, int nK, int nB, int dk, int db, int new_bias, double* tmp, cudaStream_t s) {
+  const int work = std::max(8 * nK, 6 * (nB + new_bias)) + 1;
+  slide_copy_kernel<<<(work + 127) / 128, 128, 0, s>>>(st, nK, nB, tmp);
+  slide_shift_kernel<<<(work + 127) / 128, 128, 0, s>>>(st, nK, nB, dk, db, new_bias, tmp);
+  return 2;
+}
+int launch_remap_rho(const double* old_rho, const int32_t* old_index, const double* init_rho, int n, double* out, cudaStream_t s) {
+  if (n <= 0) return 0;
+  remap_rho_kernel<<<(n + 127) / 128, 128, 0, s>>>(old_rho, old_index, init_rho, n, out);
+  return 1;
+}
+int launch_shift_imu_table(longlong2* t, double2* ga, int from, int count, double* tmp, cudaStream_t s) {
+  if (count <= 0 || from <= 0) return 0;
+  shift_imu_copy_kernel<<<(count + 127) / 128, 128, 0, s>>>(t, ga, from, count, tmp);
+  shift_imu_back_kernel<<<(count + 127) / 128, 128, 0, s>>>(t, ga, count, tmp);
+  return 2;
+}
+int launch_gather_imu(const int2* src, int n, const longlong2* tab_t, const double2* tab_ga, longlong2* out_t, double2* out_ga,
+                      cudaStream_t s) {
+  if (n <= 0) return 0;
+  gather_imu_kernel<<<(n + 127) / 128, 128, 0, s>>>(src, n, tab_t, tab_ga, out_t, out_ga);
+  return 1;
+}
+int launch_prior_x0(const StatePtrs& st, const int32_t* type, const int32_t* index, int nb, double* x0, cudaStream_t s) {
+  if (nb <= 0) return 0;
+  prior_x0_kernel<<<(nb + 63) / 64, 64, 0, s>>>(st, type, index, nb, x0);
   return 1;
 }
 

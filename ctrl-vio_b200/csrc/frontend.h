@@ -70,4 +70,13 @@ struct GatherFactorsArgs {
 };
 int launch_gather_factors(const GatherFactorsArgs& a, cudaStream_t s);
 
+// device-resident window bookkeeping (all on the device)
+int launch_extend_knots(const StatePtrs& st, int old_n, int new_n, cudaStream_t s);
+int launch_slide_state(const StatePtrs& st, int nK, int nB, int dk, int db, int new_bias, double* tmp, cudaStream_t s);
+int launch_remap_rho(const double* old_rho, const int32_t* old_index, const double* init_rho, int n, double* out, cudaStream_t s);
+int launch_shift_imu_table(longlong2* t, double2* ga, int from, int count, double* tmp, cudaStream_t s);
+int launch_gather_imu(const int2* src, int n, const longlong2* tab_t, const double2* tab_ga, longlong2* out_t, double2* out_ga,
+                      cudaStream_t s);
+int launch_prior_x0(const StatePtrs& st, const int32_t* type, const int32_t* index, int nb, double* x0, cudaStream_t s);
+
 }  // namespace ctvio

@@ -107,5 +107,19 @@ void* comm_create(int rank, int world, const uint8_t* id128, std::string* err);
 void comm_destroy(void* comm);
 // in-place sum-allreduce of n doubles on the stream; returns false on error
 bool comm_allreduce_sum(void* comm, double* buf, size_t n, cudaStream_t s, std::string* err);
+// recv[rank][n_per_rank] <- every rank's send[n_per_rank]
+bool comm_allgather(void* comm, const double* send, double* recv, size_t n_per_rank, cudaStream_t s, std::string* err);
+
+// sharded mode: lower-triangular 64x64 tiles of M + rhs + diagA <-> one contiguous all-reduce buffer
+size_t shard_pack_len(int npad);
+int launch_shard_pack(const LinearLaunch& a, double* packed, cudaStream_t s);
+// after the all-reduce: scatter back, add the LM damping / identity rows (replaces add_damping_kernel)
+int launch_shard_unpack(const LinearLaunch& a, const double* packed, double radius, cudaStream_t s);
+// sharded mode: per-rank scalar blocks (all-gathered, [world][8]) -> the common scalar block: sums of cost / g'd / d'Hd /
+// |dx|^2 / |x|^2 / error flag, maxima of the gradient / step max-norms; identical on every rank, published to the mapped
+// host block like the single-GPU path does
+int launch_shard_scalars_pack(LmScalars* scal, double* send8, cudaStream_t s);
+int launch_shard_scalars_reduce(const double* gathered, int world, LmScalars* scal, LmPublished* pub, unsigned long long seq,
+                                cudaStream_t s);
 
 }  // namespace ctvio

@@ -108,4 +108,104 @@ double measure_fp64_tflops(cudaStream_t s) {
   return flops / (best * 1e-3) / 1e12;
 }
 
+
+// ---- sharded mode: packed all-reduce buffer (lower-triangular tiles only: half the bytes of the dense slab) ----
+size_t shard_pack_len(int npad) {
+  const size_t T = npad / kCholNB;
+  return T * (T + 1) / 2 * kCholNB * kCholNB + 2 * size_t(npad);
+}
+__global__ void shard_pack_kernel(LinearLaunch a, double* packed) {
+  const int T = a.npad / kCholNB, ntile = T * (T + 1) / 2;
+  const int t = blockIdx.x;
+  if (t < ntile) {
+    int ti = 0, rem = t;
+    while (rem > ti) { rem -= ti + 1; ++ti; }
+    const int tj = rem;
+    const double* src = a.M + size_t(ti) * kCholNB * a.npad + tj * kCholNB;
+    double* dst = packed + size_t(t) * kCholNB * kCholNB;
+    for (int e = threadIdx.x; e < kCholNB * kCholNB / 2; e += blockDim.x) {
+      const int r = e >> 5, c = (e & 31) * 2;
+      *reinterpret_cast<double2*>(dst + r * kCholNB + c) = *reinterpret_cast<const double2*>(src + size_t(r) * a.npad + c);
+    }
+  } else {
+    double* tail = packed + size_t(ntile) * kCholNB * kCholNB;
+    for (int i = threadIdx.x; i < a.npad; i += blockDim.x) { tail[i] = a.rhs[i]; tail[a.npad + i] = a.diagA[i]; }
+  }
+}
+__global__ void shard_unpack_kernel(LinearLaunch a, const double* packed, double radius) {
+  const int T = a.npad / kCholNB, ntile = T * (T + 1) / 2;
+  const int t = blockIdx.x;
+  const double* tail = packed + size_t(ntile) * kCholNB * kCholNB;
+  if (t < ntile) {
+    int ti = 0, rem = t;
+    while (rem > ti) { rem -= ti + 1; ++ti; }
+    const int tj = rem;
+    double* dst = a.M + size_t(ti) * kCholNB * a.npad + tj * kCholNB;
+    const double* src = packed + size_t(t) * kCholNB * kCholNB;
+    for (int e = threadIdx.x; e < kCholNB * kCholNB / 2; e += blockDim.x) {
+      const int r = e >> 5, c = (e & 31) * 2;
+      double2 v = *reinterpret_cast<const double2*>(src + r * kCholNB + c);
+      if (ti == tj) {  // LM damping / identity rows on the diagonal (Ceres min/max_lm_diagonal 1e-6 / 1e32)
+        const int i = ti * kCholNB + r;
+        const bool live = i < a.dims.np && !a.cmask[i];
+        if (c == r || c + 1 == r) {
+          double& d = c == r ? v.x : v.y;
+          if (live) {
+            const double sd = a.sc[i] * a.sc[i] * tail[a.npad + i];
+            d += fmin(fmax(sd, 1e-6), 1e32) / radius;
+          } else {
+            d = 1.0;
+          }
+        }
+      }
+      *reinterpret_cast<double2*>(dst + size_t(r) * a.npad + c) = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < a.npad; i += blockDim.x) {
+      const bool live = i < a.dims.np && !a.cmask[i];
+      a.rhs[i] = live ? tail[i] : 0.0;
+      a.diagA[i] = tail[a.npad + i];
+    }
+  }
+}
+int launch_shard_pack(const LinearLaunch& a, double* packed, cudaStream_t s) {
+  const int T = a.npad / kCholNB;
+  shard_pack_kernel<<<T * (T + 1) / 2 + 1, 256, 0, s>>>(a, packed);
+  return 1;
+}
+int launch_shard_unpack(const LinearLaunch& a, const double* packed, double radius, cudaStream_t s) {
+  const int T = a.npad / kCholNB;
+  shard_unpack_kernel<<<T * (T + 1) / 2 + 1, 256, 0, s>>>(a, packed, radius);
+  return 1;
+}
+__global__ void shard_scalars_pack_kernel(LmScalars* scal, double* send8) {
+  send8[0] = scal->cost_eval; send8[1] = scal->gd; send8[2] = scal->dHd; send8[3] = scal->step_norm2;
+  send8[4] = scal->x_norm2; send8[5] = (scal->error_flags != 0) ? 1.0 : 0.0; send8[6] = scal->gmax; send8[7] = scal->dir_max;
+}
+__global__ void shard_scalars_reduce_kernel(const double* g, int world, LmScalars* scal, LmPublished* pub, unsigned long long seq) {
+  double sum[6] = {0, 0, 0, 0, 0, 0}, mx[2] = {0, 0};
+  for (int r = 0; r < world; ++r) {  // fixed order: every rank gets bit-identical scalars
+    for (int k = 0; k < 6; ++k) sum[k] += g[8 * r + k];
+    mx[0] = fmax(mx[0], g[8 * r + 6]);
+    mx[1] = fmax(mx[1], g[8 * r + 7]);
+  }
+  scal->cost_eval = sum[0]; scal->gd = sum[1]; scal->dHd = sum[2]; scal->step_norm2 = sum[3]; scal->x_norm2 = sum[4];
+  scal->err_sum = sum[5]; scal->gmax = mx[0]; scal->dir_max = mx[1];
+  if (pub) {
+    LmScalars out = *scal;
+    pub->s = out;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&pub->seq) = seq;
+  }
+}
+int launch_shard_scalars_pack(LmScalars* scal, double* send8, cudaStream_t s) {
+  shard_scalars_pack_kernel<<<1, 1, 0, s>>>(scal, send8);
+  return 1;
+}
+int launch_shard_scalars_reduce(const double* gathered, int world, LmScalars* scal, LmPublished* pub, unsigned long long seq,
+                                cudaStream_t s) {
+  shard_scalars_reduce_kernel<<<1, 1, 0, s>>>(gathered, world, scal, pub, seq);
+  return 1;
+}
+
 }  // namespace ctvio

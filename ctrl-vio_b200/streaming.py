@@ -176,6 +176,9 @@ class StreamingRunner:
         h2d = 0
 
         # ---- timed region: everything that crosses the C-ABI ----
+        stats = e.lib.has("transfer_stats")
+        if stats:
+            e.TransferStats(reset=True)
         t_start = time.perf_counter()
         e.SetTimeOrigin(s.t0_ns + ks * s.dt_ns)
         e.SetKnots(q, p); e.SetBiases(b); e.SetInvDepths(rho); e.SetLineDelay(self.ld)
@@ -213,6 +216,8 @@ class StreamingRunner:
         qs, ps = e.GetKnots(); bs = e.GetBiases(); rs = e.GetInvDepths(); ld = e.GetLineDelay()
         t_wall = time.perf_counter() - t_start
         d2h = qs.nbytes + ps.nbytes + bs.nbytes + rs.nbytes + 8 + (0 if new_prior is None else new_prior.J.nbytes)
+        if stats:
+            h2d, d2h = e.TransferStats(reset=True)  # the engine's own count (includes its index tables)
 
         # ---- carry the solution over (the reference updates the parameter blocks in place) ----
         self.q[ks:self.ncp] = qs; self.p[ks:self.ncp] = ps
@@ -278,3 +283,221 @@ def c3_window_a(lib, perm_seed=None, device=0):
                        ctrl_to_be_opt_now=nowk, ctrl_to_be_opt_later=later)
     e = setup_estimator(lib, wa, image_marg=img_marg, imu_marg=imu_marg, bias_marg=bias_marg, options=opt, device=device)
     return e, seq, wa, nowk
+
+
+# =====================================================================================================================
+# Device-resident window fed by the wire formats (8f-4)
+
+IMU_RECORD = np.dtype({"names": ["timestamp", "gyro", "accel", "orientation"],
+                       "formats": [np.int64, (np.float64, 3), (np.float64, 3), (np.float64, 4)],
+                       "offsets": [0, 8, 32, 64], "itemsize": 96})  # utils/parameter_struct.h:58-65 (Eigen alignment)
+
+
+def quantize_wire(seq: "syn.Window"):
+    """What survives the tracker's sensor_msgs::PointCloud: float32 bearings (rows are integers already).  Applied to
+    the source sequence so that the classic (host-buffer) and the resident (wire-format) paths see identical numbers."""
+    import copy
+    s = copy.copy(seq)
+    s.pi = seq.pi.astype(np.float32).astype(np.float64)
+    s.pj = seq.pj.astype(np.float32).astype(np.float64)
+    return s
+
+
+class FrameClouds:
+    """The tracker's per-frame messages rebuilt from the synthetic sequence: frame f carries the anchor observation of
+    every landmark anchored in f followed by the observations of older landmarks seen in f (feature id = landmark id)."""
+
+    def __init__(self, seq: "syn.Window"):
+        self.seq = seq
+        n_f = len(seq.kf_times)
+        order_a = np.argsort(seq.anchor_frame, kind="stable")
+        self.anchor_idx = np.empty(len(seq.anchor_frame), np.int32)     # landmark -> index inside its anchor frame's cloud
+        counts_a = np.bincount(seq.anchor_frame, minlength=n_f)
+        start_a = np.concatenate([[0], np.cumsum(counts_a)])
+        self.anchor_idx[order_a] = np.arange(len(order_a)) - start_a[seq.anchor_frame[order_a]]
+        order_o = np.argsort(seq.obs_frame, kind="stable")
+        counts_o = np.bincount(seq.obs_frame, minlength=n_f)
+        start_o = np.concatenate([[0], np.cumsum(counts_o)])
+        self.obs_idx = np.empty(seq.n_obs, np.int32)                     # observation -> index inside its frame's cloud
+        self.obs_idx[order_o] = np.arange(len(order_o)) - start_o[seq.obs_frame[order_o]] + counts_a[seq.obs_frame[order_o]]
+        self._order_a, self._start_a, self._order_o, self._start_o = order_a, start_a, order_o, start_o
+        # first observation of every landmark (its anchor bearing / row are replicated in every factor of the landmark)
+        first = np.full(len(seq.anchor_frame), -1, np.int64)
+        lms, idx = np.unique(seq.lm, return_index=True)
+        first[lms] = idx
+        self._first_obs = first
+
+    def message(self, f):
+        """(points float32 [n,3], id, u, v, vx, vy float32 [n]) of frame f."""
+        s = self.seq
+        la = self._order_a[self._start_a[f]:self._start_a[f + 1]]       # landmarks anchored here
+        oo = self._order_o[self._start_o[f]:self._start_o[f + 1]]       # observations made here
+        fo = self._first_obs[la]
+        ok = fo >= 0
+        xy = np.zeros((len(la), 2)); row = np.zeros(len(la))
+        xy[ok] = s.pi[fo[ok]]; row[ok] = s.rowi[fo[ok]]
+        xy = np.concatenate([xy, s.pj[oo]]); row = np.concatenate([row, s.rowj[oo].astype(np.float64)])
+        ids = np.concatenate([la, s.lm[oo]]).astype(np.float32)
+        n = len(ids)
+        pts = np.ones((n, 3), np.float32); pts[:, :2] = xy
+        z = np.zeros(n, np.float32)
+        return pts, ids, (syn.FX * xy[:, 0] + syn.U0).astype(np.float32) if hasattr(syn, "FX") else z, row.astype(np.float32), z, z
+
+
+class ResidentRunner(StreamingRunner):
+    """The same per-image cycle with the window living in HBM: the new image's PointCloud and the new IMUData records go
+    up as they are, control points are extended / dropped on the device, inverse depths are re-indexed on the device,
+    the prior is handed over device-to-device, and the factor payload is gathered from the resident tables (only index
+    tables cross the boundary).  MARGIN_OLD only (every frame a keyframe, the C5 configuration)."""
+
+    def __init__(self, lib, seq, **kw):
+        assert not kw.get("second_new_every"), "the resident runner implements the MARGIN_OLD slide only"
+        super().__init__(lib, seq, **kw)
+        self.clouds = FrameClouds(seq)
+        self.n_slots = 16
+        self.imu_sent = 0          # samples of the source sequence already ingested
+        self.prev_lm_global = None
+        self.prev_ks = None
+        self.readback = None
+
+    def _imu_records(self, lo, hi):
+        s = self.seq
+        rec = np.zeros(hi - lo, IMU_RECORD)
+        rec["timestamp"] = s.imu_t[lo:hi]; rec["gyro"] = s.imu_gyro[lo:hi]; rec["accel"] = s.imu_accel[lo:hi]
+        rec["orientation"][:, 3] = 1.0
+        return rec
+
+    def step(self, k=None):
+        s = self.seq
+        e = self.est
+        first = self.step_index == 0
+        t_push = 0.0
+        if first:
+            # the initializer's window: state, the 11 clouds and the IMU samples so far go up once
+            e.SetTimeOrigin(s.t0_ns)
+            e.SetKnots(self.q[:self.ncp], self.p[:self.ncp]); e.SetBiases(self.bias[self.frames]); e.SetLineDelay(self.ld)
+            for f in self.frames:
+                e.IngestFeatureCloud(f % self.n_slots, int(s.kf_times[f]), *self.clouds.message(f))
+            self.base_knot = 0      # global index of the engine's knot 0
+        else:
+            self.frames.append(self.next_frame)
+            self.next_frame += 1
+        frames = np.asarray(self.frames, np.int64)
+        kf = s.kf_times[frames]
+        t_newest = int(kf[-1])
+        t0 = time.perf_counter()
+        max_bef_ns = max_bef_idx = None
+        if not first:
+            f = self.frames[-1]
+            e.IngestFeatureCloud(f % self.n_slots, t_newest, *self.clouds.message(f))
+            max_bef_ns = s.t0_ns + (self.ncp - 3) * s.dt_ns
+            max_bef_idx = self.ncp - 1
+            self.ncp = e.ExtendKnotsTo(t_newest + EXTEND_NS) + self.base_knot
+        hi = int(np.searchsorted(s.imu_t, t_newest, side="right"))
+        if hi > self.imu_sent:
+            opt_min = s.t0_ns + self._knot_of(int(kf[0])) * s.dt_ns
+            e.IngestImu(self._imu_records(self.imu_sent, hi), 8, 32, drop_before_ns=opt_min)
+            self.imu_sent = hi
+        t_push = time.perf_counter() - t0
+        max_t = s.t0_ns + (self.ncp - 3) * s.dt_ns
+        ks = self._knot_of(int(kf[0]))
+        assert ks == self.base_knot, (ks, self.base_knot)
+        nloc = self.ncp - ks
+        nowk, later = 0, self._knot_of(int(kf[1])) - ks
+
+        # ---- host-side index work of the "feature manager" (ids only, not timed like the classic runner's slicing) ----
+        w = syn.subwindow_frames(s, frames, imu_max_ns=min(max_t, t_newest + 1), window_size=WINDOW_SIZE)
+        lm_global = w.meta["lm_global"]
+        if self.prev_lm_global is None:
+            old_index = np.full(len(lm_global), -1, np.int32)
+        else:
+            pos = np.searchsorted(self.prev_lm_global, lm_global)
+            pos = np.clip(pos, 0, len(self.prev_lm_global) - 1)
+            old_index = np.where(self.prev_lm_global[pos] == lm_global, pos, -1).astype(np.int32)
+        init_rho = s.rho0[lm_global]
+        img_marg = (w.anchor_frame[w.lm] == 0).astype(np.int32)  # (inverse depths are positive in the synthetic sequences)
+        bias_marg = np.zeros(len(w.bf_i), np.int32); bias_marg[0] = 1
+        # factor -> (frame slot, index in that frame's cloud) of its two observations
+        sel = self._factor_selection(frames, lm_global)
+        g_lm = lm_global[w.lm]
+        slot_i = (frames[w.anchor_frame[w.lm]] % self.n_slots).astype(np.int32)
+        idx_i = self.clouds.anchor_idx[g_lm]
+        slot_j = (frames[w.obs_frame] % self.n_slots).astype(np.int32)
+        idx_j = self.clouds.obs_idx[sel]
+        R0 = t0_ = None
+        if self.readback is not None:
+            qn, pn = self.readback[0][ks - self.prev_ks], self.readback[1][ks - self.prev_ks]
+        else:
+            qn, pn = self.q[ks], self.p[ks]
+        R0 = syn.qrot(qn[None], np.eye(3)).T.copy(); t0_ = np.array(pn, float)
+
+        # ---- timed region ----
+        e.TransferStats(reset=True) if not first else None
+        t_start = time.perf_counter()
+        e.RemapLandmarks(old_index, init_rho)
+        init_summary = None
+        if not first and self.predictor:
+            e.SetOptions(self._make_options(fixed_knot_index=max_bef_idx - ks, lock_wb=True, lock_ab=True, fix_ld=True))
+            e.ClearFactors()
+            e.EnablePrior(False)
+            n_init = e.AddImuFromTable(max_bef_ns, max_t, fixed_node=len(frames) - 1)
+            if n_init > 0:
+                init_summary = e.Solve(self.init_iters)
+        e.SetOptions(self._make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER, is_marg_state=True,
+                                        ctrl_to_be_opt_now=nowk, ctrl_to_be_opt_later=later))
+        e.ClearFactors()
+        e.EnablePrior(True)
+        e.AddImageFeaturesFromSlots(slot_i, idx_i, slot_j, idx_j, w.lm, img_marg)
+        opt_min = s.t0_ns + ks * s.dt_ns
+        e.AddImuFromTable(opt_min, min(max_t, t_newest + 1), kf_times=kf, marg_before_ns=int(kf[1]))
+        e.AddBiasFactor(w.bf_i, w.bf_j, w.bf_sqrt_info, bias_marg)
+        t_built = time.perf_counter()
+        summ = e.Solve(self.iters)
+        t_solved = time.perf_counter()
+        e.GaugeRealign(nowk, R0, t0_)
+        n_out = C_int32(); nb_out = C_int32()
+        e.lib.call("marginalize", e.h, byref(n_out), byref(nb_out))
+        if n_out.value > 0:
+            e.AdoptPrior()           # device-to-device
+        t_marged = time.perf_counter()
+        qs, ps = e.GetKnots(); ld = e.GetLineDelay()   # the trajectory is the product the caller publishes
+        drop_knots = later
+        e.SlideWindow(drop_knots, 1, 1)                # slideWindowOld: oldest frame's control points and bias node leave
+        t_wall = time.perf_counter() - t_start
+        h2d, d2h = (0, 0) if first else e.TransferStats(reset=True)
+
+        self.q[ks:self.ncp] = qs; self.p[ks:self.ncp] = ps
+        self.ld = ld
+        self.readback, self.prev_ks, self.prev_lm_global = (qs, ps), ks, lm_global
+        self.base_knot = ks + drop_knots
+        self.frames.pop(0)
+        rec = dict(window=self.step_index, ms=1e3 * (t_wall + t_push), prior_const=0.0,
+                   ms_build_and_predict=1e3 * (t_built - t_start + t_push), ms_solve=1e3 * (t_solved - t_built),
+                   ms_realign_marginalize=1e3 * (t_marged - t_solved), ms_readback=1e3 * (t_start + t_wall - t_marged),
+                   iterations=summ.iterations, final_cost=summ.final_cost, initial_cost=summ.initial_cost,
+                   termination=summ.termination, n_obs=w.n_obs, n_imu=len(w.imu_t), n_knots=nloc, n_lm=len(lm_global),
+                   device_ms=summ.device_ms, marg_flag=MARGIN_OLD,
+                   init_iterations=None if init_summary is None else init_summary.iterations, init_n_imu=0,
+                   init_device_ms=0.0 if init_summary is None else init_summary.device_ms, prior_dim=n_out.value,
+                   h2d_bytes=h2d, d2h_bytes=d2h)
+        self.records.append(rec)
+        self.step_index += 1
+        return rec
+
+    def _factor_selection(self, frames, lm_global):
+        """indices (into the source sequence's observation arrays) of the window's factors, in subwindow_frames order"""
+        s = self.seq
+        pos = -np.ones(len(s.kf_times), np.int64); pos[frames] = np.arange(len(frames))
+        keep = np.zeros(len(s.rho_gt), bool); keep[lm_global] = True
+        return np.nonzero(keep[s.lm] & (pos[s.obs_frame] >= 0))[0]
+
+    def sync_state_to_host(self):
+        """full state read-back (tests): biases of the window's frames and inverse depths of its landmarks.
+        Call right after step(): the engine's window has already slid by one keyframe."""
+        e = self.est
+        b = e.GetBiases()
+        self.bias[np.asarray(self.frames[:len(b) - 1])] = b[:-1]
+        return b
+
+
+from ctypes import byref, c_int32 as C_int32  # noqa: E402  (used by ResidentRunner.step)

@@ -222,6 +222,52 @@ int ctvio_triangulate(ctvio_handle h, int32_t n_frames, const double* Rs_rowmajo
                       const int32_t* start_frame, const int32_t* obs_offset, const double* obs_point_xyz,
                       int32_t window_size, double init_depth, double* depth_inout);
 
+/* ---- device-resident sliding window: the per-image problem build of TrajectoryManager moved behind
+ * the boundary.  State (control points, bias nodes, inverse depths, line delay) and the prior stay in HBM from one
+ * window to the next; only what is NEW crosses the boundary. ----
+ * replaces TrajectoryManager::ExtendTrajectory (estimator/trajectory_manager.cpp:108-120, spline/se3_spline.h:201-207):
+ * control points are appended on the device (copies of the last one) until maxTimeNs() >= t_ns. */
+int ctvio_extend_knots_to(ctvio_handle h, int64_t t_ns, int32_t* n_knots_out);
+/* replaces VisualOdometry::SlideWindow + the growing-spline convention: the first n_drop_knots control points and
+ * n_drop_bias bias nodes leave the window (device-side shift, time origin advanced), n_new_bias nodes are appended as
+ * copies of the newest one (Bgs_/Bas_[WINDOW_SIZE]); the ACTIVE prior's knot / bias block indices are re-based. */
+int ctvio_slide_window(ctvio_handle h, int32_t n_drop_knots, int32_t n_drop_bias, int32_t n_new_bias);
+/* replaces FeatureManager::getDepthVector / setDepth re-indexing (visual_odometry/feature_manager.cpp:139-170): landmark l
+ * of the new window takes the inverse depth of old landmark old_index[l] (>= 0), else init_inv_depth[l]. */
+int ctvio_remap_landmarks(ctvio_handle h, int32_t n_landmarks, const int32_t* old_index, const double* init_inv_depth);
+/* The reference builds a fresh TrajectoryEstimator without the prior for InitTrajectory (trajectory_manager.cpp:297);
+ * here the resident prior is switched off / on instead of being cleared and re-uploaded. */
+int ctvio_enable_prior(ctvio_handle h, int32_t on);
+/* (ctvio_adopt_prior above hands the prior of ctvio_marginalize over device-to-device: J_lin, r_lin and the
+ *  linearisation point never visit the host unless ctvio_get_prior is called.) */
+
+/* ---- wire formats as they are ----
+ * replaces FeatureMsg2Image (visual_odometry/visual_struct.h:98-121) on the tracker's sensor_msgs::PointCloud
+ * (visual_feature/feature_tracker_node.cpp:146-184): points = geometry_msgs::Point32[] (packed float32 x, y, z = 1),
+ * channels[0..4] = id, u, v, velocity_x, velocity_y (float32 arrays).  The arrays are uploaded unchanged and unpacked on
+ * the device into frame slot `frame_slot` (0..15) of the resident feature table. */
+int ctvio_ingest_feature_cloud(ctvio_handle h, int32_t frame_slot, int64_t t_ns, int32_t n_points, const float* points_xyz,
+                               const float* ch_id, const float* ch_u, const float* ch_v, const float* ch_vx,
+                               const float* ch_vy);
+/* replaces the AddImageFeatureDelayAnalytic loop of UpdateTrajectory (trajectory_manager.cpp:353-385) for factors whose
+ * two observations are features idx_i / idx_j of resident frame slots slot_i / slot_j (anchor / observation): only the
+ * indices cross the boundary, times / bearings / rows are gathered on the device. */
+int ctvio_add_image_features_from_slots(ctvio_handle h, int32_t n, const int32_t* slot_i, const int32_t* idx_i,
+                                        const int32_t* slot_j, const int32_t* idx_j, const int32_t* landmark,
+                                        const int32_t* marg);
+/* replaces TrajectoryManager::AddIMUData + RemoveIMUData (trajectory_manager.cpp:472-475): n packed IMUData records
+ * (utils/parameter_struct.h:58-65: int64 timestamp @0, Vector3d gyro @off_gyro, Vector3d accel @off_accel, record size
+ * stride_bytes) are appended to the resident IMU table as they are; samples older than drop_before_ns are retired. */
+int ctvio_ingest_imu(ctvio_handle h, int32_t n, const void* imu_data, int32_t stride_bytes, int32_t off_gyro,
+                     int32_t off_accel, int64_t drop_before_ns);
+/* replaces the AddIMUMeasurementAnalytic loops (trajectory_manager.cpp:388-417 with kf_times / fixed_node < 0: bias node
+ * from the keyframe interval; :301-310 InitTrajectory with fixed_node >= 0) over the resident samples in [t_min, t_max);
+ * samples before marg_before_ns are flagged for marginalization (:239-253). */
+int ctvio_add_imu_from_table(ctvio_handle h, int64_t t_min_ns, int64_t t_max_ns, int32_t n_kf, const int64_t* kf_times,
+                             int32_t fixed_node, int64_t marg_before_ns, int32_t* n_added);
+/* bytes moved host<->device by the C-ABI calls since the last reset (state, factors, priors, index tables) */
+int ctvio_transfer_stats(ctvio_handle h, int64_t* h2d_bytes, int64_t* d2h_bytes, int32_t reset);
+
 /* ---- measurement support (bench.py roofline) ----
  * Average CUDA-event duration (ms, on the engine stream) of one launch of each stage of an LM step at the
  * current state, over `reps` launches after 3 warm-up launches.  flush_l2 != 0 writes a 256 MiB scratch

@@ -30,7 +30,7 @@ def oracle_lib():
             if f.endswith((".cpp", ".hpp"))] + [os.path.join(REPO, "include", "ctvio.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["make", "-C", os.path.join(REPO, "oracle")], check=True, capture_output=True)
-    return pkg.CtvioLib(so, "ctvo_", optional=("nccl_unique_id", "comm_init"))
+    return pkg.CtvioLib(so, "ctvo_", optional=pkg.binding.DEVICE_ONLY_SYMBOLS)
 
 
 @pytest.fixture(scope="session")

@@ -59,7 +59,7 @@ def golden_cases(lib):
 
 if __name__ == "__main__":
     so = os.path.join(ROOT, "oracle", "liboracle.so")
-    lib = pkg.CtvioLib(so, "ctvo_", optional=("nccl_unique_id", "comm_init"))
+    lib = pkg.CtvioLib(so, "ctvo_", optional=pkg.binding.DEVICE_ONLY_SYMBOLS)
     data = golden_cases(lib)
     path = os.path.join(ROOT, "tests", "golden", "small_window.npz")
     np.savez_compressed(path, **data)

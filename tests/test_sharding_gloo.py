@@ -22,7 +22,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     pkg = importlib.import_module("ctrl-vio_b200"); syn = pkg.synthetic
     lib = pkg.CtvioLib(os.path.join(os.path.dirname(HERE), "oracle", "liboracle.so"), "ctvo_",
-                       optional=("nccl_unique_id", "comm_init"))
+                       optional=pkg.binding.DEVICE_ONLY_SYMBOLS)
     w = syn.config_c2(fix_ld=False)
     nL = len(w.rho0)
     sel = (w.lm >= rank * nL // world) & (w.lm < (rank + 1) * nL // world)

@@ -7,7 +7,7 @@ st = importlib.import_module("ctrl-vio_b200.streaming")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 seq = st.config_c5_sequence(n + 1)
 olib = pkg.CtvioLib(os.path.join(os.path.dirname(os.path.dirname(pkg.LIB_PATH)), "..", "oracle", "liboracle.so"), "ctvo_",
-                    optional=("nccl_unique_id", "comm_init"))
+                    optional=pkg.binding.DEVICE_ONLY_SYMBOLS)
 g = st.StreamingRunner(pkg.load(), seq, iters=8); o = st.StreamingRunner(olib, seq, iters=8)
 for k in range(n):
     rg, ro = g.step(k), o.step(k)

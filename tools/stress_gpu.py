@@ -7,7 +7,7 @@ pkg = importlib.import_module("ctrl-vio_b200"); syn = pkg.synthetic
 from helpers import rot_angle_between
 lib = pkg.load()
 olib = pkg.CtvioLib(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "liboracle.so"), "ctvo_",
-                    optional=("nccl_unique_id", "comm_init"))
+                    optional=pkg.binding.DEVICE_ONLY_SYMBOLS)
 bad = 0
 for name, mk, reps in (("c2", syn.config_c2, 2000), ("c4", syn.config_c4, 300)):
     est = pkg.setup_estimator(lib, mk())
