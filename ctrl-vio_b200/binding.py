@@ -93,13 +93,13 @@ class Summary(C.Structure):
 # every symbol include/ctvio.h declares (without prefix); used by the
 # export-completeness test and by the binder.
 ABI_SYMBOLS = [
-    "last_error", "abi_version", "create", "destroy", "set_options",
+    "last_error", "abi_version", "create", "destroy", "set_options", "set_deterministic",
     "set_knots", "set_biases", "set_inv_depths", "set_line_delay", "set_time_origin",
     "get_knots", "get_biases", "get_inv_depths", "get_line_delay",
     "clear_factors", "add_image_features", "add_imu_measurements", "add_bias_factors", "set_prior",
     "solve", "gauge_realign", "marginalize", "get_prior", "adopt_prior",
     "save_state", "restore_state",
-    "eval_image_factors", "eval_imu_factors", "eval_cost", "normal_equations",
+    "eval_image_factors", "eval_imu_factors", "residual_summary", "eval_cost", "normal_equations",
     "query_trajectory", "triangulate",
     "extend_knots_to", "slide_window", "remap_landmarks", "enable_prior", "ingest_feature_cloud", "add_image_features_from_slots",
     "ingest_imu", "add_imu_from_table", "transfer_stats", "profile_kernels", "measure_fp64_tflops", "selfcheck_solver", "nccl_unique_id", "comm_init",
@@ -108,9 +108,9 @@ ABI_SYMBOLS = [
 
 # entry points a checker library (the CPU oracle mirrors the ABI under `ctvo_`) need not provide: multi-GPU plumbing and
 # the device-residency / wire-format calls, which have no CPU meaning
-DEVICE_ONLY_SYMBOLS = ("nccl_unique_id", "comm_init", "enable_prior", "extend_knots_to", "slide_window", "remap_landmarks", "enable_prior",
+DEVICE_ONLY_SYMBOLS = ("nccl_unique_id", "comm_init", "set_deterministic", "enable_prior", "extend_knots_to", "slide_window", "remap_landmarks", "enable_prior",
                        "ingest_feature_cloud", "add_image_features_from_slots", "ingest_imu", "add_imu_from_table",
-                       "transfer_stats")
+                       "transfer_stats", "residual_summary")
 
 
 def _dp(a):
@@ -219,6 +219,9 @@ class Estimator:
     # --- options / state ---------------------------------------------------
     def SetOptions(self, opt: Options):
         self.lib.call("set_options", self.h, C.byref(opt))
+
+    def SetDeterministic(self, on=True):
+        self.lib.call("set_deterministic", self.h, C.c_int32(int(on)))
 
     def SetKnots(self, q, p):
         q = _f64(q, (-1, 4)); p = _f64(p, (-1, 3))
@@ -347,6 +350,13 @@ class Estimator:
         self.lib.call("eval_imu_factors", self.h, C.c_int32(int(want_jacobians)), _dp(r), _ip(s), _dp(J),
                       C.byref(cost))
         return r, s, J, cost.value
+
+    def ResidualSummary(self, prior_n=0):
+        """GetResidualSummary: ({type: (count, per-component sums of |r|)})."""
+        counts = np.zeros(4, np.int32); sums = np.zeros(18); pr = np.zeros(max(prior_n, 1))
+        self.lib.call("residual_summary", self.h, _ip(counts), _dp(sums), _dp(pr) if prior_n else None)
+        return {"image": (int(counts[0]), sums[0:2].copy()), "imu": (int(counts[1]), sums[2:8].copy()),
+                "bias": (int(counts[2]), sums[8:14].copy()), "prior": (int(counts[3]), pr[:prior_n].copy())}
 
     def EvalCost(self):
         cost = C.c_double()

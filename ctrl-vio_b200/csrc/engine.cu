@@ -89,6 +89,8 @@ struct ctvio_engine {
   SplineParams sp;
   RigParams rig;
   bool use_tma = true;
+  bool deterministic = false;   // ctvio_set_deterministic: ordered flushes, single stream (kernels.h)
+  DevBuf<int32_t> d_ticket;     // [0] kernel flush ticket, [1] scalar flush ticket
 
   // sizes
   int nK = 0, nB = 0, nL = 0;
@@ -585,6 +587,7 @@ VisualLaunch visual_launch(ctvio_engine* e, int xb, int nb, double cauchy) {
   v.cmask = e->d_cmask.p;
   v.scal = e->d_scal.p;
   v.use_tma = e->use_tma;
+  v.det_ticket = e->deterministic ? e->d_ticket.p : nullptr;
   return v;
 }
 ImuLaunch imu_launch(ctvio_engine* e, int xb, int nb) {
@@ -599,6 +602,7 @@ ImuLaunch imu_launch(ctvio_engine* e, int xb, int nb) {
   v.rig = e->rig;
   v.cmask = e->d_cmask.p;
   v.scal = e->d_scal.p;
+  v.det_ticket = e->deterministic ? e->d_ticket.p : nullptr;
   return v;
 }
 SmallFactorsLaunch small_launch(ctvio_engine* e, int xb, int nb) {
@@ -610,6 +614,7 @@ SmallFactorsLaunch small_launch(ctvio_engine* e, int xb, int nb) {
   v.dims = e->dims();
   v.cmask = e->d_cmask.p;
   v.scal = e->d_scal.p;
+  v.deterministic = e->deterministic ? 1 : 0;
   return v;
 }
 LinearLaunch linear_launch(ctvio_engine* e, int nb) {
@@ -633,6 +638,7 @@ LinearLaunch linear_launch(ctvio_engine* e, int nb) {
   a.hh = e->d_hh.p; a.dc = e->d_dc.p; a.dl = e->d_dl.p;
   a.npad = e->npad;
   a.scal = e->d_scal.p;
+  a.det_ticket = e->deterministic ? e->d_ticket.p : nullptr;
   return a;
 }
 
@@ -695,6 +701,7 @@ int shard_check_ownership(ctvio_engine* e) {
 int lm_step(ctvio_engine* e, int nb, double radius, const ApplyLaunch* fused_apply = nullptr) {
   LinearLaunch lin = linear_launch(e, nb);
   cudaStream_t st = e->stream;
+  if (e->deterministic) cudaMemsetAsync(e->d_ticket.p, 0, 2 * sizeof(int32_t), st);
   e->launches += launch_reduced_system(lin, radius, st);
   if (e->world > 1) {
     // one all-reduce of the lower-triangular tiles + rhs + diagonal (half the bytes of the dense slab), damping after it
@@ -727,6 +734,17 @@ void evaluate(ctvio_engine* e, int xb, int nb, bool full, bool reset_cost = true
   // fork: the (latency-bound) IMU + bias + prior kernels overlap the visual kernel on a second stream
   // sharded mode: IMU / bias / prior factors live on rank 0 only (every rank holds its own landmark shard)
   const bool fork = (e->rank == 0) && (!e->imu.empty() || !e->biasf.empty() || (e->prior.n > 0 && e->prior_enabled));
+  if (e->deterministic) {
+    // one stream, one kernel at a time, every kernel flushing in block order: every sum has ONE accumulation order
+    cudaMemsetAsync(e->d_ticket.p, 0, 2 * sizeof(int32_t), st);
+    e->launches += launch_visual(visual_launch(e, xb, nb, e->cfg.cauchy_solve), full, st);
+    if (fork) {
+      cudaMemsetAsync(e->d_ticket.p, 0, 2 * sizeof(int32_t), st);
+      e->launches += launch_imu(imu_launch(e, xb, nb), full, st);
+      e->launches += launch_small_factors(small_launch(e, xb, nb), full, st);
+    }
+    return;
+  }
   if (fork) {
     cudaEventRecord(e->ev_fork, st);
     cudaStreamWaitEvent(e->stream2, e->ev_fork, 0);
@@ -823,6 +841,7 @@ int ctvio_create(const ctvio_config* cfg, ctvio_handle* out) {
   e->rig.w_img = cfg->image_weight;
   e->rig.gravity = V3{cfg->gravity[0], cfg->gravity[1], cfg->gravity[2]};
   for (int k = 0; k < 6; ++k) e->rig.imu_info[k] = cfg->imu_info[k];
+  if (const char* det = std::getenv("CTVIO_DETERMINISTIC")) e->deterministic = det[0] == '1';
   const char* no_tma = std::getenv("CTVIO_NO_TMA");
   e->use_tma = !(no_tma && no_tma[0] == '1');
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -832,7 +851,8 @@ int ctvio_create(const ctvio_config* cfg, ctvio_handle* out) {
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_zero, cudaEventDisableTiming) != cudaSuccess ||
       cudaHostAlloc(&e->h_pub, sizeof(LmPublished), cudaHostAllocMapped) != cudaSuccess ||
-      cudaMallocHost(&e->h_scal, sizeof(LmScalars)) != cudaSuccess || e->d_scal.reserve(1) != cudaSuccess) {
+      cudaMallocHost(&e->h_scal, sizeof(LmScalars)) != cudaSuccess || e->d_scal.reserve(1) != cudaSuccess ||
+      e->d_ticket.reserve(4) != cudaSuccess) {
     delete e;
     return fail(CTVIO_ERR_CUDA, "could not create stream / events / scalar block");
   }
@@ -1124,9 +1144,11 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     ap.clamp_ld = e->opt.fix_ld ? 0 : 1;
     ap.ld_lower = e->opt.ld_lower; ap.ld_upper = e->opt.ld_upper;
     ap.scal = e->d_scal.p;
+    ap.det_ticket = e->deterministic ? e->d_ticket.p : nullptr;
     return ap;
   };
   auto apply = [&](int from, int to, double alpha, bool reset = true) {
+    if (e->deterministic) cudaMemsetAsync(e->d_ticket.p, 0, 2 * sizeof(int32_t), st);
     e->launches += launch_apply_step(make_apply(from, to, alpha), st, reset);
   };
 
@@ -1377,6 +1399,41 @@ int ctvio_eval_imu_factors(ctvio_handle e, int32_t want_jac, double* r, int32_t*
   if (s && n) CUDA_OK(cudaMemcpy(s, ds.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
   if (J && want_jac && n) CUDA_OK(cudaMemcpy(J, dJ.p, 156 * n * sizeof(double), cudaMemcpyDeviceToHost));
   if (cost) *cost = e->h_scal->cost_eval;
+  return CTVIO_OK;
+}
+
+int ctvio_residual_summary(ctvio_handle e, int32_t* counts, double* sums, double* prior_sum) {
+  if (!e || !counts || !sums) return fail(CTVIO_ERR_INVALID, "null argument");
+  cudaSetDevice(e->cfg.device);
+  int rc = prepare(e);
+  if (rc) return rc;
+  ensure_table(e);
+  cudaStream_t st = e->stream;
+  const size_t ni = e->img.size(), nm = e->imu.size(), nb = e->biasf.size();
+  const int np_ = e->prior_enabled ? e->prior.n : 0;
+  DevBuf<double> dr, dout;
+  DevBuf<int32_t> ds;
+  CUDA_OK(dr.reserve(2 * ni + 6 * nm + 8));
+  CUDA_OK(ds.reserve(2 * ni + nm + 8));
+  CUDA_OK(dout.reserve(18));
+  CUDA_OK(cudaMemsetAsync(dout.p, 0, 18 * sizeof(double), st));
+  // residuals without the loss (cauchy scale 0 = no corrector), original factor order does not matter for the sums
+  if (ni) e->launches += launch_probe_image(visual_launch(e, e->cur, e->cur, 0.0), e->d_img_orig.p, false, dr.p, ds.p, nullptr, st);
+  if (nm) e->launches += launch_probe_imu(imu_launch(e, e->cur, e->cur), e->d_imu_orig.p, false, dr.p + 2 * ni, ds.p + 2 * ni, nullptr, st);
+  e->launches += ctvio::launch_abs_column_sums(dr.p, int(ni), 2, dout.p, st);
+  e->launches += ctvio::launch_abs_column_sums(dr.p + 2 * ni, int(nm), 6, dout.p + 2, st);
+  e->launches += ctvio::launch_bias_abs_sums(e->d_bf_ij.p, e->d_bf_s.p, int(nb), e->x[e->cur].bias.p, dout.p + 8, st);
+  if (np_ > 0) {
+    e->launches += launch_small_factors(small_launch(e, e->cur, e->cur), false, st);  // leaves r + J dx in prior.res
+  }
+  rc = read_scalars(e);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpy(sums, dout.p, 18 * sizeof(double), cudaMemcpyDeviceToHost));
+  counts[0] = int32_t(ni); counts[1] = int32_t(nm); counts[2] = int32_t(nb); counts[3] = np_ > 0 ? 1 : 0;
+  if (prior_sum && np_ > 0) {
+    CUDA_OK(cudaMemcpy(prior_sum, e->d_prior_res.p, size_t(np_) * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < np_; ++i) prior_sum[i] = std::fabs(prior_sum[i]);
+  }
   return CTVIO_OK;
 }
 
@@ -1878,6 +1935,14 @@ int ctvio_adopt_prior(ctvio_handle e) {
   e->new_prior = ctvio::PriorHost();  // its device buffers are gone
   e->prior_dirty = true;
   e->masks_dirty = true;
+  return CTVIO_OK;
+}
+
+int ctvio_set_deterministic(ctvio_handle e, int32_t on) {
+  if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
+  if (e->world > 1 && on) return fail(CTVIO_ERR_STATE, "deterministic mode is single-GPU");
+  e->deterministic = on != 0;
+  e->structure_dirty = true;  // K1 work items are rebuilt with single-round chunks
   return CTVIO_OK;
 }
 

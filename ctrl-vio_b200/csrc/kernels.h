@@ -155,6 +155,28 @@ inline int device_sm_count() {
   return v;
 }
 
+// ---- deterministic mode (ctvio_set_deterministic): the fp64 atomics that merge CTA partial sums are kept, but the CTAs
+// of a kernel perform their flush in BLOCK-INDEX ORDER (a ticket in global memory: CTA i flushes after CTA i-1 has
+// flushed and fenced), so every sum is accumulated in one fixed order and a solve is bit-reproducible run to run.
+// Blocks are dispatched in index order, so a waiting CTA's predecessors are always resident or done (no deadlock).
+// The serialised flush costs time (C2: K1 22 -> ~60 us); it is a verification / regression mode, off by default.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void det_ticket_wait(const int* ticket, int my) {
+  if (!ticket) return;
+  if (threadIdx.x == 0) {
+    int v;
+    do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ticket) : "memory"); } while (v != my);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void det_ticket_done(int* ticket, int my) {
+  if (!ticket) return;
+  __threadfence();   // this thread's atomics are performed before the ticket moves on
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ticket), "r"(my + 1) : "memory");
+}
+#endif
+
 // ---- launch wrappers (each returns the number of kernels it launched) ----------------------------
 int launch_knot_table(const StatePtrs& st, int nK, cudaStream_t s);
 
@@ -172,6 +194,7 @@ struct VisualLaunch {
   const uint8_t* cmask;   // [np] 1 = constant
   LmScalars* scal;
   bool use_tma;
+  int* det_ticket = nullptr;  // deterministic mode: flush in block order
 };
 int launch_visual(const VisualLaunch& a, bool full, cudaStream_t s);
 size_t visual_smem_bytes();
@@ -187,6 +210,7 @@ struct ImuLaunch {
   RigParams rig;
   const uint8_t* cmask;
   LmScalars* scal;
+  int* det_ticket = nullptr;
 };
 int launch_imu(const ImuLaunch& a, bool full, cudaStream_t s);
 
@@ -198,6 +222,7 @@ struct SmallFactorsLaunch {
   ProblemDims dims;
   const uint8_t* cmask;
   LmScalars* scal;
+  int deterministic = 0;  // one thread walks the bias factors / prior columns in order
 };
 int launch_small_factors(const SmallFactorsLaunch& a, bool full, cudaStream_t s);
 
@@ -237,6 +262,7 @@ struct LinearLaunch {
   double* dl;                   // [nL]
   int32_t npad;
   LmScalars* scal;
+  int* det_ticket;              // deterministic mode (K4 parts, step kernels): flush in block order; else null
 };
 int launch_jacobi_scale(const LinearLaunch& a, cudaStream_t s);
 // builds the damped, scaled reduced system, factors it, solves and back-substitutes: dc, dl, gd, dHd
@@ -274,6 +300,7 @@ struct ApplyLaunch {
   int32_t clamp_ld;
   double ld_lower, ld_upper;
   LmScalars* scal;
+  int* det_ticket = nullptr;
 };
 int launch_apply_step(const ApplyLaunch& a, cudaStream_t s, bool reset = true);
 // step vectors + full step (alpha = 1) applied in one launch; the per-step accumulators must already be zero

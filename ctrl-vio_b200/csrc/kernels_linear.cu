@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(256, 2) schur_tile_kernel(LinearLaunch a) {
     __syncthreads();
   }
   // flush: M_tile -= acc (several parts may share a tile: fp64 RED atomics), rhs_block -= racc
+  det_ticket_wait(a.det_ticket, blockIdx.x);
   double* tile = a.M + size_t(kCholNB) * it.ti * npad + kCholNB * it.tj;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(256, 2) schur_tile_kernel(LinearLaunch a) {
       }
     }
   }
+  det_ticket_done(a.det_ticket, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,6 +243,7 @@ __device__ __forceinline__ void camera_step_block(const LinearLaunch& a, int blo
   dHd = warp_sum_d(dHd);
   if (lane == 0) { red[0][threadIdx.x >> 5] = gd; red[1][threadIdx.x >> 5] = dHd; red[2][threadIdx.x >> 5] = dmax; }
   __syncthreads();
+  det_ticket_wait(a.det_ticket ? a.det_ticket + 1 : nullptr, blockIdx.x);
   if (threadIdx.x == 0) {
     double g = 0, h = 0, m = 0;
     for (int w = 0; w < 8; ++w) { g += red[0][w]; h += red[1][w]; m = fmax(m, red[2][w]); }
@@ -248,6 +251,7 @@ __device__ __forceinline__ void camera_step_block(const LinearLaunch& a, int blo
     atomicAdd(&a.scal->dHd, h);
     atomic_max_pos(&a.scal->dir_max, m);
   }
+  det_ticket_done(a.det_ticket ? a.det_ticket + 1 : nullptr, blockIdx.x);
 }
 
 // landmark back-substitution + landmark parts of gd / dHd: one WARP per landmark (coalesced reads of
@@ -285,6 +289,7 @@ __device__ __forceinline__ void landmark_step_block(const LinearLaunch& a, int b
   }
   if (lane == 0) { red[0][warp] = gd; red[1][warp] = dHd; red[2][warp] = dmax; red2[0][warp] = xn; red2[1][warp] = sn; }
   __syncthreads();
+  det_ticket_wait(a.det_ticket ? a.det_ticket + 1 : nullptr, blockIdx.x);
   if (threadIdx.x == 0) {
     double g = 0, h = 0, m = 0, x = 0, s = 0;
     for (int w = 0; w < 8; ++w) { g += red[0][w]; h += red[1][w]; m = fmax(m, red[2][w]); x += red2[0][w]; s += red2[1][w]; }
@@ -294,6 +299,7 @@ __device__ __forceinline__ void landmark_step_block(const LinearLaunch& a, int b
     if (x != 0.0) atomicAdd(&a.scal->x_norm2, x);
     if (s != 0.0) atomicAdd(&a.scal->step_norm2, s);
   }
+  det_ticket_done(a.det_ticket ? a.det_ticket + 1 : nullptr, blockIdx.x);
 }
 
 // after the all-reduce of [M | rhs | diagA]
@@ -493,12 +499,14 @@ __device__ __forceinline__ void apply_step_block(const ApplyLaunch& a, const Ste
   xn = warp_sum_d(xn); sn = warp_sum_d(sn);
   if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = xn; red[1][threadIdx.x >> 5] = sn; }
   __syncthreads();
+  det_ticket_wait(a.det_ticket ? a.det_ticket + 1 : nullptr, blockIdx.x);
   if (threadIdx.x == 0) {
     double x = 0, s = 0;
     for (int w = 0; w < 8; ++w) { x += red[0][w]; s += red[1][w]; }
     if (x != 0.0) atomicAdd(&a.scal->x_norm2, x);
     if (s != 0.0) atomicAdd(&a.scal->step_norm2, s);
   }
+  det_ticket_done(a.det_ticket ? a.det_ticket + 1 : nullptr, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(256) apply_step_kernel(ApplyLaunch a) {

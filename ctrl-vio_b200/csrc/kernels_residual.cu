@@ -100,6 +100,7 @@ struct VisArgs {
   const uint8_t* cmask;
   LmScalars* scal;
   int use_tma;
+  int* det_ticket;
 };
 
 struct __align__(128) VisStatic {
@@ -353,8 +354,10 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
               row0[col + c] = r0v; row1[col + c] = r1v;
               row0[col + 3 + c] = p0v; row1[col + 3 + c] = p1v;
 #ifndef CTVIO_EXPERIMENT_NO_W_ATOMICS
-              if (!mr) atomicAdd(Wl + gd + c, r0v * jrho[0] + r1v * jrho[1]);
-              if (!mp) atomicAdd(Wl + gd + 3 + c, p0v * jrho[0] + p1v * jrho[1]);
+              if (!a.det_ticket) {  // (deterministic mode: recomputed from the shared tile inside the ordered flush)
+                if (!mr) atomicAdd(Wl + gd + c, r0v * jrho[0] + r1v * jrho[1]);
+                if (!mp) atomicAdd(Wl + gd + 3 + c, p0v * jrho[0] + p1v * jrho[1]);
+              }
 #endif
             }
           });
@@ -369,11 +372,13 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
             row1[kColLd] = ld_const ? 0.0 : jld[1];
             row0[63] = 0.0; row1[63] = 0.0;
           }
-          if (side == 0) {
-            atomicAdd(a.ne.hl + l, jrho[0] * jrho[0] + jrho[1] * jrho[1]);
-            atomicAdd(a.ne.gl + l, jrho[0] * cm.r[0] + jrho[1] * cm.r[1]);
-          } else {
-            atomicAdd(a.ne.wld + l, row0[kColLd] * jrho[0] + row1[kColLd] * jrho[1]);
+          if (!a.det_ticket) {
+            if (side == 0) {
+              atomicAdd(a.ne.hl + l, jrho[0] * jrho[0] + jrho[1] * jrho[1]);
+              atomicAdd(a.ne.gl + l, jrho[0] * cm.r[0] + jrho[1] * cm.r[1]);
+            } else {
+              atomicAdd(a.ne.wld + l, row0[kColLd] * jrho[0] + row1[kColLd] * jrho[1]);
+            }
           }
         }
       }
@@ -389,12 +394,47 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
       VCLK(2);
       __syncthreads();
       VCLK(3);
+      if (a.det_ticket) {
+        // deterministic mode: the landmark pieces of this round's observations from the finished rows of the shared tile
+        // (same products as the per-lane atomics of the fast path), issued in the CTA's turn
+        det_ticket_wait(a.det_ticket, blockIdx.x * 1024 + base / kVisObsPerRound);
+        if (active && valid) {
+          const int oi = item.start + base + ol;
+          const int l = a.obs.meta[oi].z;
+          const double j0 = row0[kColRho], j1 = row1[kColRho];
+          if (side == 0) {
+            atomicAdd(a.ne.hl + l, j0 * j0 + j1 * j1);
+            atomicAdd(a.ne.gl + l, j0 * row0[kColR] + j1 * row1[kColR]);
+          } else {
+            atomicAdd(a.ne.wld + l, row0[kColLd] * j0 + row1[kColLd] * j1);
+          }
+        }
+        // the two knot windows of an observation may overlap (same global dims): anchor side first, then the other one
+        for (int ph = 0; ph < 2; ++ph) {
+          if (active && valid && side == ph) {
+            const int oi = item.start + base + ol;
+            const int l = a.obs.meta[oi].z;
+            const double j0 = row0[kColRho], j1 = row1[kColRho];
+            double* Wl = a.ne.W + (a.lm.woff[l] - a.lm.lo[l]);
+            const int cb = side * 30, gk0 = w0[side];
+            for (int c = 0; c < 30; ++c) {
+              const double v = row0[cb + c] * j0 + row1[cb + c] * j1;
+              if (v != 0.0) atomicAdd(Wl + 6 * gk0 + c, v);
+            }
+          }
+          __threadfence();
+          __syncthreads();
+        }
+        det_ticket_done(a.det_ticket, blockIdx.x * 1024 + base / kVisObsPerRound);
+      }
       syrk_round(Jt, accs, nround, tid);
       VCLK(4);
     }
   }
 
   // ---- cost + flush ----
+  const int n_rounds = (item.count + kVisObsPerRound - 1) / kVisObsPerRound;
+  det_ticket_wait(a.det_ticket, blockIdx.x * 1024 + (FULL ? n_rounds : 0));
   cost_local = warp_sum(cost_local);
   if (lane == 0) sm.cost_part[warp] = cost_local;
   __syncthreads();
@@ -407,29 +447,56 @@ __global__ void __launch_bounds__(kVisThreads, 1) visual_kernel(const __grid_con
   }
   if (FULL) {
     const int np = a.dims.np;
-    for (int idx = tid; idx < 36 * 64; idx += kVisThreads) {
-      const double val = accs[idx];
-      if (val == 0.0) continue;
-      const int tile = idx >> 6, e = idx & 63;
-      const int la = c_tile_i[tile] * 8 + (e >> 3), lb = c_tile_j[tile] * 8 + (e & 7);
-      if (la > lb || lb > kColR || la >= kColR) continue;
-      const int ga = la < 30 ? 6 * item.wi0 + la : (la < 60 ? 6 * item.wj0 + (la - 30) : a.dims.idx_ld);
-      if (lb == kColR) {
-        atomicAdd(a.ne.gc + ga, val);
-        continue;
+    // Fast mode: one pass.  Deterministic mode: when the two knot windows overlap, different LOCAL entries of this CTA land
+    // on the same global entry; the flush then runs in 11 classes (side of the row dim x side of the column dim, the
+    // mixed class split by the order of the global indices) inside each of which the local -> global map is injective,
+    // with a fence + barrier between classes, so the order of the additions to every address is fixed.
+    const int n_class = a.det_ticket ? 11 : 1;
+    for (int cls = 0; cls < n_class; ++cls) {
+      for (int idx = tid; idx < 36 * 64; idx += kVisThreads) {
+        const double val = accs[idx];
+        if (val == 0.0) continue;
+        const int tile = idx >> 6, e = idx & 63;
+        const int la = c_tile_i[tile] * 8 + (e >> 3), lb = c_tile_j[tile] * 8 + (e & 7);
+        if (la > lb || lb > kColR || la >= kColR) continue;
+        const int sa = la < 30 ? 0 : (la < 60 ? 1 : 2);
+        const int ga = sa == 0 ? 6 * item.wi0 + la : (sa == 1 ? 6 * item.wj0 + (la - 30) : a.dims.idx_ld);
+        if (lb == kColR) {
+          if (n_class > 1 && cls != 8 + sa) continue;
+          atomicAdd(a.ne.gc + ga, val);
+          continue;
+        }
+        const int sb = lb < 30 ? 0 : (lb < 60 ? 1 : 2);
+        const int gb = sb == 0 ? 6 * item.wi0 + lb : (sb == 1 ? 6 * item.wj0 + (lb - 30) : a.dims.idx_ld);
+        if (n_class > 1) {
+          int c;
+          if (sb == 2) c = 5 + sa;                                  // (anchor | obs | ld) x ld
+          else if (sa == sb) c = sa == 0 ? 0 : 4;                   // anchor x anchor, obs x obs
+          else c = ga < gb ? 1 : (ga > gb ? 2 : 3);                 // anchor x obs by the order of the global dims
+          if (c != cls) continue;
+        }
+        const double v = (la != lb && ga == gb) ? 2.0 * val : val;
+        const int g0 = min(ga, gb), g1 = max(ga, gb);
+        atomicAdd(a.ne.A + size_t(g0) * np + g1, v);
       }
-      const int gb = lb < 30 ? 6 * item.wi0 + lb : (lb < 60 ? 6 * item.wj0 + (lb - 30) : a.dims.idx_ld);
-      const double v = (la != lb && ga == gb) ? 2.0 * val : val;
-      const int g0 = min(ga, gb), g1 = max(ga, gb);
-      atomicAdd(a.ne.A + size_t(g0) * np + g1, v);
+      if (n_class > 1) {
+        __threadfence();
+        __syncthreads();
+      }
     }
+  }
+  // the next CTA's first ticket value: (blockIdx.x + 1) * 1024
+  if (a.det_ticket) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.det_ticket), "r"((int(blockIdx.x) + 1) * 1024) : "memory");
   }
   VCLK(5);
 }
 
 int launch_visual(const VisualLaunch& l, bool full, cudaStream_t s) {
   if (l.n_items <= 0) return 0;
-  VisArgs a{l.obs, l.items, l.st, l.ne, l.lm, l.dims, l.sp, l.rig, l.cauchy, l.cmask, l.scal, l.use_tma ? 1 : 0};
+  VisArgs a{l.obs, l.items, l.st, l.ne, l.lm, l.dims, l.sp, l.rig, l.cauchy, l.cmask, l.scal, l.use_tma ? 1 : 0, l.det_ticket};
   static PerDeviceOnce once;
   if (once.first()) {
     cudaFuncSetAttribute(visual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(visual_smem_bytes()));
@@ -456,6 +523,7 @@ struct ImuArgs {
   RigParams rig;
   const uint8_t* cmask;
   LmScalars* scal;
+  int* det_ticket;
 };
 
 constexpr int kImuThreads = 64;
@@ -548,6 +616,7 @@ __global__ void __launch_bounds__(kImuThreads) imu_kernel(const __grid_constant_
       __syncthreads();
     }
     const int np = a.dims.np;
+    det_ticket_wait(a.det_ticket, blockIdx.x);
     for (int idx = tid; idx < 10 * 64; idx += kImuThreads) {
       const double val = accs[idx];
       if (val == 0.0) continue;
@@ -563,13 +632,15 @@ __global__ void __launch_bounds__(kImuThreads) imu_kernel(const __grid_constant_
       atomicAdd(a.ne.A + size_t(ga) * np + gb, val);  // ga <= gb: knot dims precede bias dims
     }
   }
+  if (!FULL) det_ticket_wait(a.det_ticket, blockIdx.x);
   cost = warp_sum(cost);
   if (tid == 0 && cost != 0.0) atomicAdd(a.ne.cost, cost);  // only warp 0 evaluates (count <= 32)
+  det_ticket_done(a.det_ticket, blockIdx.x);
 }
 
 int launch_imu(const ImuLaunch& l, bool full, cudaStream_t s) {
   if (l.n_items <= 0) return 0;
-  ImuArgs a{l.obs, l.items, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal};
+  ImuArgs a{l.obs, l.items, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal, l.det_ticket};
   const size_t smem = (size_t(kImuMaxPerItem) * 6 * kImuRowStride + 10 * 64) * sizeof(double);
   static PerDeviceOnce once;
   if (once.first()) cudaFuncSetAttribute(imu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
@@ -590,6 +661,7 @@ struct SmallArgs {
   ProblemDims dims;
   const uint8_t* cmask;
   LmScalars* scal;
+  int deterministic;
 };
 
 __device__ __forceinline__ const double* block_data(const StatePtrs& st, int type, int index) {
@@ -609,8 +681,8 @@ __global__ void __launch_bounds__(256) small_factors_kernel(const __grid_constan
   const int tid = threadIdx.x;
   double cost = 0.0;
   const int np = a.dims.np;
-  // bias factors (trajectory_value_factor.h:45-99)
-  for (int n = tid; n < a.bf.n; n += blockDim.x) {
+  // bias factors (trajectory_value_factor.h:45-99); deterministic mode: thread 0 walks them in order
+  for (int n = a.deterministic ? (tid == 0 ? 0 : a.bf.n) : tid; n < a.bf.n; n += a.deterministic ? 1 : blockDim.x) {
     const int2 ij = a.bf.ij[n];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -696,7 +768,7 @@ __global__ void prior_add_jtj_kernel(PriorPtrs pr, double* A, int np) {
 
 int launch_small_factors(const SmallFactorsLaunch& l, bool full, cudaStream_t s) {
   if (l.bf.n <= 0 && l.prior.n <= 0) return 0;
-  SmallArgs a{l.bf, l.prior, l.st, l.ne, l.dims, l.cmask, l.scal};
+  SmallArgs a{l.bf, l.prior, l.st, l.ne, l.dims, l.cmask, l.scal, l.deterministic};
   int launches = 1;
   if (full) small_factors_kernel<true><<<1, 256, 0, s>>>(a);
   else small_factors_kernel<false><<<1, 256, 0, s>>>(a);
@@ -759,7 +831,7 @@ __global__ void probe_image_kernel(VisArgs a, const int32_t* orig_index, int wan
 int launch_probe_image(const VisualLaunch& l, const int32_t* orig_index, bool want_jac, double* r, int32_t* s,
                        double* J, cudaStream_t st) {
   if (l.obs.n <= 0) return 0;
-  VisArgs a{l.obs, l.items, l.st, l.ne, l.lm, l.dims, l.sp, l.rig, l.cauchy, l.cmask, l.scal, 0};
+  VisArgs a{l.obs, l.items, l.st, l.ne, l.lm, l.dims, l.sp, l.rig, l.cauchy, l.cmask, l.scal, 0, nullptr};
   probe_image_kernel<<<(l.obs.n + 63) / 64, 64, 0, st>>>(a, orig_index, want_jac ? 1 : 0, r, s, J);
   return 1;
 }
@@ -798,7 +870,7 @@ __global__ void probe_imu_kernel(ImuArgs a, const int32_t* orig_index, int want_
 int launch_probe_imu(const ImuLaunch& l, const int32_t* orig_index, bool want_jac, double* r, int32_t* s, double* J,
                      cudaStream_t st) {
   if (l.obs.n <= 0) return 0;
-  ImuArgs a{l.obs, l.items, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal};
+  ImuArgs a{l.obs, l.items, l.st, l.ne, l.dims, l.sp, l.rig, l.cmask, l.scal, nullptr};
   probe_imu_kernel<<<(l.obs.n + 63) / 64, 64, 0, st>>>(a, orig_index, want_jac ? 1 : 0, r, s, J);
   return 1;
 }

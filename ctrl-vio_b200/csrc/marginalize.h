@@ -95,6 +95,9 @@ int launch_dense_gemm(int m, int n, int k, double alpha, const double* A, int ld
 int launch_marg_elementwise(int mode, int n, int ld, const double* src, double* dst, const double* ev, const double* vb,
                             double* rlin, double eps, cudaStream_t s);
 
+int launch_abs_column_sums(const double* r, int n, int cols, double* out, cudaStream_t s);
+int launch_bias_abs_sums(const int2* ij, const double* sq, int n, const double* bias, double* out6, cudaStream_t s);
+
 // measured fp64 FMA throughput of the current device (TFLOP/s); < 0 on error
 double measure_fp64_tflops(cudaStream_t s);
 

@@ -208,4 +208,38 @@ int launch_shard_scalars_reduce(const double* gathered, int world, LmScalars* sc
   return 1;
 }
 
+
+// ResidualSummary support: out[c] = sum_k |r[k][c]| (one CTA, fixed order), and the bias random-walk residuals
+__global__ void abs_column_sums_kernel(const double* r, int n, int cols, double* out) {
+  __shared__ double part[32][8];
+  const int c = threadIdx.x & 7, g = threadIdx.x >> 3;  // 8 column slots x 32 row groups
+  double s = 0.0;
+  if (c < cols)
+    for (int k = g; k < n; k += 32) s += fabs(r[size_t(k) * cols + c]);
+  part[g][c] = s;
+  __syncthreads();
+  if (threadIdx.x < cols) {
+    double t = 0.0;
+    for (int k = 0; k < 32; ++k) t += part[k][threadIdx.x];
+    out[threadIdx.x] = t;
+  }
+}
+int launch_abs_column_sums(const double* r, int n, int cols, double* out, cudaStream_t s) {
+  if (n <= 0 || cols > 8) return 0;
+  abs_column_sums_kernel<<<1, 256, 0, s>>>(r, n, cols, out);
+  return 1;
+}
+__global__ void bias_abs_sums_kernel(const int2* ij, const double* sq, int n, const double* bias, double* out6) {
+  const int c = threadIdx.x;
+  if (c >= 6) return;
+  double t = 0.0;
+  for (int k = 0; k < n; ++k) t += fabs(sq[6 * k + c] * (bias[6 * ij[k].y + c] - bias[6 * ij[k].x + c]));
+  out6[c] = t;
+}
+int launch_bias_abs_sums(const int2* ij, const double* sq, int n, const double* bias, double* out6, cudaStream_t s) {
+  if (n <= 0) return 0;
+  bias_abs_sums_kernel<<<1, 32, 0, s>>>(ij, sq, n, bias, out6);
+  return 1;
+}
+
 }  // namespace ctvio

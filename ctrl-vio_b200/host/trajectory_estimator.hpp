@@ -17,9 +17,12 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -66,6 +69,26 @@ struct MarginalizationInfo {
   int n = 0;
   std::vector<double> linearized_jacobians, linearized_residuals, keep_block_data;  // n x n, n, nb x 4
   std::vector<int32_t> keep_block_type, keep_block_index, keep_block_idx;
+};
+
+// ResidualSummary (trajectory_estimator.h:38-58, .cpp:36-95): per residual type the number of blocks and the sum of
+// |residual_i| (evaluated WITHOUT the loss, like cost_function->Evaluate in AddResidualInfo); err_ave = sum / num.
+enum ResidualType { RType_IMU = 0, RType_Bias = 1, RType_Image = 2, RType_Prior = 3 };
+struct ResidualSummary {
+  int err_type_number[4] = {0, 0, 0, 0};
+  std::vector<double> err_type_sum[4];
+  std::string descri_info;
+  void PrintSummary(FILE* f = stderr) const {
+    static const char* names[4] = {"IMU", "Bias", "Image", "Prior"};
+    if (err_type_number[0] + err_type_number[1] + err_type_number[2] + err_type_number[3] == 0) return;
+    std::fprintf(f, "ResidualSummary :%s\n", descri_info.c_str());
+    for (int t = 0; t < 4; ++t) {
+      if (err_type_number[t] <= 0) continue;
+      std::fprintf(f, "\t- %s: num = %d; err_ave = ", names[t], err_type_number[t]);
+      for (size_t i = 0; i < err_type_sum[t].size(); ++i) std::fprintf(f, "%g, ", err_type_sum[t][i] / err_type_number[t]);
+      std::fprintf(f, "\n");
+    }
+  }
 };
 
 struct SolverSummary {  // what callers log from ceres::Solver::Summary::BriefReport()
@@ -134,12 +157,99 @@ class TrajectoryEstimator {
   // trajectory_estimator.cpp:334-348
   void AddMarginalizationFactor(const MarginalizationInfo::Ptr& last) { prior_ = last; }
 
+  // ---- the reference's EXACT argument shapes (trajectory_estimator.h:101-146), templated on anything that exposes
+  //      .data() (Eigen::Vector3d, Eigen::Matrix<double,6,1>, std::array, ...) so that TrajectoryManager's call sites
+  //      compile unchanged without Eigen being included here ----
+  // AddIMUMeasurementAnalytic(const IMUData&, const Vector3d& gravity, double* bg, double* ba, const Vector6d& info, bool marg)
+  template <class ImuData, class Vec3, class Vec6>
+  auto AddIMUMeasurementAnalytic(const ImuData& imu_data, const Vec3& gravity, double* gyro_bias, double* accel_bias,
+                                 const Vec6& info_vec, bool marg_this_factor = false)
+      -> decltype(imu_data.timestamp, gravity.data(), info_vec.data(), void()) {
+    (void)gravity; (void)info_vec;  // statics of the engine (ctvio_config.gravity / imu_info), checked once by the constructor
+    AddIMUMeasurementAnalytic(int64_t(imu_data.timestamp), imu_data.gyro.data(), imu_data.accel.data(), gyro_bias, accel_bias,
+                              marg_this_factor);
+  }
+  // AddBiasFactor(double*, double*, double*, double*, double dt, const Vector6d& info_vec, bool marg)
+  template <class Vec6>
+  auto AddBiasFactor(double* bias_gyr_i, double* bias_gyr_j, double* bias_acc_i, double* bias_acc_j, double dt,
+                     const Vec6& info_vec, bool marg_this_factor = false) -> decltype(info_vec.data(), void()) {
+    AddBiasFactor(bias_gyr_i, bias_gyr_j, bias_acc_i, bias_acc_j, dt, info_vec.data(), marg_this_factor);
+  }
+  // AddImageFeatureDelayAnalytic(int64 ti, int rowi, const Vector3d& pi, int64 tj, int rowj, const Vector3d& pj, double* inv_depth,
+  //                              double* line_delay, bool fixed_depth, bool marg)
+  template <class Vec3>
+  auto AddImageFeatureDelayAnalytic(int64_t ti, int rowi, const Vec3& pi, int64_t tj, int rowj, const Vec3& pj, double* inv_depth,
+                                    double* line_delay, bool fixed_depth = false, bool marg_this_feature = false)
+      -> decltype(pi.data(), void()) {
+    AddImageFeatureDelayAnalytic(ti, rowi, pi.data(), tj, rowj, pj.data(), inv_depth, line_delay, fixed_depth, marg_this_feature);
+  }
+  // AddMarginalizationFactor(MarginalizationInfo::Ptr, std::vector<double*>& parameter_blocks): the block list is implied by
+  // the info's (kind, index) pairs; the vector is accepted for source compatibility
+  void AddMarginalizationFactor(const MarginalizationInfo::Ptr& last, std::vector<double*>& /*parameter_blocks*/) { prior_ = last; }
+
+  // PrepareMarginalizationInfo(RType_Prior, factor, NULL, parameter_blocks, drop_set) (trajectory_estimator.cpp:143-151,
+  // trajectory_manager.cpp:166-203): the old prior takes part in the marginalization with an explicit drop set (indices
+  // into its block list).  The engine derives the same drop set from options.ctrl_to_be_opt_now / _later and bias node 0
+  // (engine.cu: ctvio_marginalize [1]); here the caller's set is CHECKED against that rule so that a divergence is loud.
+  void PrepareMarginalizationInfo(ResidualType r_type, const MarginalizationInfo::Ptr& prior, const std::vector<int>& drop_set) {
+    if (r_type != RType_Prior || !prior) throw Error(CTVIO_ERR_INVALID, "PrepareMarginalizationInfo: only the prior is recorded explicitly");
+    std::vector<int> expect;
+    for (size_t b = 0; b < prior->keep_block_type.size(); ++b) {
+      const int t = prior->keep_block_type[b], i = prior->keep_block_index[b];
+      const bool knot = t == CTVIO_BLK_ROT || t == CTVIO_BLK_POS;
+      if ((knot && i >= options.ctrl_to_be_opt_now && i < options.ctrl_to_be_opt_later) ||
+          ((t == CTVIO_BLK_BG || t == CTVIO_BLK_BA) && i == 0))
+        expect.push_back(int(b));
+    }
+    std::vector<int> got = drop_set;
+    std::sort(got.begin(), got.end());
+    if (got != expect) throw Error(CTVIO_ERR_INVALID, "PrepareMarginalizationInfo: drop set differs from the window rule");
+    prior_ = prior;
+  }
+  // SaveMarginalizationInfo(MarginalizationInfo::Ptr& out, std::vector<double*>& blocks_out) (trajectory_estimator.cpp:184-204)
+  void SaveMarginalizationInfo(MarginalizationInfo::Ptr& marg_info_out, std::vector<double*>& marg_param_blocks_out) {
+    marg_info_out = SaveMarginalizationInfo();
+    marg_param_blocks_out.clear();
+    if (!marg_info_out) return;
+    for (size_t b = 0; b < marg_info_out->keep_block_type.size(); ++b)
+      marg_param_blocks_out.push_back(blockPointer(marg_info_out->keep_block_type[b], marg_info_out->keep_block_index[b]));
+  }
+  // GetResidualSummary() (trajectory_estimator.h:168-171): evaluated on the device at the CURRENT state of the engine
+  const ResidualSummary& GetResidualSummary() {
+    upload();
+    double sums[18];
+    int32_t counts[4];
+    std::vector<double> prior_sum(prior_ ? size_t(prior_->n) : 0);
+    check(ctvio_residual_summary(h_, counts, sums, prior_sum.empty() ? nullptr : prior_sum.data()), "ctvio_residual_summary");
+    residual_summary_ = ResidualSummary();
+    residual_summary_.err_type_number[RType_Image] = counts[0];
+    residual_summary_.err_type_sum[RType_Image].assign(sums, sums + 2);
+    residual_summary_.err_type_number[RType_IMU] = counts[1];
+    residual_summary_.err_type_sum[RType_IMU].assign(sums + 2, sums + 8);
+    residual_summary_.err_type_number[RType_Bias] = counts[2];
+    residual_summary_.err_type_sum[RType_Bias].assign(sums + 8, sums + 14);
+    residual_summary_.err_type_number[RType_Prior] = counts[3];
+    residual_summary_.err_type_sum[RType_Prior] = prior_sum;
+    return residual_summary_;
+  }
+  // AddCallback (trajectory_estimator.cpp:350-365, CheckStateCallback): the reference prints the registered blocks after
+  // every iteration.  The LM loop runs on the device; the callbacks are invoked once per Solve with the final state.
+  void AddCallback(const std::vector<std::string>& descriptions, const std::vector<size_t>& block_size,
+                   std::vector<double*>& param_block) {
+    for (size_t i = 0; i < block_size.size(); ++i) callbacks_.push_back({descriptions[i], block_size[i], param_block[i]});
+  }
+
   // trajectory_estimator.cpp:367-408 — uploads state + factors, solves in HBM, writes every block back in place
   SolverSummary Solve(int max_iterations = 50, bool /*progress*/ = false, int /*num_threads*/ = -1) {
     upload();
     ctvio_summary s{};
     check(ctvio_solve(h_, max_iterations, &s), "ctvio_solve");
     download();
+    for (const auto& cb : callbacks_) {
+      std::fprintf(stderr, "%s:", cb.name.c_str());
+      for (size_t k = 0; k < cb.size; ++k) std::fprintf(stderr, " %g", cb.ptr[k]);
+      std::fprintf(stderr, "\n");
+    }
     SolverSummary out;
     out.iterations = s.iterations; out.num_successful_steps = s.num_successful_steps;
     out.num_unsuccessful_steps = s.num_unsuccessful_steps; out.termination = s.termination;
@@ -193,6 +303,16 @@ class TrajectoryEstimator {
     landmarks_.push_back(inv_depth);
     lm_index_[inv_depth] = int(landmarks_.size()) - 1;
     return int(landmarks_.size()) - 1;
+  }
+  double* blockPointer(int type, int index) {
+    switch (type) {
+      case CTVIO_BLK_ROT: return trajectory_->getKnotSO3(size_t(index));
+      case CTVIO_BLK_POS: return trajectory_->getKnotPos(size_t(index));
+      case CTVIO_BLK_BG: return bias_nodes_[size_t(index)].first;
+      case CTVIO_BLK_BA: return bias_nodes_[size_t(index)].second;
+      case CTVIO_BLK_LD: return &trajectory_->line_delay;
+      default: return landmarks_[size_t(index)];
+    }
   }
   void upload() {
     Trajectory& T = *trajectory_;
@@ -250,6 +370,9 @@ class TrajectoryEstimator {
   std::vector<int32_t> img_rowi_, img_rowj_, img_lm_, img_marg_, imu_node_, imu_marg_, bf_i_, bf_j_, bf_marg_;
   std::vector<double> img_pi_, img_pj_, imu_gyro_, imu_accel_, bf_s_;
   MarginalizationInfo::Ptr prior_;
+  ResidualSummary residual_summary_;
+  struct Callback { std::string name; size_t size; double* ptr; };
+  std::vector<Callback> callbacks_;
 };
 
 }  // namespace ctvio_host

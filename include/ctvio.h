@@ -123,6 +123,11 @@ int ctvio_abi_version(void);
 int ctvio_create(const ctvio_config* cfg, ctvio_handle* out);
 int ctvio_destroy(ctvio_handle h);
 int ctvio_set_options(ctvio_handle h, const ctvio_options* opt);
+/* Deterministic mode (also CTVIO_DETERMINISTIC=1 at ctvio_create): every kernel merges its per-CTA partial sums in block
+ * order (a ticket) and all factor kernels run on one stream, so a solve and the prior built from it are bit-reproducible
+ * run to run - like the reference's single-threaded sums (trajectory_estimator.cpp:379-383).  Slower (serialised flush);
+ * off by default; single GPU only.  K5 and K7 are order-fixed in both modes. */
+int ctvio_set_deterministic(ctvio_handle h, int32_t on);
 
 /* state in — replaces the raw `double*` parameter blocks handed to
  * problem_->AddParameterBlock (estimator/trajectory_estimator.cpp:114-141,
@@ -199,6 +204,11 @@ int ctvio_eval_image_factors(ctvio_handle h, int32_t want_jacobians, double cauc
  *   r[6n], s[n], J[n][156]: [knot k][rot 6x3 | pos 6x3] (144) + diag d/d bg (6) + diag d/d ba (6). */
 int ctvio_eval_imu_factors(ctvio_handle h, int32_t want_jacobians, double* r, int32_t* s, double* J,
                            double* cost);
+/* replaces ResidualSummary / TrajectoryEstimator::GetResidualSummary (estimator/trajectory_estimator.cpp:36-95, printed by every
+ * UpdateVIOPrior :283): per residual type the number of blocks and the per-component sums of |r_i| evaluated WITHOUT the loss
+ * at the current state.  counts4 = {image, imu, bias, prior}; err_sum18 = image[2] | imu[6] | bias[6] | pad[4];
+ * prior_err_sum (may be NULL) receives the n sums of the active prior. */
+int ctvio_residual_summary(ctvio_handle h, int32_t* counts4, double* err_sum18, double* prior_err_sum);
 /* total cost 0.5*sum rho(|r|^2) of all factors incl. bias + prior at the current state */
 int ctvio_eval_cost(ctvio_handle h, double* cost);
 /* Schur-form normal equations at the current state: camera block H_cc (np x np, row-major, symmetric),

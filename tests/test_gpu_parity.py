@@ -380,3 +380,35 @@ def test_resident_window_matches_host_buffer_path(cuda_lib):
     da = np.mean([x["d2h_bytes"] for x in a.records[1:]]); db = np.mean([x["d2h_bytes"] for x in b.records[1:]])
     print(f"H2D bytes / window: host-buffer path {ha:.0f}, resident {hb:.0f};  D2H: {da:.0f} vs {db:.0f}")
     assert hb < 0.5 * ha and db < 0.1 * da
+
+
+@pytest.mark.parametrize("case", ["c2-ldfree", "c3-chain"])
+def test_deterministic_mode_is_bitwise_reproducible(oracle_lib, cuda_lib, case):
+    """ctvio_set_deterministic: ordered flushes + one stream -> two runs of the same solve give BIT-identical states, and
+    the chain solve -> re-align -> marginalize gives bit-identical priors (the product was not run-to-run
+    deterministic while the reference's sums are).  The mode must not change the answer beyond rounding either."""
+    def run(det):
+        if case == "c2-ldfree":
+            w = syn.config_c2(fix_ld=False)
+            g = pkg.setup_estimator(cuda_lib, w)
+            g.SetDeterministic(det)
+            s = g.Solve(15)
+            return s, get_state(g), None
+        g, seq, wa, nowk = c3_window_a(cuda_lib)
+        g.SetDeterministic(det)
+        R0 = syn.qrot(wa.q0[nowk][None], np.eye(3)).T.copy(); t0 = wa.p0[nowk].copy()
+        s = g.Solve(15)
+        g.GaugeRealign(nowk, R0, t0)
+        pr = g.SaveMarginalizationInfo()
+        return s, get_state(g), pr
+    s1, st1, p1 = run(True)
+    s2, st2, p2 = run(True)
+    assert (s1.iterations, s1.termination) == (s2.iterations, s2.termination) and s1.final_cost == s2.final_cost
+    for a, b in zip(st1[:4], st2[:4]):
+        assert np.array_equal(a, b)
+    assert st1[4] == st2[4]
+    if p1 is not None:
+        assert np.array_equal(p1.J, p2.J) and np.array_equal(p1.r, p2.r)
+    s0, st0, _ = run(False)
+    assert s0.iterations == s1.iterations and np.isclose(s0.final_cost, s1.final_cost, rtol=1e-9)
+    assert np.abs(st0[1] - st1[1]).max() <= 1e-6 * np.abs(st0[1]).max()  # another summation order: rounding-level drift over 15 LM steps
