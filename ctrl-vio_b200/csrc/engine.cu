@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -46,6 +47,45 @@ int fail(int code, const std::string& msg) {
 
 thread_local size_t g_upload_bytes = 0;  // bytes moved by DevBuf::upload (index tables etc.), see ctvio_transfer_stats
 
+// Pinned staging arena of one engine: every host -> device copy of a C-ABI call is staged here and issued as a truly
+// asynchronous copy (a cudaMemcpyAsync from pageable memory is a synchronous staged copy: ~15 us each, ~20 of them per
+// window).  The arena is rewound whenever the engine's stream is found idle at the start of a call (then every copy that
+// read from it has completed); a request that does not fit falls back to the pageable copy and grows the arena at the
+// next rewind.
+struct PinnedArena {
+  unsigned char* base = nullptr;
+  size_t cap = 0, need = 0;  // need: bytes requested since the last rewind (may exceed cap: those requests fell back)
+  ~PinnedArena() { if (base) cudaFreeHost(base); }
+  void rewind() {
+    if (need > cap) {
+      if (base) cudaFreeHost(base);
+      base = nullptr;
+      cap = 0;
+      const size_t n = std::max<size_t>(size_t(1) << 20, need + need / 2);
+      if (cudaHostAlloc(reinterpret_cast<void**>(&base), n, cudaHostAllocDefault) == cudaSuccess) cap = n;
+      else cudaGetLastError();
+    }
+    need = 0;
+  }
+  void* put(const void* src, size_t bytes) {
+    const size_t o = (need + 15) & ~size_t(15);
+    need = o + bytes;
+    if (!base || need > cap) return nullptr;
+    std::memcpy(base + o, src, bytes);
+    return base + o;
+  }
+};
+thread_local PinnedArena* g_arena = nullptr;  // arena of the engine whose C-ABI call is running on this thread
+
+inline cudaError_t staged_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return cudaSuccess;
+  if (g_arena) {
+    if (void* st = g_arena->put(src, bytes)) return cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, s);
+  }
+  // pageable source: the runtime stages it synchronously, the caller's buffer is free again on return
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -64,7 +104,7 @@ struct DevBuf {
     cudaError_t e = reserve(h.size());
     if (e != cudaSuccess || h.empty()) return e;
     g_upload_bytes += h.size() * sizeof(T);
-    return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    return staged_h2d(p, h.data(), h.size() * sizeof(T), s);
   }
 };
 
@@ -115,6 +155,9 @@ struct ctvio_engine {
   DevBuf<VisualItem> d_items;
   int n_items = 0;
   std::vector<int32_t> img_order;  // sorted position -> original index
+  std::vector<int32_t> img_li, img_lj;    // ... and the last knot of those windows
+  std::vector<int32_t> img_wi0, img_wj0;  // first knot of the padded anchor / observation window per factor (caller order)
+  std::vector<VisualItem> h_items;        // K1 work items (one per chunk of a frame-pair group)
   std::vector<int32_t> imu_order;
   DevBuf<longlong2> d_imu_t;
   DevBuf<double2> d_imu_ga;
@@ -178,6 +221,12 @@ struct ctvio_engine {
   std::vector<int64_t> h_imu_tab_t;        // host mirror: timestamps only
   std::vector<int32_t> imu_src;            // parallel to imu when the samples came from the resident table (table index)
   DevBuf<int2> d_imu_src;
+  PinnedArena arena;
+  // pinned host mirror of the state, refreshed by the calls that end with a stream synchronisation anyway (solve,
+  // re-alignment): the getters then cost a memcpy instead of a device copy + synchronise each
+  double* h_mirror = nullptr;
+  size_t h_mirror_cap = 0;
+  bool mirror_valid = false;
   size_t h2d_bytes = 0, d2h_bytes = 0;     // bytes moved by the C-ABI calls since ctvio_transfer_stats(reset)
 
   DevBuf<double> d_tmp;  // scratch (gauge inputs, probe outputs)
@@ -213,6 +262,47 @@ struct ctvio_engine {
 
 namespace {
 
+// RAII: route this thread's uploads through the engine's arena for the duration of one C-ABI call
+struct ArenaScope {
+  PinnedArena* prev;
+  explicit ArenaScope(ctvio_engine* e) : prev(g_arena) {
+    if (e->stream && cudaStreamQuery(e->stream) == cudaSuccess) e->arena.rewind();  // idle: nothing reads the arena any more
+    else cudaGetLastError();
+    g_arena = &e->arena;
+  }
+  ~ArenaScope() { g_arena = prev; }
+};
+
+// enqueue the device -> pinned-host copies of the whole state (the caller synchronises the stream afterwards)
+int refresh_mirror(ctvio_engine* e) {
+  const size_t need = 4 * size_t(e->nK) + kPStride * size_t(e->nK) + 6 * size_t(std::max(e->nB, 1)) + size_t(std::max(e->nL, 1)) + 8;
+  if (need > e->h_mirror_cap) {
+    if (e->h_mirror) cudaFreeHost(e->h_mirror);
+    e->h_mirror = nullptr;
+    e->h_mirror_cap = 0;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&e->h_mirror), (2 * need) * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      e->mirror_valid = false;
+      return CTVIO_OK;  // the getters fall back to direct copies
+    }
+    e->h_mirror_cap = 2 * need;
+  }
+  DevState& x = e->x[e->cur];
+  double* m = e->h_mirror;
+  cudaStream_t st = e->stream;
+  CUDA_OK(cudaMemcpyAsync(m, x.q.p, 4 * size_t(e->nK) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  m += 4 * size_t(e->nK);
+  CUDA_OK(cudaMemcpyAsync(m, x.p.p, kPStride * size_t(e->nK) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  m += kPStride * size_t(e->nK);
+  if (e->nB) CUDA_OK(cudaMemcpyAsync(m, x.bias.p, 6 * size_t(e->nB) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  m += 6 * size_t(std::max(e->nB, 1));
+  if (e->nL) CUDA_OK(cudaMemcpyAsync(m, x.rho.p, size_t(e->nL) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  m += size_t(std::max(e->nL, 1));
+  CUDA_OK(cudaMemcpyAsync(m, x.ld.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  e->mirror_valid = true;  // valid once the caller has synchronised
+  return CTVIO_OK;
+}
+
 int knot_window_first(const ctvio_engine* e, int64_t t) {
   int64_t s = (t - e->cfg.t0_ns) / e->cfg.dt_ns;
   return int(s);
@@ -238,6 +328,15 @@ int fetch_new_prior(ctvio_engine* e);
 // Build every host-side structure that depends on the factor set / sizes and upload it.
 int prepare(ctvio_engine* e) {
   if (!e->have_knots) return fail(CTVIO_ERR_STATE, "knots have not been set");
+  ArenaScope arena(e);
+  static const bool prep_timing = std::getenv("CTVIO_PREP_TIMING") != nullptr;
+  auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!prep_timing) return;
+    auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[prepare] %-22s %7.1f us\n", what, std::chrono::duration<double, std::micro>(t - tp0).count());
+    tp0 = t;
+  };
   if (e->nK < 4) return fail(CTVIO_ERR_STATE, "need at least 4 knots");
   if (!e->have_bias) { e->nB = 0; }
   cudaStream_t st = e->stream;
@@ -246,26 +345,63 @@ int prepare(ctvio_engine* e) {
     e->shard_checked = false;
     // ---- image factors: frame-pair groups ----
     const int n = int(e->img.size());
-    std::vector<int32_t> wi0(n), wj0(n);
+    std::vector<int32_t>&wi0 = e->img_wi0, &wj0 = e->img_wj0;
+    wi0.resize(n); wj0.resize(n);
+    e->img_li.resize(n); e->img_lj.resize(n);
     e->h_lo.assign(e->nL, INT32_MAX);
     e->h_hi.assign(e->nL, 0);
+    // the image factors of a window carry a dozen distinct frame times: the padded knot window of a time (two 64-bit
+    // divisions) is looked up in a small direct-mapped cache
+    struct WinCache { int64_t t = INT64_MIN; int f = 0, l = 0; bool ok = false; } wc[64];
+    auto window_of = [&](int64_t t, int& f, int& l) {
+      WinCache& c = wc[size_t(uint64_t(t) * 0x9E3779B97F4A7C15ull >> 58)];
+      if (c.t != t) { c.t = t; c.ok = knot_window(e, t, c.f, c.l); }
+      f = c.f; l = c.l;
+      return c.ok;
+    };
     for (int k = 0; k < n; ++k) {
       const HostImage& o = e->img[k];
       int f0, l0, f1, l1;
-      if (!knot_window(e, o.ti, f0, l0) || !knot_window(e, o.tj, f1, l1))
+      if (!window_of(o.ti, f0, l0) || !window_of(o.tj, f1, l1))
         return fail(CTVIO_ERR_TIME_RANGE, "image factor time (+ rolling-shutter padding) outside the spline");
       if (o.lm < 0 || o.lm >= e->nL) return fail(CTVIO_ERR_INVALID, "landmark index out of range");
       wi0[k] = f0; wj0[k] = f1;
+      e->img_li[k] = l0; e->img_lj[k] = l1;
       e->h_lo[o.lm] = std::min(e->h_lo[o.lm], 6 * std::min(f0, f1));
       e->h_hi[o.lm] = std::max(e->h_hi[o.lm], 6 * (std::max(l0, l1) + 1));
     }
     e->img_order.resize(n);
-    for (int k = 0; k < n; ++k) e->img_order[k] = k;
-    std::stable_sort(e->img_order.begin(), e->img_order.end(), [&](int a, int b) {
-      if (wi0[a] != wi0[b]) return wi0[a] < wi0[b];
-      if (wj0[a] != wj0[b]) return wj0[a] < wj0[b];
-      return e->img[a].lm < e->img[b].lm;
-    });
+    {
+      // order: (frame-pair group, landmark, position).  The reference's feature loop hands the factors over landmark by
+      // landmark (trajectory_manager.cpp:360-385), so they usually arrive sorted by landmark already: then a STABLE
+      // counting sort by group is the whole job (O(n), this runs once per window inside the end-to-end time); any other
+      // input order takes the general key sort.
+      bool lm_sorted = true;
+      for (int k = 1; k < n && lm_sorted; ++k) lm_sorted = e->img[k - 1].lm <= e->img[k].lm;
+      const size_t nKk = size_t(e->nK) + 1;
+      if (lm_sorted && nKk * nKk <= (size_t(1) << 22)) {
+        std::vector<int32_t> start(nKk * nKk + 1, 0);
+        for (int k = 0; k < n; ++k) ++start[size_t(wi0[k]) * nKk + size_t(wj0[k]) + 1];
+        for (size_t g = 1; g < start.size(); ++g) start[g] += start[g - 1];
+        for (int k = 0; k < n; ++k) e->img_order[start[size_t(wi0[k]) * nKk + size_t(wj0[k])]++] = k;
+      } else {
+        std::vector<uint64_t> key(n);
+        const uint64_t nLl = uint64_t(std::max(e->nL, 1));
+        if (uint64_t(nKk) * nKk * nLl < (uint64_t(1) << 40) && uint64_t(n) < (uint64_t(1) << 24)) {
+          for (int k = 0; k < n; ++k)
+            key[k] = (((uint64_t(wi0[k]) * nKk + uint64_t(wj0[k])) * nLl + uint64_t(e->img[k].lm)) << 24) | uint64_t(k);
+          std::sort(key.begin(), key.end());
+          for (int k = 0; k < n; ++k) e->img_order[k] = int32_t(key[k] & 0xffffffu);
+        } else {
+          for (int k = 0; k < n; ++k) e->img_order[k] = k;
+          std::stable_sort(e->img_order.begin(), e->img_order.end(), [&](int a, int b) {
+            if (wi0[a] != wi0[b]) return wi0[a] < wi0[b];
+            if (wj0[a] != wj0[b]) return wj0[a] < wj0[b];
+            return e->img[a].lm < e->img[b].lm;
+          });
+        }
+      }
+    }
     std::vector<longlong2> ht(n);
     std::vector<double2> hpi(n), hpj(n);
     std::vector<int4> hm(n);
@@ -276,6 +412,7 @@ int prepare(ctvio_engine* e) {
       hpj[k] = make_double2(o.pj[0], o.pj[1]);
       hm[k] = make_int4(o.rowi, o.rowj, o.lm, o.marg);
     }
+    lap("image windows + sort");
     // work items: chunks of one group; chunk size adapts so that small problems still spread over the SMs
     // (a group is split into equal chunks of at most `cap` observations, cap a multiple of the 128-observation round)
     // one evaluation round (<= 128 observations, a lane pair each) per CTA: the round is latency bound whatever its
@@ -283,7 +420,8 @@ int prepare(ctvio_engine* e) {
     // and every chunk gets its own CTA; CTVIO_VIS_CAP overrides (multiples of 128) for experiments
     int cap = kVisObsPerRound;
     if (const char* env = std::getenv("CTVIO_VIS_CAP")) cap = std::max(kVisObsPerRound, std::atoi(env) / kVisObsPerRound * kVisObsPerRound);
-    std::vector<VisualItem> items;
+    std::vector<VisualItem>& items = e->h_items;
+    items.clear();
     for (int k = 0; k < n;) {
       const int a = e->img_order[k];
       int end = k;
@@ -317,6 +455,7 @@ int prepare(ctvio_engine* e) {
     CUDA_OK(e->d_img_orig.upload(e->img_order, st));
     CUDA_OK(e->d_items.upload(items, st));
 
+    lap("image arrays + upload");
     // ---- landmark layout ----
     e->h_woff.assign(e->nL + 1, 0);
     for (int l = 0; l < e->nL; ++l) {
@@ -326,6 +465,7 @@ int prepare(ctvio_engine* e) {
     CUDA_OK(e->d_lo.upload(e->h_lo, st));
     CUDA_OK(e->d_hi.upload(e->h_hi, st));
     CUDA_OK(e->d_woff.upload(e->h_woff, st));
+    lap("landmark layout");
     // ---- imu / bias factors ----
     const int ni = int(e->imu.size());
     std::vector<longlong2> it(ni);
@@ -385,6 +525,7 @@ int prepare(ctvio_engine* e) {
     CUDA_OK(e->d_bf_ij.upload(bij, st));
     CUDA_OK(e->d_bf_s.upload(bs, st));
 
+    lap("imu / bias");
     // ---- buffers ----
     const size_t np = size_t(d.np);
     e->off_gc = np * np;
@@ -403,6 +544,7 @@ int prepare(ctvio_engine* e) {
       e->linv_npad = e->npad;
       e->chol_seq = 0;
     }
+    lap("buffers");
     {
       // ---- K4 work items: per 64x64 tile (ti >= tj) of the reduced system the landmarks whose knot-dim range
       // [lo, hi) touches both blocks, cut into parts of `part` landmarks so that about two waves of CTAs exist
@@ -445,6 +587,7 @@ int prepare(ctvio_engine* e) {
       CUDA_OK(e->d_lis.reserve(e->nL));
       CUDA_OK(e->d_lc.reserve(e->nL));
     }
+    lap("schur lists");
     if (chol_dag_flags_len(e->npad) > e->d_chol_flags.cap) {
       CUDA_OK(e->d_chol_flags.reserve(chol_dag_flags_len(e->npad)));
       CUDA_OK(cudaMemsetAsync(e->d_chol_flags.p, 0, e->d_chol_flags.cap * sizeof(int32_t), e->stream));
@@ -458,6 +601,7 @@ int prepare(ctvio_engine* e) {
     if (e->nL > 0) CUDA_OK(cudaMemsetAsync(e->d_hh.p, 0, sizeof(double) * e->nL, st));
     e->prior_dirty = true;
   }
+  lap("reserves");
   // ---- masks (depend on options + structure) ----
   if (e->structure_dirty || e->masks_dirty) {
     e->h_cmask.assign(d.np, 0);
@@ -475,12 +619,21 @@ int prepare(ctvio_engine* e) {
       for (int k = f; k <= l; ++k)
         for (int c = 0; c < 6; ++c) touched[6 * k + c] = 1;
     };
-    for (const HostImage& o : e->img) {
-      int f, l;
-      knot_window(e, o.ti, f, l); mark(f, l);
-      knot_window(e, o.tj, f, l); mark(f, l);
-      touched[d.idx_ld] = 1;
-      touched[d.np + o.lm] = 1;
+    // image factors: a window of a dozen frames has a few dozen distinct padded knot windows [first, last]; each is
+    // marked once (the windows were computed by the structure pass above)
+    {
+      std::vector<uint8_t> seen(size_t(e->nK) * 8, 0);
+      auto mark_once = [&](int f, int l) {
+        uint8_t& sflag = seen[size_t(f) * 8 + size_t(l - f)];
+        if (!sflag) { sflag = 1; mark(f, l); }
+      };
+      const size_t n = e->img.size();
+      for (size_t k = 0; k < n; ++k) {
+        mark_once(e->img_wi0[k], e->img_li[k]);
+        mark_once(e->img_wj0[k], e->img_lj[k]);
+        touched[d.np + e->img[k].lm] = 1;
+      }
+      if (n) touched[d.idx_ld] = 1;
     }
     for (const HostImu& o : e->imu) {
       const int s = knot_window_first(e, o.t);
@@ -502,6 +655,7 @@ int prepare(ctvio_engine* e) {
     CUDA_OK(e->d_active.upload(e->h_active, st));
     e->masks_dirty = false;
   }
+  lap("masks");
   e->structure_dirty = false;
   if (e->prior_dirty) {
     const int rc = prepare_prior(e);
@@ -869,6 +1023,7 @@ int ctvio_destroy(ctvio_handle e) {
   ctvio::comm_destroy(e->nccl_comm);
   if (e->h_scal) cudaFreeHost(e->h_scal);
   if (e->h_pub) cudaFreeHost(e->h_pub);
+  if (e->h_mirror) cudaFreeHost(e->h_mirror);
   if (e->ev_zero) cudaEventDestroy(e->ev_zero);
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
@@ -895,11 +1050,12 @@ int ctvio_set_knots(ctvio_handle e, int32_t n, const double* q, const double* p)
   e->nK = n;
   e->sp.n_knots = n;
   for (int b = 0; b < 2; ++b) { const int rc = alloc_state(e, e->x[b]); if (rc) return rc; }
+  ArenaScope arena(e);
   std::vector<double> p4(kPStride * size_t(n), 0.0);
   for (int k = 0; k < n; ++k) for (int c = 0; c < 3; ++c) p4[kPStride * k + c] = p[3 * k + c];
-  CUDA_OK(cudaMemcpyAsync(e->x[e->cur].q.p, q, 4 * size_t(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  CUDA_OK(cudaMemcpyAsync(e->x[e->cur].p.p, p4.data(), p4.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  CUDA_OK(cudaStreamSynchronize(e->stream));  // p4 is a stack-lifetime staging buffer
+  CUDA_OK(staged_h2d(e->x[e->cur].q.p, q, 4 * size_t(n) * sizeof(double), e->stream));
+  CUDA_OK(staged_h2d(e->x[e->cur].p.p, p4.data(), p4.size() * sizeof(double), e->stream));  // staged: p4 may go away
+  e->mirror_valid = false;
   e->h2d_bytes += size_t(n) * 56;
   e->have_knots = true;
   e->table_valid = false;
@@ -912,8 +1068,9 @@ int ctvio_set_biases(ctvio_handle e, int32_t n, const double* b) {
   if (n != e->nB) e->structure_dirty = true;
   e->nB = n;
   for (int k = 0; k < 2; ++k) CUDA_OK(e->x[k].bias.reserve(6 * size_t(std::max(n, 1))));
-  if (n > 0) CUDA_OK(cudaMemcpyAsync(e->x[e->cur].bias.p, b, 6 * size_t(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  CUDA_OK(cudaStreamSynchronize(e->stream));
+  ArenaScope arena(e);
+  if (n > 0) CUDA_OK(staged_h2d(e->x[e->cur].bias.p, b, 6 * size_t(n) * sizeof(double), e->stream));
+  e->mirror_valid = false;
   e->h2d_bytes += size_t(n) * 48;
   e->have_bias = true;
   return CTVIO_OK;
@@ -925,8 +1082,9 @@ int ctvio_set_inv_depths(ctvio_handle e, int32_t n, const double* r) {
   if (n != e->nL) e->structure_dirty = true;
   e->nL = n;
   for (int k = 0; k < 2; ++k) CUDA_OK(e->x[k].rho.reserve(size_t(std::max(n, 1))));
-  if (n > 0) CUDA_OK(cudaMemcpyAsync(e->x[e->cur].rho.p, r, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  CUDA_OK(cudaStreamSynchronize(e->stream));
+  ArenaScope arena(e);
+  if (n > 0) CUDA_OK(staged_h2d(e->x[e->cur].rho.p, r, size_t(n) * sizeof(double), e->stream));
+  e->mirror_valid = false;
   e->h2d_bytes += size_t(n) * 8;
   e->have_rho = true;
   return CTVIO_OK;
@@ -946,14 +1104,23 @@ int ctvio_set_line_delay(ctvio_handle e, double ld) {
   if (!e) return fail(CTVIO_ERR_INVALID, "null handle");
   cudaSetDevice(e->cfg.device);
   for (int k = 0; k < 2; ++k) CUDA_OK(e->x[k].ld.reserve(1));
-  CUDA_OK(cudaMemcpyAsync(e->x[e->cur].ld.p, &ld, sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  CUDA_OK(cudaStreamSynchronize(e->stream));
+  ArenaScope arena(e);
+  CUDA_OK(staged_h2d(e->x[e->cur].ld.p, &ld, sizeof(double), e->stream));
+  e->mirror_valid = false;
   return CTVIO_OK;
 }
 
 int ctvio_get_knots(ctvio_handle e, double* q, double* p) {
   if (!e || !e->have_knots) return fail(CTVIO_ERR_STATE, "knots have not been set");
   cudaSetDevice(e->cfg.device);
+  e->d2h_bytes += size_t(e->nK) * ((q ? 32 : 0) + (p ? 32 : 0));
+  if (e->mirror_valid) {  // refreshed by the last solve / re-alignment: no device round trip
+    const double* mq = e->h_mirror;
+    const double* mp = mq + 4 * size_t(e->nK);
+    if (q) std::memcpy(q, mq, 4 * size_t(e->nK) * sizeof(double));
+    if (p) for (int k = 0; k < e->nK; ++k) for (int c = 0; c < 3; ++c) p[3 * k + c] = mp[kPStride * k + c];
+    return CTVIO_OK;
+  }
   if (q) CUDA_OK(cudaMemcpyAsync(q, e->x[e->cur].q.p, 4 * size_t(e->nK) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   std::vector<double> p4;
   if (p) {
@@ -962,28 +1129,39 @@ int ctvio_get_knots(ctvio_handle e, double* q, double* p) {
   }
   CUDA_OK(cudaStreamSynchronize(e->stream));
   if (p) for (int k = 0; k < e->nK; ++k) for (int c = 0; c < 3; ++c) p[3 * k + c] = p4[kPStride * k + c];
-  e->d2h_bytes += size_t(e->nK) * ((q ? 32 : 0) + (p ? 32 : 0));
   return CTVIO_OK;
 }
 int ctvio_get_biases(ctvio_handle e, double* b) {
   if (!e || !b) return fail(CTVIO_ERR_INVALID, "null argument");
   cudaSetDevice(e->cfg.device);
+  e->d2h_bytes += size_t(e->nB) * 48;
+  if (e->mirror_valid) {
+    std::memcpy(b, e->h_mirror + (4 + kPStride) * size_t(e->nK), 6 * size_t(e->nB) * sizeof(double));
+    return CTVIO_OK;
+  }
   if (e->nB > 0) CUDA_OK(cudaMemcpyAsync(b, e->x[e->cur].bias.p, 6 * size_t(e->nB) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
-  e->d2h_bytes += size_t(e->nB) * 48;
   return CTVIO_OK;
 }
 int ctvio_get_inv_depths(ctvio_handle e, double* r) {
   if (!e || !r) return fail(CTVIO_ERR_INVALID, "null argument");
   cudaSetDevice(e->cfg.device);
+  e->d2h_bytes += size_t(e->nL) * 8;
+  if (e->mirror_valid) {
+    std::memcpy(r, e->h_mirror + (4 + kPStride) * size_t(e->nK) + 6 * size_t(std::max(e->nB, 1)), size_t(e->nL) * sizeof(double));
+    return CTVIO_OK;
+  }
   if (e->nL > 0) CUDA_OK(cudaMemcpyAsync(r, e->x[e->cur].rho.p, size_t(e->nL) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
-  e->d2h_bytes += size_t(e->nL) * 8;
   return CTVIO_OK;
 }
 int ctvio_get_line_delay(ctvio_handle e, double* ld) {
   if (!e || !ld) return fail(CTVIO_ERR_INVALID, "null argument");
   cudaSetDevice(e->cfg.device);
+  if (e->mirror_valid) {
+    *ld = e->h_mirror[(4 + kPStride) * size_t(e->nK) + 6 * size_t(std::max(e->nB, 1)) + size_t(std::max(e->nL, 1))];
+    return CTVIO_OK;
+  }
   CUDA_OK(cudaMemcpyAsync(ld, e->x[e->cur].ld.p, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
   return CTVIO_OK;
@@ -1294,8 +1472,12 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     if (!ctvio::comm_allreduce_sum(e->nccl_comm, e->d_rho_sync.p, 2 * size_t(e->nL), st, &err)) return fail(CTVIO_ERR_NCCL, err);
     e->launches += ctvio::launch_rho_unpack(e->x[cur].rho.p, e->d_rho_sync.p, e->nL, st);
   }
-  cudaEventRecord(e->ev1, st);
-  CUDA_OK(cudaEventSynchronize(e->ev1));
+  cudaEventRecord(e->ev1, st);  // (the timed region of summary.device_ms ends here)
+  {
+    const int rcm = refresh_mirror(e);  // state -> pinned host mirror, rides on the synchronisation below
+    if (rcm) return rcm;
+  }
+  CUDA_OK(cudaStreamSynchronize(st));
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   sum.iterations = iter;
@@ -1315,8 +1497,12 @@ int ctvio_gauge_realign(ctvio_handle e, int32_t min_idx, const double* R0, const
   double h[12];
   for (int k = 0; k < 9; ++k) h[k] = R0[k];
   for (int k = 0; k < 3; ++k) h[9 + k] = t0[k];
-  CUDA_OK(cudaMemcpyAsync(e->d_tmp.p, h, sizeof(h), cudaMemcpyHostToDevice, e->stream));
+  CUDA_OK(cudaMemcpyAsync(e->d_tmp.p, h, sizeof(h), cudaMemcpyHostToDevice, e->stream));  // (stack source: staged by the runtime)
   e->launches += launch_gauge_realign(e->x[e->cur].ptrs(), e->nK, min_idx, e->d_tmp.p, e->stream);
+  {
+    const int rcm = refresh_mirror(e);
+    if (rcm) return rcm;
+  }
   CUDA_OK(cudaStreamSynchronize(e->stream));
   e->table_valid = true;
   return CTVIO_OK;
@@ -1347,6 +1533,7 @@ int ctvio_restore_state(ctvio_handle e) {
   if (e->nL) CUDA_OK(cudaMemcpyAsync(s.rho.p, e->snap.rho.p, size_t(e->nL) * sizeof(double), cudaMemcpyDeviceToDevice, st));
   CUDA_OK(cudaMemcpyAsync(s.ld.p, e->snap.ld.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
   e->table_valid = false;
+  e->mirror_valid = false;
   return CTVIO_OK;
 }
 
@@ -1703,6 +1890,7 @@ int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
   cudaSetDevice(e->cfg.device);
   e->new_prior = ctvio::PriorHost();
   if (!e->opt.is_marg_state) return CTVIO_OK;
+  ArenaScope arena(e);
   int rc = prepare(e);
   if (rc) return rc;
   ensure_table(e);
@@ -1983,6 +2171,7 @@ int ctvio_extend_knots_to(ctvio_handle e, int64_t t_ns, int32_t* n_out) {
     e->sp.n_knots = n;
     e->structure_dirty = true;
     e->table_valid = false;
+    e->mirror_valid = false;
   }
   if (n_out) *n_out = n;
   return CTVIO_OK;
@@ -2021,6 +2210,7 @@ int ctvio_slide_window(ctvio_handle e, int32_t drop_knots, int32_t drop_bias, in
   e->masks_dirty = true;
   e->structure_dirty = true;
   e->table_valid = false;
+  e->mirror_valid = false;
   return CTVIO_OK;
 }
 
@@ -2045,6 +2235,7 @@ int ctvio_remap_landmarks(ctvio_handle e, int32_t n_new, const int32_t* old_inde
     std::swap(e->x[e->cur].rho.cap, e->x[other].rho.cap);
   }
   if (n_new != e->nL) e->structure_dirty = true;
+  e->mirror_valid = false;
   e->nL = n_new;
   e->have_rho = true;
   return CTVIO_OK;
