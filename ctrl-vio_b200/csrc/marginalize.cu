@@ -8,6 +8,8 @@
 // fp64 atomics, the two eigen-decompositions run as a parallel (round-robin ordered) cyclic Jacobi solver in
 // one CTA, and the dense products are plain tiled kernels — this runs once per window, not per LM step.
 #include "marginalize.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace ctvio {
 
@@ -613,12 +615,19 @@ __global__ void __launch_bounds__(128) jacobi_apply_log_kernel(const JacobiRot* 
 
 size_t jacobi_log_bytes(int n, int max_sweeps) {
   const int ne = (n + 1) & ~1;
-  return size_t(max_sweeps) * (ne - 1) * (ne / 2) * sizeof(JacobiRot) + 64;
+  const size_t elementwise = size_t(max_sweeps) * (ne - 1) * (ne / 2) * sizeof(JacobiRot) + 64;
+  const size_t blocked = jacobi_blocked_log_bytes(n, max_sweeps);
+  return elementwise > blocked ? elementwise : blocked;
 }
 
 int launch_jacobi_eig(double* A, double* V, double* ev, int n, void* log_buf, cudaStream_t s) {
   if (n <= 0) return 0;
   constexpr int kMaxSweeps = 40;
+  // streaming-window sizes: blocked solver (jacobi_blocked.cu); CTVIO_JACOBI=elementwise keeps the solver below
+  if (log_buf && jacobi_blocked_fits(n)) {
+    const char* v = std::getenv("CTVIO_JACOBI");
+    if (!(v && std::strcmp(v, "elementwise") == 0)) return launch_jacobi_blocked(A, V, ev, n, log_buf, kMaxSweeps, s);
+  }
   const int ne = (n + 1) & ~1, npairs = ne / 2;
   const size_t pairs = size_t(npairs) * (2 * sizeof(double) + 2 * sizeof(int));
   const size_t mat = size_t(n) * (n | 1) * sizeof(double);

@@ -90,6 +90,10 @@ int launch_marg_small(const MargSmallArgs& a, cudaStream_t s);
 // by a replay kernel with one CTA per row)
 size_t jacobi_log_bytes(int n, int max_sweeps);
 int launch_jacobi_eig(double* A, double* V, double* ev, int n, void* log_buf, cudaStream_t s);
+// blocked variant (jacobi_blocked.cu): 16 <= n and the padded matrix fits one SM's shared memory (n <= 112)
+bool jacobi_blocked_fits(int n);
+size_t jacobi_blocked_log_bytes(int n, int max_sweeps);
+int launch_jacobi_blocked(const double* A, double* V, double* ev, int n, void* log_buf, int max_sweeps, cudaStream_t s);
 int launch_dense_gemm(int m, int n, int k, double alpha, const double* A, int lda, bool ta, const double* B, int ldb,
                       bool tb, double beta, double* C, int ldc, cudaStream_t s);
 int launch_marg_elementwise(int mode, int n, int ld, const double* src, double* dst, const double* ev, const double* vb,

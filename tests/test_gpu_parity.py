@@ -412,3 +412,45 @@ def test_deterministic_mode_is_bitwise_reproducible(oracle_lib, cuda_lib, case):
     s0, st0, _ = run(False)
     assert s0.iterations == s1.iterations and np.isclose(s0.final_cost, s1.final_cost, rtol=1e-9)
     assert np.abs(st0[1] - st1[1]).max() <= 1e-6 * np.abs(st0[1]).max()  # another summation order: rounding-level drift over 15 LM steps
+
+
+def _eig_case(n, seed, rank_deficient):
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    ev = 10.0 ** rng.uniform(-6, 6, n)
+    if rank_deficient:  # what a streaming prior looks like: a few directions at the rounding floor, either sign
+        ev[:6] = 10.0 ** rng.uniform(-14, -10, 6) * rng.choice([-1.0, 1.0], 6)
+    a = (q * ev) @ q.T
+    return 0.5 * (a + a.T)
+
+
+def _debug_eig(cuda_lib, a):
+    import ctypes as C
+    n = a.shape[0]
+    f = cuda_lib.lib.ctvio_debug_eig
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    a = np.ascontiguousarray(a)
+    v, ev = np.zeros((n, n)), np.zeros(n)
+    assert f(n, a.ctypes.data, v.ctypes.data, ev.ctypes.data, 0) == 0
+    return v, ev
+
+
+@pytest.mark.parametrize("n", [16, 23, 85, 100, 112, 150])
+@pytest.mark.parametrize("rank_deficient", [False, True])
+def test_eigen_solvers_match_lapack(cuda_lib, n, rank_deficient, monkeypatch):
+    """The two Jacobi eigen-solvers behind marginalize() (blocked, jacobi_blocked.cu, for 16 <= n <= 112; element-wise,
+    marginalize.cu, otherwise and with CTVIO_JACOBI=elementwise) against LAPACK: eigenvalues, orthogonality,
+    reconstruction; bit-identical run to run.  Replaces SelfAdjointEigenSolver, marginalization_factor.cpp:240-263."""
+    a = _eig_case(n, 100 + n, rank_deficient)
+    scale = np.linalg.norm(a, 2)
+    ref = np.linalg.eigvalsh(a)
+    for mode in ("default", "elementwise"):
+        if mode == "elementwise":
+            monkeypatch.setenv("CTVIO_JACOBI", "elementwise")
+        v, ev = _debug_eig(cuda_lib, a)
+        v2, ev2 = _debug_eig(cuda_lib, a)
+        assert np.array_equal(v, v2) and np.array_equal(ev, ev2)
+        assert np.max(np.abs(np.sort(ev) - ref)) <= 1e-13 * scale, mode
+        assert np.max(np.abs(v.T @ v - np.eye(n))) <= 1e-12, mode
+        assert np.max(np.abs((v * ev) @ v.T - a)) <= 1e-12 * scale, mode
