@@ -214,7 +214,8 @@ struct CholDagArgs {
   int npad;
   double* Lpub;       // this launch's packet buffer [nb][4][16][80] (self-validating words, see kSentinel)
   double* Lpub_other; // the other parity's buffer: reset to sentinels by the producers at the end of this launch
-  double* Spub;       // [nb][4][16][64] slabs P_s^T of the sub-diagonal tiles (j, j-1) for diagonal CTA j (self-validating)
+  double* Spub;       // [nb][nb][4][16][64] slabs P_s^T of every tile (i, k) as its solve produces them (self-validating):
+                      // read by diagonal CTA i (k = i - 1) and by the tiles whose last update needs L(i,k)
   double* Spub_other;
   const double* rhs;  // [npad]
   double* y;          // [npad] solution
@@ -419,15 +420,42 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
       tile_gemm_dmma<true>(S1, S2, acc, L);
       __syncthreads();
     }
-    if (j >= 1) {  // operands of the last update stay resident (D is unused by tile CTAs); applied lazily inside the solve
-      wait_flags2(tile_ready + i * nb + (j - 1), tile_ready + j * nb + (j - 1), epoch);
-      load_tile_cg(D, a.M + size_t(i) * kCholNB * npad + (j - 1) * kCholNB, npad, tid);
-      load_tile_cg(S2, a.M + size_t(j) * kCholNB * npad + (j - 1) * kCholNB, npad, tid);
-      __syncthreads();
+    if (j >= 1) {
+      // The last update T -= L(i,j-1) L(j,j-1)' is STREAMED: both operand tiles arrive 16 columns (k) at a time, as
+      // self-validating slabs, straight from the CTAs (i, j-1) and (j, j-1) that are still solving them, and are applied as
+      // rank-16 updates.  (Waiting for the finished tiles - flag, 2 x 32 KB from L2, four lazy slab products inside the
+      // solve - left this CTA ~2 us behind the packets of column j at every column of the critical chain.)
+      const double* srcA = a.Spub + (size_t(i) * nb + (j - 1)) * 4096;
+      const double* srcB = a.Spub + (size_t(j) * nb + (j - 1)) * 4096;
+      const int r0 = tid >> 5, c0 = (tid & 31) * 2;  // thread's two double2 of a slab: rows r0, r0 + 8
+      double2 pa[2], pb[2];
+      auto issue = [&](int s) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          pa[u] = ld_relaxed2(srcA + size_t(s) * 1024 + (r0 + 8 * u) * 64 + c0);
+          pb[u] = ld_relaxed2(srcB + size_t(s) * 1024 + (r0 + 8 * u) * 64 + c0);
+        }
+      };
+      issue(0);
+#pragma unroll 1
+      for (int s = 0; s < 4; ++s) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const size_t o = size_t(s) * 1024 + (r0 + 8 * u) * 64 + c0;
+          while (is_sentinel(pa[u].x) || is_sentinel(pa[u].y)) pa[u] = ld_relaxed2(srcA + o);
+          while (is_sentinel(pb[u].x) || is_sentinel(pb[u].y)) pb[u] = ld_relaxed2(srcB + o);
+          *reinterpret_cast<double2*>(D + (16 * s + r0 + 8 * u) * kTS + c0) = pa[u];
+          *reinterpret_cast<double2*>(S2 + (16 * s + r0 + 8 * u) * kTS + c0) = pb[u];
+        }
+        if (s < 3) issue(s + 1);
+        __syncthreads();
+        mma_dispatch(0xFFu, acc, D + (16 * s + L.q) * kTS + L.g, kTS, S2 + (16 * s + L.q) * kTS + L.g, kTS, L, 4);
+      }
     }
-    // L(i,j) = T L_jj^-T, 16 columns at a time behind the factorisation of block column j
-    trsm_pipelined(acc, L, S1, At, Bp, a.Lpub + size_t(j) * 4 * kPacketG, sub ? a.Spub + size_t(i) * 4 * 16 * 64 : nullptr,
-                   j >= 1 ? D : nullptr, S2, tid, sub ? i : -100);
+    // L(i,j) = T L_jj^-T, 16 columns at a time behind the factorisation of block column j; every finished slab is
+    // published (diagonal CTA i if this is the sub-diagonal tile, the tiles (r, i), r > i, and (i, j+1) otherwise)
+    trsm_pipelined(acc, L, S1, At, Bp, a.Lpub + size_t(j) * 4 * kPacketG, a.Spub + (size_t(i) * nb + j) * 4096, nullptr, nullptr, tid,
+                   sub ? i : -100);
     __syncthreads();
     store_tile_global(slot, npad, S1, tid);  // published transposed
     post_flag(tile_ready + i * nb + j, epoch);  // the updates of row i / column i wait for it
@@ -444,9 +472,10 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
         a.part_other[(size_t(i) * nb + j) * kCholNB + tid] = sv;
         a.part_other[nn + (size_t(j) * nb + i) * kCholNB + tid] = sv;
       }
-    } else {
-      double* o = a.Spub_other + size_t(i) * 4 * 16 * 64;
-      for (int e = tid; e < 4 * 16 * 64 / 2; e += 256) *reinterpret_cast<double2*>(o + 2 * e) = make_double2(sv, sv);
+    }
+    {
+      double* o = a.Spub_other + (size_t(i) * nb + j) * 4096;
+      for (int e = tid; e < 4096 / 2; e += 256) *reinterpret_cast<double2*>(o + 2 * e) = make_double2(sv, sv);
     }
     return;
   }
@@ -471,7 +500,7 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   }
   if (j >= 1) {
     // the sub-diagonal tile arrives 16 columns at a time from CTA (j, j-1): S1 rows 16 s .. = P_s^T, accD -= P_s P_s'
-    const double* src = a.Spub + size_t(j) * 4 * 16 * 64;
+    const double* src = a.Spub + (size_t(j) * nb + (j - 1)) * 4096;
     const int r0 = tid >> 5, c0 = (tid & 31) * 2;  // thread's two double2 of a slab: rows r0, r0 + 8
     double2 pre[2];
     auto issue = [&](int s) {
@@ -592,7 +621,10 @@ size_t chol_dag_flags_len(int npad) {
   return nb * nb;
 }
 // [barrier kernel's block inverses npad x 64 | packets parity 0 | packets parity 1 | slabs parity 0 | slabs parity 1]
-static size_t dag_pub_len(int npad) { return size_t(npad / kCholNB) * 4 * (kPacketG + 16 * 64); }
+static size_t dag_pub_len(int npad) {
+  const size_t nb = npad / kCholNB;
+  return nb * 4 * kPacketG + nb * nb * 4096;  // packets of the diagonal CTAs + slabs of every tile (i, k)
+}
 size_t chol_dag_lpub_len(int npad) { return size_t(npad) * kCholNB + 2 * dag_pub_len(npad); }
 
 __global__ void fill_sentinel_kernel(double* p, size_t n) {
@@ -615,7 +647,7 @@ int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
   const size_t half = size_t(l.npad / kCholNB) * 4 * kPacketG;
   const unsigned parity = l.chol_seq ? ((*l.chol_seq)++ & 1u) : 0u;
   a.M = l.M; a.npad = l.npad;
-  const size_t shalf = size_t(l.npad / kCholNB) * 4 * 16 * 64;
+  const size_t shalf = size_t(l.npad / kCholNB) * size_t(l.npad / kCholNB) * 4096;
   double* pk = l.Linv + size_t(l.npad) * kCholNB;
   a.Lpub = pk + parity * half;
   a.Lpub_other = pk + (parity ^ 1u) * half;

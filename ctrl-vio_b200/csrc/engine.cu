@@ -138,6 +138,11 @@ struct ctvio_engine {
 
   // state: two buffers (current / candidate) + snapshot
   DevState x[2], snap;
+  DevState xs;                 // third state buffer of the pipelined LM driver (swapped into x[] when it ends up current)
+  DevBuf<LmDecision> d_dec;    // device-side step decision (accept, next radius) read by the speculated linear solve
+  cudaEvent_t ev_iter = nullptr;  // recorded behind the last kernel of every LM step (before anything speculative)
+  bool speculate = true;       // CTVIO_NO_SPECULATION=1 switches the pipelined driver off
+  DevState& state(int i) { return i < 2 ? x[i] : xs; }
   int cur = 0;
   bool table_valid = false;
 
@@ -274,7 +279,7 @@ struct ArenaScope {
 };
 
 // enqueue the device -> pinned-host copies of the whole state (the caller synchronises the stream afterwards)
-int refresh_mirror(ctvio_engine* e) {
+int refresh_mirror(ctvio_engine* e, cudaStream_t on = nullptr) {
   const size_t need = 4 * size_t(e->nK) + kPStride * size_t(e->nK) + 6 * size_t(std::max(e->nB, 1)) + size_t(std::max(e->nL, 1)) + 8;
   if (need > e->h_mirror_cap) {
     if (e->h_mirror) cudaFreeHost(e->h_mirror);
@@ -289,7 +294,7 @@ int refresh_mirror(ctvio_engine* e) {
   }
   DevState& x = e->x[e->cur];
   double* m = e->h_mirror;
-  cudaStream_t st = e->stream;
+  cudaStream_t st = on ? on : e->stream;
   CUDA_OK(cudaMemcpyAsync(m, x.q.p, 4 * size_t(e->nK) * sizeof(double), cudaMemcpyDeviceToHost, st));
   m += 4 * size_t(e->nK);
   CUDA_OK(cudaMemcpyAsync(m, x.p.p, kPStride * size_t(e->nK) * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -731,7 +736,7 @@ VisualLaunch visual_launch(ctvio_engine* e, int xb, int nb, double cauchy) {
   v.obs = ImageObsPtrs{e->d_img_t.p, e->d_img_pi.p, e->d_img_pj.p, e->d_img_meta.p, int32_t(e->img.size())};
   v.items = e->d_items.p;
   v.n_items = e->n_items;
-  v.st = e->x[xb].ptrs();
+  v.st = e->state(xb).ptrs();
   v.ne = e->ne(nb);
   v.lm = e->lml();
   v.dims = e->dims();
@@ -749,7 +754,7 @@ ImuLaunch imu_launch(ctvio_engine* e, int xb, int nb) {
   v.obs = ImuObsPtrs{e->d_imu_t.p, e->d_imu_ga.p, int32_t(e->imu.size())};
   v.items = e->d_imu_items.p;
   v.n_items = e->n_imu_items;
-  v.st = e->x[xb].ptrs();
+  v.st = e->state(xb).ptrs();
   v.ne = e->ne(nb);
   v.dims = e->dims();
   v.sp = e->sp;
@@ -763,7 +768,7 @@ SmallFactorsLaunch small_launch(ctvio_engine* e, int xb, int nb) {
   SmallFactorsLaunch v;
   v.bf = BiasFactorPtrs{e->d_bf_ij.p, e->d_bf_s.p, int32_t(e->biasf.size())};
   v.prior = prior_ptrs(e);
-  v.st = e->x[xb].ptrs();
+  v.st = e->state(xb).ptrs();
   v.ne = e->ne(nb);
   v.dims = e->dims();
   v.cmask = e->d_cmask.p;
@@ -852,11 +857,11 @@ int shard_check_ownership(ctvio_engine* e) {
 }
 
 // the LM step: reduced system (+ all-reduce of [M | rhs | diagA] over NVLink in sharded mode), factor, solve
-int lm_step(ctvio_engine* e, int nb, double radius, const ApplyLaunch* fused_apply = nullptr) {
+int lm_step(ctvio_engine* e, int nb, double radius, const ApplyLaunch* fused_apply = nullptr, const double* radius_dev = nullptr) {
   LinearLaunch lin = linear_launch(e, nb);
   cudaStream_t st = e->stream;
   if (e->deterministic) cudaMemsetAsync(e->d_ticket.p, 0, 2 * sizeof(int32_t), st);
-  e->launches += launch_reduced_system(lin, radius, st);
+  e->launches += launch_reduced_system(lin, radius, st, radius_dev);
   if (e->world > 1) {
     // one all-reduce of the lower-triangular tiles + rhs + diagonal (half the bytes of the dense slab), damping after it
     std::string err;
@@ -996,6 +1001,7 @@ int ctvio_create(const ctvio_config* cfg, ctvio_handle* out) {
   e->rig.gravity = V3{cfg->gravity[0], cfg->gravity[1], cfg->gravity[2]};
   for (int k = 0; k < 6; ++k) e->rig.imu_info[k] = cfg->imu_info[k];
   if (const char* det = std::getenv("CTVIO_DETERMINISTIC")) e->deterministic = det[0] == '1';
+  if (const char* ns = std::getenv("CTVIO_NO_SPECULATION")) e->speculate = ns[0] != '1';
   const char* no_tma = std::getenv("CTVIO_NO_TMA");
   e->use_tma = !(no_tma && no_tma[0] == '1');
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1004,6 +1010,7 @@ int ctvio_create(const ctvio_config* cfg, ctvio_handle* out) {
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_zero, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&e->ev_iter) != cudaSuccess || e->d_dec.reserve(1) != cudaSuccess ||
       cudaHostAlloc(&e->h_pub, sizeof(LmPublished), cudaHostAllocMapped) != cudaSuccess ||
       cudaMallocHost(&e->h_scal, sizeof(LmScalars)) != cudaSuccess || e->d_scal.reserve(1) != cudaSuccess ||
       e->d_ticket.reserve(4) != cudaSuccess) {
@@ -1313,8 +1320,8 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
   auto make_apply = [&](int from, int to, double alpha) {
     ApplyLaunch ap;
     ap.dims = d;
-    ap.x = e->x[from].ptrs();
-    ap.xc = e->x[to].ptrs();
+    ap.x = e->state(from).ptrs();
+    ap.xc = e->state(to).ptrs();
     ap.dc = e->d_dc.p; ap.dl = e->d_dl.p;
     ap.alpha = alpha;
     ap.active = e->d_active.p;
@@ -1329,6 +1336,132 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     if (e->deterministic) cudaMemsetAsync(e->d_ticket.p, 0, 2 * sizeof(int32_t), st);
     e->launches += launch_apply_step(make_apply(from, to, alpha), st, reset);
   };
+
+  // ---- pipelined driver (single GPU, no bounds, default flush mode) --------------------------------------------
+  // The host round trip between two LM steps (publish -> host decision -> launch: ~10 us of an ~100 us step at C2) is
+  // taken off the critical path: gradient_norm_kernel also takes the accept / radius decision on the device, and the
+  // linear solve of step i+1 is enqueued BEFORE the host has seen step i, assuming acceptance (the common case),
+  // reading its radius from device memory and writing its candidate into a third state buffer.  When the host then
+  // finds step i rejected / invalid / terminating, the speculated kernels' results are simply never used (they touch
+  // only the step vectors, the free state buffer and per-step scalars that the next real step resets).
+  const bool pipelined = e->speculate && !sharded && !is_constrained && !e->deterministic;
+  int cur_ne = cur;  // normal-equation buffer of the current point (state and normal equations flip separately here)
+  if (pipelined) {
+    rc = alloc_state(e, e->xs);
+    if (rc) return rc;
+    bool spec_ready = false;     // a speculated linear solve from (cur, cur_ne) into state `spec_out` is in flight
+    bool spec_in_flight = false; // speculated kernels that read ne_slab[cur_ne ^ 1] may still be running
+    int spec_out = -1;
+    cudaEventRecord(e->ev_iter, st);
+    while (true) {
+      if (iter >= max_iterations) { term = CTVIO_TERM_NO_CONVERGENCE; break; }
+      if (last_ok && gmax <= gradient_tolerance) { term = CTVIO_TERM_GRADIENT; break; }
+      if (radius < min_radius) { term = CTVIO_TERM_MIN_RADIUS; break; }
+      ++iter;
+      const int cand_ne = cur_ne ^ 1;
+      int cand;
+      if (spec_ready) {
+        cand = spec_out;  // the linear solve of this step already ran (or is running) behind the previous step
+        // ne_slab[cand_ne] was the current point's buffer of the previous step: its last reader finished before that
+        // step's scalars were published, and the speculated kernels read ne_slab[cur_ne] only
+        prezero_slab(e, cand_ne);
+      } else {
+        cand = 0;
+        while (cand == cur) ++cand;
+        if (!spec_in_flight) prezero_slab(e, cand_ne);  // else: cleared in stream order by evaluate()
+        const ApplyLaunch full_step = make_apply(cur, cand, 1.0);
+        rc = lm_step(e, cur_ne, radius, &full_step);
+        if (rc) return rc;
+      }
+      sum.num_linear_solves++;
+      evaluate(e, cand, cand_ne, true, false);
+      sum.num_jacobian_evals++;
+      const LmDecideArgs da{e->d_dec.p, x_cost, radius, min_relative_decrease, max_radius};
+      e->launches += launch_gradient_norm(linear_launch(e, cand_ne), e->state(cand).ptrs(), e->opt.fix_ld, e->opt.ld_lower,
+                                          e->opt.ld_upper, st, false, e->h_pub, ++e->pub_seq, &da);
+      cudaEventRecord(e->ev_iter, st);
+      // ---- speculate: step iter + 1 from (cand, cand_ne), radius from the device-side decision ----
+      spec_ready = false;
+      if (iter < max_iterations) {
+        spec_out = 0;
+        while (spec_out == cur || spec_out == cand) ++spec_out;
+        const ApplyLaunch spec_step = make_apply(cand, spec_out, 1.0);
+        rc = lm_step(e, cand_ne, 0.0, &spec_step, &e->d_dec.p->radius_next);
+        if (rc) return rc;
+        spec_ready = true;
+        spec_in_flight = true;
+      }
+      rc = read_scalars(e, true);
+      if (rc) return rc;
+      const LmScalars sc = *e->h_scal;
+      const LmDecision dec = const_cast<const LmPublished*>(e->h_pub)->dec;
+      if (!dec.valid) {
+        spec_ready = false;
+        ++sum.num_unsuccessful_steps;
+        last_ok = false;
+        if (++num_invalid >= max_consecutive_invalid) { term = CTVIO_TERM_FAILURE; break; }
+        radius /= decrease_factor;
+        decrease_factor *= 2.0;
+        continue;
+      }
+      num_invalid = 0;
+      const double step_norm = std::sqrt(sc.step_norm2), x_norm = std::sqrt(sc.x_norm2);
+      if (step_norm <= parameter_tolerance * (x_norm + parameter_tolerance)) { term = CTVIO_TERM_PARAMETER; break; }
+      const double cost_change = x_cost - sc.cost_eval;
+      if (std::fabs(cost_change) <= function_tolerance * x_cost) { term = CTVIO_TERM_FUNCTION; break; }
+      if (dec.accept) {
+        cur = cand;
+        cur_ne = cand_ne;
+        x_cost = sc.cost_eval;
+        gmax = sc.gmax;
+        radius = dec.radius_next;
+        decrease_factor = 2.0;
+        last_ok = true;
+        ++sum.num_successful_steps;
+        if (!spec_ready) spec_in_flight = false;
+      } else {
+        spec_ready = false;
+        radius /= decrease_factor;
+        decrease_factor *= 2.0;
+        last_ok = false;
+        ++sum.num_unsuccessful_steps;
+      }
+    }
+    // the current state must live in x[0] / x[1] outside this function: exchange buffer names (kernels in flight hold
+    // raw pointers and only touch buffers that are free under either name)
+    if (cur == 2) {
+      const int f = 0;  // any of the two: neither is current
+      DevState &a = e->xs, &b = e->x[f];
+      std::swap(a.q.p, b.q.p); std::swap(a.q.cap, b.q.cap);
+      std::swap(a.p.p, b.p.p); std::swap(a.p.cap, b.p.cap);
+      std::swap(a.bias.p, b.bias.p); std::swap(a.bias.cap, b.bias.cap);
+      std::swap(a.rho.p, b.rho.p); std::swap(a.rho.cap, b.rho.cap);
+      std::swap(a.ld.p, b.ld.p); std::swap(a.ld.cap, b.ld.cap);
+      std::swap(a.tab.p, b.tab.p); std::swap(a.tab.cap, b.tab.cap);
+      cur = f;
+    }
+    e->cur = cur;
+    e->table_valid = true;
+    e->slab_zeroed[0] = e->slab_zeroed[1] = false;  // (a pending clear is ordered by ev_zero only inside this loop)
+    // results: wait for the last REAL kernel only (ev_iter); speculated leftovers keep running behind it and are
+    // ordered before anything the next call enqueues on the engine stream
+    CUDA_OK(cudaStreamWaitEvent(e->stream2, e->ev_iter, 0));
+    {
+      const int rcm = refresh_mirror(e, e->stream2);
+      if (rcm) return rcm;
+    }
+    CUDA_OK(cudaStreamSynchronize(e->stream2));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev_iter);
+    sum.iterations = iter;
+    sum.termination = term;
+    sum.final_cost = x_cost;
+    sum.final_radius = radius;
+    sum.device_ms = ms;
+    sum.kernel_launches = e->launches - launches0;
+    if (out) *out = sum;
+    return CTVIO_OK;
+  }
 
   while (true) {
     if (iter >= max_iterations) { term = CTVIO_TERM_NO_CONVERGENCE; break; }

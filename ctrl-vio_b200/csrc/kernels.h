@@ -125,8 +125,24 @@ struct LmScalars {
 };
 // host-visible copy of the scalar block (mapped pinned memory) with a sequence number: the last kernel of an LM step
 // writes it directly, the host spins on `seq` instead of paying a device-to-host copy plus a stream synchronisation
+// Step decision of the LM driver, taken on the device by the last kernel of a step (gradient_norm_kernel) so that the
+// linear solve of the NEXT step can be enqueued before the host has seen this step's scalars (pipelined driver,
+// engine.cu): the speculated scale_copy_kernel reads `radius_next` from device memory.
+struct LmDecision {
+  double radius_next;         // trust-region radius after an accepted step (Ceres 1.14 trust_region_minimizer.cc)
+  double model_cost_change;   // -g'd - d'Hd / 2
+  double rho;                 // relative decrease (cost(x) - cost(x + d)) / model_cost_change
+  int32_t valid;              // the linear solve succeeded and the model decreases
+  int32_t accept;             // valid and rho > min_relative_decrease
+};
+struct LmDecideArgs {
+  LmDecision* dec;            // device copy (null: no decision is taken)
+  double x_cost, radius;      // cost and radius at the current point
+  double min_relative_decrease, max_radius;
+};
 struct LmPublished {
   LmScalars s;
+  LmDecision dec;
   unsigned long long seq;
   unsigned long long pad;
 };
@@ -268,7 +284,8 @@ int launch_jacobi_scale(const LinearLaunch& a, cudaStream_t s);
 // builds the damped, scaled reduced system, factors it, solves and back-substitutes: dc, dl, gd, dHd
 int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s);
 // the three stages of launch_lm_step, separately launchable for measurement
-int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s);
+// radius_dev != null: the radius is read from device memory (first double of an LmDecision)
+int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s, const double* radius_dev = nullptr);
 int launch_factor_solve(const LinearLaunch& a, cudaStream_t s);
 // tile-DAG variant (chol_dag.cu): usable when every tile gets its own SM
 bool chol_dag_supported(int npad, int n_sm);
@@ -287,7 +304,8 @@ int launch_jacobi_scale_from_diag(const LinearLaunch& a, cudaStream_t s);
 // reset = false: the accumulator was already zeroed by scale_copy_kernel of the same LM step
 // pub != nullptr: after the norm the whole scalar block is copied to *pub (mapped host memory) and pub->seq = seq
 int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld, double ld_lower, double ld_upper,
-                         cudaStream_t s, bool reset = true, LmPublished* pub = nullptr, unsigned long long seq = 0);
+                         cudaStream_t s, bool reset = true, LmPublished* pub = nullptr, unsigned long long seq = 0,
+                         const LmDecideArgs* decide = nullptr);
 
 struct ApplyLaunch {
   int32_t count_camera;     // sharded mode: only rank 0 counts the (replicated) camera blocks in the norms

@@ -48,7 +48,8 @@ int launch_jacobi_scale(const LinearLaunch& a, cudaStream_t s) {
 }
 
 // M = S A S + clamp(diag)/radius on the full (padded, symmetric) matrix; rhs = S g
-__global__ void scale_copy_kernel(LinearLaunch a, double radius) {
+__global__ void scale_copy_kernel(LinearLaunch a, double radius, const double* __restrict__ radius_dev) {
+  if (radius_dev) radius = *radius_dev;  // speculated step: decided by the previous step's gradient_norm_kernel
   const int npad = a.npad, np = a.dims.np;
   const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx < size_t(a.dims.nL)) {
@@ -347,10 +348,10 @@ int launch_jacobi_scale_from_diag(const LinearLaunch& a, cudaStream_t s) {
   return 1;
 }
 
-int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s) {
+int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s, const double* radius_dev) {
   int launches = 0;
   const size_t total = std::max(size_t(a.npad) * a.npad, size_t(a.dims.nL));
-  scale_copy_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(a, radius);
+  scale_copy_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(a, radius, radius_dev);
   ++launches;
   if (a.n_schur_items > 0) {
     schur_tile_kernel<<<a.n_schur_items, 256, 0, s>>>(a);
@@ -372,7 +373,8 @@ int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s) {
 // max-norm of the (bounds-projected) gradient over the active parameters; ONE CTA (the vectors are small), so the
 // result needs no atomics and the same CTA can hand the finished scalar block of the LM step to the host
 __global__ void __launch_bounds__(1024) gradient_norm_kernel(LinearLaunch a, StatePtrs st, int fix_ld, double ld_lower,
-                                                             double ld_upper, LmPublished* pub, unsigned long long seq) {
+                                                             double ld_upper, LmPublished* pub, unsigned long long seq,
+                                                             LmDecideArgs da) {
   __shared__ double red[32];
   const int np = a.dims.np, nL = a.dims.nL;
   double v = 0.0;
@@ -412,6 +414,26 @@ __global__ void __launch_bounds__(1024) gradient_norm_kernel(LinearLaunch a, Sta
 #pragma unroll
         for (int k = 0; k < 5; ++k) dst[k] = w[k];
         *reinterpret_cast<uint2*>(dst + 5) = w5;
+        if (da.dec) {
+          // accept / reject and the next radius, exactly as the host driver would compute them (the host ADOPTS these
+          // values in pipelined mode, so the two can not disagree); no fused multiply-adds: same roundings as the
+          // plain C++ expressions of the oracle
+          LmScalars sc;
+          uint4* loc = reinterpret_cast<uint4*>(&sc);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) loc[k] = w[k];
+          *reinterpret_cast<uint2*>(loc + 5) = w5;
+          LmDecision d;
+          d.model_cost_change = __dsub_rn(-sc.gd, __dmul_rn(0.5, sc.dHd));
+          d.valid = (!sc.chol_fail && isfinite(d.model_cost_change) && d.model_cost_change > 0.0) ? 1 : 0;
+          d.rho = __ddiv_rn(__dsub_rn(da.x_cost, sc.cost_eval), d.model_cost_change);
+          d.accept = (d.valid && d.rho > da.min_relative_decrease) ? 1 : 0;
+          const double t = __dsub_rn(__dmul_rn(2.0, d.rho), 1.0);
+          const double t3 = __dmul_rn(__dmul_rn(t, t), t);
+          d.radius_next = fmin(da.max_radius, __ddiv_rn(da.radius, fmax(1.0 / 3.0, __dsub_rn(1.0, t3))));
+          *da.dec = d;
+          pub->dec = d;
+        }
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long*>(&pub->seq) = seq;
       }
@@ -419,9 +441,11 @@ __global__ void __launch_bounds__(1024) gradient_norm_kernel(LinearLaunch a, Sta
   }
 }
 int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld, double ld_lower, double ld_upper,
-                         cudaStream_t s, bool reset, LmPublished* pub, unsigned long long seq) {
+                         cudaStream_t s, bool reset, LmPublished* pub, unsigned long long seq, const LmDecideArgs* decide) {
   if (reset) cudaMemsetAsync(&a.scal->gmax, 0, sizeof(double), s);
-  gradient_norm_kernel<<<1, 1024, 0, s>>>(a, st, fix_ld, ld_lower, ld_upper, pub, seq);
+  LmDecideArgs da{};
+  if (decide) da = *decide;
+  gradient_norm_kernel<<<1, 1024, 0, s>>>(a, st, fix_ld, ld_lower, ld_upper, pub, seq, da);
   return 1;
 }
 
