@@ -226,6 +226,7 @@ struct CholDagArgs {
   int* flags;         // tile_ready[nb*nb]: L(i,k) final and written (release / acquire, epoch valued)
   int epoch;
   LmScalars* scal;
+  const int32_t* go;  // speculated LM step: null or &LmDecision::go (0: every CTA returns before touching any message)
 };
 
 #ifdef CTVIO_CHOL_TIMING
@@ -401,6 +402,9 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   double* xf_pub = a.part + 2 * nn;     // [j][64] forward-solved x_j
   double* xb_pub = xf_pub + size_t(nb) * kCholNB;  // [j][64] solution x_j
   const double sv = sentinel_value();
+  // speculated step behind a rejected / terminating one: nothing has been sent or reset yet, and the host takes the
+  // launch out of its parity count (engine.cu)
+  if (a.go && *a.go == 0) return;
 
   const int cta = blockIdx.x;
   if (cta >= nb) {
@@ -576,18 +580,27 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     vec2[tid] = vec[tid];
   }
   DSTAMP(j, 6);
-  // explicit inverse of the diagonal block (into D, free since the factorisation): off the critical chain for every
-  // column but the last - the backward sweep arrives here much later - and it turns the backward solve of this block
-  // into one 64x64 product
-  inverse_from_packets(Pk, D, tid);
-
-  // backward sweep: x_j = L_jj^-T (yf_j - sum_{r > j} L(r,j)^T x_r); the partials are self-validating words
-  {
-    const double sp = sum_partials(bwd_part + (size_t(j) * nb + j + 1) * kCholNB, nb - 1 - j, kCholNB, red, tid);
-    if (tid < kCholNB) vec[tid] = vec2[tid] - sp;
+  if (j == nb - 1) {
+    // last block: the backward sweep starts here, with nothing to wait for - substitute straight from the packets
+    // (forming the explicit inverse first, as the other columns do off the chain, would put ~4 us ON it)
+    __syncthreads();
+    block_solve_packets<false>(Pk, vec, x16, tid);  // vec = yf_j on entry (set above), x_j on exit
+    if (tid < kCholNB) {
+      st_relaxed1(xb_pub + j * kCholNB + tid, vec[tid]);  // tile owners (j, k) spin on xb_pub
+      vec2[tid] = vec[tid];
+    }
+  } else {
+    // explicit inverse of the diagonal block (into D, free since the factorisation): off the critical chain - the
+    // backward sweep arrives here much later - and it turns the backward solve of this block into one 64x64 product
+    inverse_from_packets(Pk, D, tid);
+    // backward sweep: x_j = L_jj^-T (yf_j - sum_{r > j} L(r,j)^T x_r); the partials are self-validating words
+    {
+      const double sp = sum_partials(bwd_part + (size_t(j) * nb + j + 1) * kCholNB, nb - 1 - j, kCholNB, red, tid);
+      if (tid < kCholNB) vec[tid] = vec2[tid] - sp;
+    }
+    __syncthreads();
+    tile_matvec_t(D, vec, xb_pub + j * kCholNB, red, tid, vec2);  // x_j = Xi^T v ; tile owners (j, k) spin on xb_pub
   }
-  __syncthreads();
-  tile_matvec_t(D, vec, xb_pub + j * kCholNB, red, tid, vec2);  // x_j = Xi^T v ; tile owners (j, k) spin on xb_pub
   __syncthreads();
   if (j >= 1) {
     // own sub-diagonal tile: L(j,j-1)^T x_j for diagonal CTA j-1, the next link of the backward chain
@@ -656,7 +669,7 @@ int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
   a.part = l.chol_part + parity * dag_part_half(l.npad);
   a.part_other = l.chol_part + (parity ^ 1u) * dag_part_half(l.npad);
   a.rhs = l.rhs; a.y = l.y; a.yf = l.yf;
-  a.flags = l.chol_flags; a.scal = l.scal;
+  a.flags = l.chol_flags; a.scal = l.scal; a.go = l.go;
   // process-wide unique, never 0 (flag buffers start zeroed); a wrap after 2^31 launches would need the flags of a
   // buffer to hold exactly the value 2^31 launches old: not a practical concern
   a.epoch = int(epoch_src.fetch_add(1, std::memory_order_relaxed) % 0x7ffffffeu) + 1;

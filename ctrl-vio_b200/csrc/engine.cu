@@ -797,6 +797,7 @@ LinearLaunch linear_launch(ctvio_engine* e, int nb) {
   a.hh = e->d_hh.p; a.dc = e->d_dc.p; a.dl = e->d_dl.p;
   a.npad = e->npad;
   a.scal = e->d_scal.p;
+  a.go = nullptr;
   a.det_ticket = e->deterministic ? e->d_ticket.p : nullptr;
   return a;
 }
@@ -857,8 +858,10 @@ int shard_check_ownership(ctvio_engine* e) {
 }
 
 // the LM step: reduced system (+ all-reduce of [M | rhs | diagA] over NVLink in sharded mode), factor, solve
-int lm_step(ctvio_engine* e, int nb, double radius, const ApplyLaunch* fused_apply = nullptr, const double* radius_dev = nullptr) {
+int lm_step(ctvio_engine* e, int nb, double radius, const ApplyLaunch* fused_apply = nullptr, const double* radius_dev = nullptr,
+            const int32_t* go = nullptr) {
   LinearLaunch lin = linear_launch(e, nb);
+  lin.go = go;
   cudaStream_t st = e->stream;
   if (e->deterministic) cudaMemsetAsync(e->d_ticket.p, 0, 2 * sizeof(int32_t), st);
   e->launches += launch_reduced_system(lin, radius, st, radius_dev);
@@ -1352,6 +1355,7 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     bool spec_ready = false;     // a speculated linear solve from (cur, cur_ne) into state `spec_out` is in flight
     bool spec_in_flight = false; // speculated kernels that read ne_slab[cur_ne ^ 1] may still be running
     int spec_out = -1;
+    unsigned spec_chol_seq0 = e->chol_seq;
     cudaEventRecord(e->ev_iter, st);
     while (true) {
       if (iter >= max_iterations) { term = CTVIO_TERM_NO_CONVERGENCE; break; }
@@ -1376,7 +1380,8 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
       sum.num_linear_solves++;
       evaluate(e, cand, cand_ne, true, false);
       sum.num_jacobian_evals++;
-      const LmDecideArgs da{e->d_dec.p, x_cost, radius, min_relative_decrease, max_radius};
+      const LmDecideArgs da{e->d_dec.p, x_cost, radius, min_relative_decrease, max_radius,
+                            parameter_tolerance, function_tolerance, gradient_tolerance, min_radius};
       e->launches += launch_gradient_norm(linear_launch(e, cand_ne), e->state(cand).ptrs(), e->opt.fix_ld, e->opt.ld_lower,
                                           e->opt.ld_upper, st, false, e->h_pub, ++e->pub_seq, &da);
       cudaEventRecord(e->ev_iter, st);
@@ -1386,7 +1391,8 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
         spec_out = 0;
         while (spec_out == cur || spec_out == cand) ++spec_out;
         const ApplyLaunch spec_step = make_apply(cand, spec_out, 1.0);
-        rc = lm_step(e, cand_ne, 0.0, &spec_step, &e->d_dec.p->radius_next);
+        spec_chol_seq0 = e->chol_seq;
+        rc = lm_step(e, cand_ne, 0.0, &spec_step, &e->d_dec.p->radius_next, &e->d_dec.p->go);
         if (rc) return rc;
         spec_ready = true;
         spec_in_flight = true;
@@ -1395,6 +1401,12 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
       if (rc) return rc;
       const LmScalars sc = *e->h_scal;
       const LmDecision dec = const_cast<const LmPublished*>(e->h_pub)->dec;
+      if (spec_ready && !dec.go) {
+        // the device has cancelled the speculated step (its expensive kernels return at once): it does not count as a
+        // launch of the tile-DAG solver (message buffer parity), and this driver will not use it
+        e->chol_seq = spec_chol_seq0;
+        spec_ready = false;
+      }
       if (!dec.valid) {
         spec_ready = false;
         ++sum.num_unsuccessful_steps;

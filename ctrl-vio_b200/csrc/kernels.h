@@ -134,11 +134,14 @@ struct LmDecision {
   double rho;                 // relative decrease (cost(x) - cost(x + d)) / model_cost_change
   int32_t valid;              // the linear solve succeeded and the model decreases
   int32_t accept;             // valid and rho > min_relative_decrease
+  int32_t go;                 // accept, and none of the termination tests fires: the speculated next step is needed
+  int32_t pad;
 };
 struct LmDecideArgs {
   LmDecision* dec;            // device copy (null: no decision is taken)
   double x_cost, radius;      // cost and radius at the current point
   double min_relative_decrease, max_radius;
+  double parameter_tolerance, function_tolerance, gradient_tolerance, min_radius;
 };
 struct LmPublished {
   LmScalars s;
@@ -279,6 +282,7 @@ struct LinearLaunch {
   int32_t npad;
   LmScalars* scal;
   int* det_ticket;              // deterministic mode (K4 parts, step kernels): flush in block order; else null
+  const int32_t* go;            // speculated step only: &LmDecision::go - the expensive kernels return at once when it is 0
 };
 int launch_jacobi_scale(const LinearLaunch& a, cudaStream_t s);
 // builds the damped, scaled reduced system, factors it, solves and back-substitutes: dc, dl, gd, dHd
