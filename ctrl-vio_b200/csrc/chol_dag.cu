@@ -21,6 +21,8 @@
 // Needs nb (nb + 1) / 2 <= #SMs (all CTAs co-resident: cooperative launch); launch_factor_solve falls back to the
 // barrier kernel (chol_coop.cu) otherwise.
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 
 #include "chol_tiles.cuh"
 #include "dmma_tiles.cuh"
@@ -45,6 +47,39 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 // slots of the OTHER buffer at the end of a launch (nobody reads that buffer during this launch), so the next launch
 // finds sentinels.  (A NaN in the data - non-positive pivot - is the default qNaN, never the sentinel: no deadlock.)
 constexpr unsigned long long kSentinel = 0xFFF8C0DEC0DE0001ull;
+// ---- thread-block cluster / distributed shared memory (the two hops per block column of the critical chain) ----
+// Chain positions p = 0, 1, 2, ... = diag 0, tile (1,0), diag 1, tile (2,1), ... are consecutive CTAs, so position p + 1
+// sits in the same cluster unless p + 1 is a multiple of the cluster size: the producer then writes its message words
+// straight into the consumer's shared memory (st.shared::cluster), the consumer spins on its OWN shared memory
+// (~30 cycles per poll instead of an L2 round trip of 600-1200, die-crossing dependent).  Same self-validating words:
+// the consumer fills its receive area with sentinels, then arrives at the cluster barrier; a producer waits on that
+// barrier once, before its first remote store.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster2(unsigned addr, double2 v) {
+  asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ double2 ld_shared_volatile2(const double* p) {
+  double2 v;
+  asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ bool is_sentinel(double v) { return static_cast<unsigned long long>(__double_as_longlong(v)) == kSentinel; }
 __device__ __forceinline__ double2 ld_relaxed2(const double* p) {
   double2 v;
@@ -273,7 +308,7 @@ __device__ __forceinline__ void tile_matvec_t(const double* St, const double* v,
 // product after its operands arrive instead of a whole one, which keeps this CTA in step with the factorisation.
 __device__ __forceinline__ void trsm_pipelined(Frag& acc, const Lane& L, double* S1, double* At, double* Bp2,
                                                const double* Lpub_col, double* slab_out, const double* Ua, const double* Ub,
-                                               int tid, int jstamp) {
+                                               int tid, int jstamp, const double* pk_local = nullptr, unsigned slab_remote = 0u) {
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   // packet words of this thread: e = tid, tid + 256, tid + 512 of the 640 double2 of a full packet (16 rows x 40); the
   // last packet only carries the 16x16 inverse (128 double2).  Loads of packet s + 1 are IN FLIGHT while step s computes.
@@ -288,6 +323,7 @@ __device__ __forceinline__ void trsm_pipelined(Frag& acc, const Lane& L, double*
   const int goff3 = tid < 128 ? (tid >> 3) * 80 + 64 + (tid & 7) * 2 : -1, soff3 = (tid >> 3) * kPS + 64 + (tid & 7) * 2;
   double2 pre[3];
   auto issue = [&](int s) {
+    if (pk_local) return;  // the packets arrive in this CTA's shared memory
     const double* src = Lpub_col + size_t(s) * kPacketG;
     if (s < 3) {
 #pragma unroll
@@ -298,6 +334,20 @@ __device__ __forceinline__ void trsm_pipelined(Frag& acc, const Lane& L, double*
     }
   };
   auto commit = [&](int s, double* Bp) {
+    if (pk_local) {  // Bp IS the receive area of packet s: wait for this thread's words
+      if (s < 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (goff[u] >= 0) {
+            double2 v = ld_shared_volatile2(Bp + soff[u]);
+            while (is_sentinel(v.x) || is_sentinel(v.y)) v = ld_shared_volatile2(Bp + soff[u]);
+          }
+      } else if (goff3 >= 0) {
+        double2 v = ld_shared_volatile2(Bp + soff3);
+        while (is_sentinel(v.x) || is_sentinel(v.y)) v = ld_shared_volatile2(Bp + soff3);
+      }
+      return;
+    }
     const double* src = Lpub_col + size_t(s) * kPacketG;
     if (s < 3) {
 #pragma unroll
@@ -314,7 +364,7 @@ __device__ __forceinline__ void trsm_pipelined(Frag& acc, const Lane& L, double*
   issue(0);
 #pragma unroll 1
   for (int s = 0; s < 4; ++s) {
-    double* Bp = Bp2 + (s & 1) * kPacket;
+    double* Bp = pk_local ? const_cast<double*>(pk_local) + s * kPacket : Bp2 + (s & 1) * kPacket;
     // lazy last update, one slab AHEAD of the solve (slab 0 and 1 before the first packet is needed, slab s + 1 while
     // packet s is in flight), so that nothing but the 16x16 product of step 3 follows the last packet
     if (Ua) {
@@ -366,7 +416,9 @@ __device__ __forceinline__ void trsm_pipelined(Frag& acc, const Lane& L, double*
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int e = tid + 256 * u, r = e >> 5, c = (e & 31) * 2;
-        st_relaxed2(slab_out + size_t(s) * 16 * 64 + r * 64 + c, *reinterpret_cast<const double2*>(S1 + (16 * s + r) * kTS + c));
+        const double2 v = *reinterpret_cast<const double2*>(S1 + (16 * s + r) * kTS + c);
+        if (slab_remote) st_cluster2(slab_remote + unsigned(((16 * s + r) * kTS + c) * sizeof(double)), v);  // diagonal CTA's S1
+        st_relaxed2(slab_out + size_t(s) * 16 * 64 + r * 64 + c, v);
       }
     }
     // d. trailing columns of the tile:  T[:, c] -= sum_k P_s[:, k] L_jj[c][16 s + k]  for c >= 16 (s + 1)
@@ -406,12 +458,38 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   // launch out of its parity count (engine.cu)
   if (a.go && *a.go == 0) return;
 
-  const int cta = blockIdx.x;
-  if (cta >= nb) {
+  // chain order: position p = blockIdx.x: p even < 2 nb - 1: diagonal CTA p / 2; p odd: sub-diagonal tile
+  // ((p + 1) / 2, (p - 1) / 2); then the other tiles (i >= j + 2) column by column; then fillers (grid padded to the
+  // cluster size).  Consecutive chain positions share a cluster (see the helpers above).
+  const int pos = blockIdx.x, nchain = 2 * nb - 1;
+  const unsigned crank = cluster_ctarank(), csize = cluster_nctarank();
+  const bool dsm = csize > 1;
+  const bool is_diag = pos < nchain && (pos & 1) == 0;
+  const bool recv_local = dsm && pos < nchain && pos > 0 && crank != 0;        // my predecessor on the chain is in my cluster
+  const bool send_remote = dsm && pos + 1 < nchain && crank + 1 < csize;       // my successor on the chain is in my cluster
+  if (dsm) {
+    // receive areas <- sentinels (diagonal CTA: the four slabs in S1; sub-diagonal tile: the four packets in Pk), then arrive
+    if (recv_local) {
+      double* area = is_diag ? S1 : Pk;
+      const int n2 = (is_diag ? kTile : 4 * kPacket) / 2;
+      for (int e = tid; e < n2; e += 256) *reinterpret_cast<double2*>(area + 2 * e) = make_double2(sv, sv);
+    }
+    __syncthreads();
+    cluster_arrive();
+    if (pos >= nb * (nb + 1) / 2) { cluster_wait(); return; }  // filler CTA
+  }
+  if (!is_diag) {
     // ======================= tile (i, j), i > j =======================
-    int t = cta - nb, j = 0;
-    while (t >= nb - 1 - j) { t -= nb - 1 - j; ++j; }
-    const int i = j + 1 + t;
+    int i, j;
+    if (pos < nchain) {
+      i = (pos + 1) >> 1;
+      j = i - 1;
+    } else {
+      int t = pos - nchain;
+      j = 0;
+      while (t >= nb - 2 - j) { t -= nb - 2 - j; ++j; }
+      i = j + 2 + t;
+    }
     const bool sub = i == j + 1;  // sub-diagonal tile: feeds the diagonal CTA of row i slab by slab
     double* slot = a.M + size_t(i) * kCholNB * npad + j * kCholNB;
     Frag acc;
@@ -458,8 +536,13 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     }
     // L(i,j) = T L_jj^-T, 16 columns at a time behind the factorisation of block column j; every finished slab is
     // published (diagonal CTA i if this is the sub-diagonal tile, the tiles (r, i), r > i, and (i, j+1) otherwise)
+    unsigned slab_remote = 0u;
+    if (dsm) {
+      cluster_wait();  // every CTA of the cluster has prepared its receive area (long ago by now)
+      if (sub && send_remote) slab_remote = mapa_u32(smem_u32(S1), crank + 1);
+    }
     trsm_pipelined(acc, L, S1, At, Bp, a.Lpub + size_t(j) * 4 * kPacketG, a.Spub + (size_t(i) * nb + j) * 4096, nullptr, nullptr, tid,
-                   sub ? i : -100);
+                   sub ? i : -100, (sub && recv_local) ? Pk : nullptr, slab_remote);
     __syncthreads();
     store_tile_global(slot, npad, S1, tid);  // published transposed
     post_flag(tile_ready + i * nb + j, epoch);  // the updates of row i / column i wait for it
@@ -485,7 +568,7 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   }
 
   // ======================= diagonal CTA j: tile (j, j) =======================
-  const int j = cta;
+  const int j = pos >> 1;
   DSTAMP(j, 0);
   Frag accD;
   frag_load_global(accD, a.M + size_t(j) * kCholNB * npad + j * kCholNB, npad, L);
@@ -511,16 +594,25 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
       pre[0] = ld_relaxed2(src + size_t(s) * 1024 + r0 * 64 + c0);
       pre[1] = ld_relaxed2(src + size_t(s) * 1024 + (r0 + 8) * 64 + c0);
     };
-    issue(0);
+    if (!recv_local) issue(0);
 #pragma unroll 1
     for (int s = 0; s < 4; ++s) {
+      if (recv_local) {  // the slabs land in S1 itself (written by the sub-diagonal CTA through the cluster's shared memory)
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const double* w = src + size_t(s) * 1024 + (r0 + 8 * u) * 64 + c0;
-        while (is_sentinel(pre[u].x) || is_sentinel(pre[u].y)) pre[u] = ld_relaxed2(w);
-        *reinterpret_cast<double2*>(S1 + (16 * s + r0 + 8 * u) * kTS + c0) = pre[u];
+        for (int u = 0; u < 2; ++u) {
+          const double* w = S1 + (16 * s + r0 + 8 * u) * kTS + c0;
+          double2 v = ld_shared_volatile2(w);
+          while (is_sentinel(v.x) || is_sentinel(v.y)) v = ld_shared_volatile2(w);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const double* w = src + size_t(s) * 1024 + (r0 + 8 * u) * 64 + c0;
+          while (is_sentinel(pre[u].x) || is_sentinel(pre[u].y)) pre[u] = ld_relaxed2(w);
+          *reinterpret_cast<double2*>(S1 + (16 * s + r0 + 8 * u) * kTS + c0) = pre[u];
+        }
+        if (s < 3) issue(s + 1);
       }
-      if (s < 3) issue(s + 1);
       __syncthreads();
       DSTAMP(j, 8 + s);
       if (s == 3) DSTAMP(j, 2);
@@ -535,6 +627,10 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   // partial of the sub-diagonal tile (a copy of L(j,j-1)^T sits in S1: the four slabs).
   double* own = red;  // [64] L(j,j-1) x_{j-1}   (red is free until the backward sweep)
   double* gpk = a.Lpub + size_t(j) * 4 * kPacketG;
+  unsigned rpk = 0u;  // the sub-diagonal tile's packet area, when that CTA is the next one of this cluster
+  if (send_remote) rpk = mapa_u32(smem_u32(Pk), crank + 1);
+  // (the cluster barrier is waited on by the publishing warps right before their first remote store - by then every CTA
+  //  of the cluster has long arrived - so that the pivot chain of this block starts without it)
   auto side = [&](int step) {
     if (j == 0) return;
     const int tt = tid - 32;  // 0..223
@@ -552,6 +648,7 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
     }
   };
   auto pub = [&](int s) {  // warps 1..7: packet s (panel + 16x16 inverse) -> global; the words validate themselves
+    if (dsm && s == 0) cluster_wait();
     const int tt = tid - 32;
     const double* src = Pk + s * kPacket;
     double* dst = gpk + size_t(s) * kPacketG;
@@ -559,13 +656,17 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
       const int r = e / 40, c = (e - r * 40) * 2;
       double2 v = *reinterpret_cast<const double2*>(src + r * kPS + c);
       if (c < 16 * (s + 1) && c < 64) v = make_double2(0.0, 0.0);  // rows of the panel above the diagonal block: unused
+      if (rpk) st_cluster2(rpk + unsigned((s * kPacket + r * kPS + c) * sizeof(double)), v);  // the chain's consumer first
       st_relaxed2(dst + r * 80 + c, v);
     }
   };
   auto pub_last = [&]() {  // all threads: the last 16x16 inverse
+    if (dsm && tid < 32) cluster_wait();  // (warp 0 has not published anything yet)
     if (tid < 128) {
       const int r = tid >> 3, c = 64 + (tid & 7) * 2;
-      st_relaxed2(gpk + size_t(3) * kPacketG + r * 80 + c, *reinterpret_cast<const double2*>(Pk + 3 * kPacket + r * kPS + c));
+      const double2 v = *reinterpret_cast<const double2*>(Pk + 3 * kPacket + r * kPS + c);
+      if (rpk) st_cluster2(rpk + unsigned((3 * kPacket + r * kPS + c) * sizeof(double)), v);
+      st_relaxed2(gpk + size_t(3) * kPacketG + r * 80 + c, v);
     }
   };
   if (!factor_64_pipe(D, Pk, L16t, rdiag, &s_bad, pub, pub_last, side) && tid == 0) a.scal->chol_fail = 1;
@@ -619,6 +720,8 @@ __global__ void __launch_bounds__(256, 1) chol_dag_kernel(CholDagArgs a) {
   }
 }
 
+constexpr int kDagCluster = 8;
+static std::atomic<long long> g_dag_cluster_launches{0};
 // number of CTAs the DAG kernel needs for nb block columns
 static int dag_grid(int nb) { return nb * (nb + 1) / 2; }
 
@@ -673,8 +776,38 @@ int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
   // process-wide unique, never 0 (flag buffers start zeroed); a wrap after 2^31 launches would need the flags of a
   // buffer to hold exactly the value 2^31 launches old: not a practical concern
   a.epoch = int(epoch_src.fetch_add(1, std::memory_order_relaxed) % 0x7ffffffeu) + 1;
+  // first choice: clusters of 8 consecutive CTAs (the chain's hops go through distributed shared memory), still a
+  // cooperative launch (every CTA resident: the CTAs spin on each other's messages)
+  static std::atomic<int> cluster_state{-1};  // -1 untested, 0 unavailable / switched off, 1 in use
+  if (cluster_state.load(std::memory_order_relaxed) < 0) {
+    const char* v = std::getenv("CTVIO_CHOL_CLUSTER");
+    if (v && v[0] == '0') cluster_state.store(0);
+  }
+  const int total = dag_grid(l.npad / kCholNB);
+  if (cluster_state.load(std::memory_order_relaxed) != 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned((total + kDagCluster - 1) / kDagCluster * kDagCluster));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = kCholDagSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kDagCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    const cudaError_t cerr = cudaLaunchKernelEx(&cfg, chol_dag_kernel, a);
+    if (cerr == cudaSuccess) {
+      cluster_state.store(1, std::memory_order_relaxed);
+      g_dag_cluster_launches.fetch_add(1, std::memory_order_relaxed);
+      return 1;
+    }
+    cudaGetLastError();
+    if (cluster_state.load(std::memory_order_relaxed) < 0) cluster_state.store(0, std::memory_order_relaxed);  // never worked here
+  }
   void* args[] = {&a};
-  const cudaError_t err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_dag_kernel), dim3(dag_grid(l.npad / kCholNB)),
+  const cudaError_t err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_dag_kernel), dim3(total),
                                                       dim3(256), args, kCholDagSmem, s);
   if (err != cudaSuccess) {
     // the flag protocol needs every CTA resident; if the runtime cannot promise that (MIG slice, fewer usable SMs than
@@ -684,5 +817,8 @@ int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
   }
   return 1;
 }
+
+// test / tools hook: launches of the tile-DAG kernel that ran with thread-block clusters so far
+extern "C" long long ctvio_debug_chol_cluster_launches() { return g_dag_cluster_launches.load(); }
 
 }  // namespace ctvio

@@ -29,3 +29,9 @@ for name in ("c2", "c4"):
     print("  diag factor of column 0 (cycles since loop start), per 16-col step: loop top | P2a done | after barrier | before end barrier ; pub done (warps>0)")
     for s_ in range(4):
         print("   step %d: " % s_ + "  ".join("w%d %5d %5d %5d %5d p%5d" % (w_, fc[w_, s_, 0] - t00, fc[w_, s_, 1] - t00, fc[w_, s_, 2] - t00, fc[w_, s_, 3] - t00, fc[w_, s_, 4] - t00) for w_ in (0, 1, 2, 7)))
+try:
+    f = LIB.lib.ctvio_debug_chol_cluster_launches
+    f.restype = C.c_longlong
+    print("tile-DAG launches that used thread-block clusters:", f())
+except AttributeError:
+    pass
