@@ -139,9 +139,12 @@ struct ctvio_engine {
   // state: two buffers (current / candidate) + snapshot
   DevState x[2], snap;
   DevState xs;                 // third state buffer of the pipelined LM driver (swapped into x[] when it ends up current)
+  DevBuf<LmPublished> d_pubstage;  // device staging copy of the published block (forwarded to h_pub from stream2)
   DevBuf<LmDecision> d_dec;    // device-side step decision (accept, next radius) read by the speculated linear solve
   cudaEvent_t ev_iter = nullptr;  // recorded behind the last kernel of every LM step (before anything speculative)
   bool speculate = true;       // CTVIO_NO_SPECULATION=1 switches the pipelined driver off
+  bool staged_publish = false; // CTVIO_STAGED_PUBLISH=1: the scalar block reaches the host through a device staging copy
+                               // forwarded from stream2 (measured: C2 +2.5 %, C4 -0.7 % - off by default)
   DevState& state(int i) { return i < 2 ? x[i] : xs; }
   int cur = 0;
   bool table_valid = false;
@@ -936,6 +939,7 @@ int read_scalars(ctvio_engine* e, bool published = false) {
       if ((++spins & 0xfffu) == 0 && cudaStreamQuery(e->stream) != cudaErrorNotReady) {
         if (*seq == e->pub_seq) break;
         CUDA_OK(cudaStreamSynchronize(e->stream));
+        CUDA_OK(cudaStreamSynchronize(e->stream2));  // (pipelined driver: the publication is forwarded from stream2)
         if (*seq != e->pub_seq) return fail(CTVIO_ERR_CUDA, "LM step finished without publishing its scalars");
       }
     }
@@ -1005,6 +1009,7 @@ int ctvio_create(const ctvio_config* cfg, ctvio_handle* out) {
   for (int k = 0; k < 6; ++k) e->rig.imu_info[k] = cfg->imu_info[k];
   if (const char* det = std::getenv("CTVIO_DETERMINISTIC")) e->deterministic = det[0] == '1';
   if (const char* ns = std::getenv("CTVIO_NO_SPECULATION")) e->speculate = ns[0] != '1';
+  if (const char* dp = std::getenv("CTVIO_STAGED_PUBLISH")) e->staged_publish = dp[0] == '1';
   const char* no_tma = std::getenv("CTVIO_NO_TMA");
   e->use_tma = !(no_tma && no_tma[0] == '1');
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1013,7 +1018,7 @@ int ctvio_create(const ctvio_config* cfg, ctvio_handle* out) {
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_zero, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreate(&e->ev_iter) != cudaSuccess || e->d_dec.reserve(1) != cudaSuccess ||
+      cudaEventCreate(&e->ev_iter) != cudaSuccess || e->d_dec.reserve(1) != cudaSuccess || e->d_pubstage.reserve(1) != cudaSuccess ||
       cudaHostAlloc(&e->h_pub, sizeof(LmPublished), cudaHostAllocMapped) != cudaSuccess ||
       cudaMallocHost(&e->h_scal, sizeof(LmScalars)) != cudaSuccess || e->d_scal.reserve(1) != cudaSuccess ||
       e->d_ticket.reserve(4) != cudaSuccess) {
@@ -1383,8 +1388,14 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
       const LmDecideArgs da{e->d_dec.p, x_cost, radius, min_relative_decrease, max_radius,
                             parameter_tolerance, function_tolerance, gradient_tolerance, min_radius};
       e->launches += launch_gradient_norm(linear_launch(e, cand_ne), e->state(cand).ptrs(), e->opt.fix_ld, e->opt.ld_lower,
-                                          e->opt.ld_upper, st, false, e->h_pub, ++e->pub_seq, &da);
+                                          e->opt.ld_upper, st, false, e->staged_publish ? e->d_pubstage.p : e->h_pub, ++e->pub_seq,
+                                          &da);
       cudaEventRecord(e->ev_iter, st);
+      if (e->staged_publish) {
+        // the block goes to the host from the second stream: its PCIe round trip overlaps the speculated linear solve
+        cudaStreamWaitEvent(e->stream2, e->ev_iter, 0);
+        e->launches += launch_publish(e->d_pubstage.p, e->h_pub, e->stream2);
+      }
       // ---- speculate: step iter + 1 from (cand, cand_ne), radius from the device-side decision ----
       spec_ready = false;
       if (iter < max_iterations) {

@@ -290,6 +290,7 @@ int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s);
 // the three stages of launch_lm_step, separately launchable for measurement
 // radius_dev != null: the radius is read from device memory (first double of an LmDecision)
 int launch_reduced_system(const LinearLaunch& a, double radius, cudaStream_t s, const double* radius_dev = nullptr);
+int launch_publish(const LmPublished* stage, LmPublished* pub, cudaStream_t s);
 int launch_factor_solve(const LinearLaunch& a, cudaStream_t s);
 // tile-DAG variant (chol_dag.cu): usable when every tile gets its own SM
 bool chol_dag_supported(int npad, int n_sm);

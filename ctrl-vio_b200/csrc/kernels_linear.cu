@@ -13,6 +13,8 @@
 #include <algorithm>
 
 #include "dmma_tiles.cuh"
+#include <cstddef>
+
 #include "kernels.h"
 
 namespace ctvio {
@@ -372,15 +374,18 @@ int launch_lm_step(const LinearLaunch& a, double radius, cudaStream_t s) {
   return launch_reduced_system(a, radius, s) + launch_factor_solve(a, s) + launch_step_vectors(a, s);
 }
 
-// max-norm of the (bounds-projected) gradient over the active parameters; ONE CTA (the vectors are small), so the
-// result needs no atomics and the same CTA can hand the finished scalar block of the LM step to the host
+// max-norm of the (bounds-projected) gradient over the active parameters; a few CTAs (one per 1024 entries, at most
+// 16), combined with an integer atomicMax on the bit pattern (the values are non-negative); the CTA that arrives
+// last hands the finished scalar block of the LM step to `pub`: mapped host memory, or a device staging block that
+// publish_kernel forwards from a second stream (pipelined driver: the PCIe write round trip of the publication then
+// overlaps the next step's linear solve instead of delaying it)
 __global__ void __launch_bounds__(1024) gradient_norm_kernel(LinearLaunch a, StatePtrs st, int fix_ld, double ld_lower,
                                                              double ld_upper, LmPublished* pub, unsigned long long seq,
                                                              LmDecideArgs da) {
   __shared__ double red[32];
   const int np = a.dims.np, nL = a.dims.nL;
   double v = 0.0;
-  for (int i = threadIdx.x; i < np + nL; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np + nL; i += gridDim.x * blockDim.x) {
     if (!a.active[i]) continue;
     double x;
     if (i < np) {
@@ -400,8 +405,16 @@ __global__ void __launch_bounds__(1024) gradient_norm_kernel(LinearLaunch a, Sta
   if (threadIdx.x < 32) {
     v = warp_max_d(red[threadIdx.x]);
     if (threadIdx.x == 0) {
-      a.scal->gmax = fmax(a.scal->gmax, v);
-      if (pub) {
+      bool last = true;
+      if (gridDim.x > 1) {
+        atomicMax(reinterpret_cast<unsigned long long*>(&a.scal->gmax), static_cast<unsigned long long>(__double_as_longlong(v)));
+        __threadfence();
+        last = atomicAdd(&a.scal->pad[0], 1) == int(gridDim.x) - 1;
+        if (last) a.scal->pad[0] = 0;  // (the arrival counter of the next launch)
+      } else {
+        a.scal->gmax = fmax(a.scal->gmax, v);
+      }
+      if (last && pub) {
         // the other kernels' atomics into the scalar block are complete (stream order) and live in L2: fetch the block
         // with six independent 16-byte L2 loads (one latency instead of eleven volatile reads) and hand it
         // to the host
@@ -455,7 +468,32 @@ int launch_gradient_norm(const LinearLaunch& a, const StatePtrs& st, int fix_ld,
   if (reset) cudaMemsetAsync(&a.scal->gmax, 0, sizeof(double), s);
   LmDecideArgs da{};
   if (decide) da = *decide;
-  gradient_norm_kernel<<<1, 1024, 0, s>>>(a, st, fix_ld, ld_lower, ld_upper, pub, seq, da);
+  const int n = a.dims.np + a.dims.nL;
+  const int grid = std::min(16, std::max(1, (n + 1023) / 1024));
+  gradient_norm_kernel<<<grid, 1024, 0, s>>>(a, st, fix_ld, ld_lower, ld_upper, pub, seq, da);
+  return 1;
+}
+
+// staging block (device) -> mapped host memory, on a stream of its own
+__global__ void publish_kernel(const LmPublished* __restrict__ stage, LmPublished* pub) {
+  if (threadIdx.x == 0) {
+    static_assert(sizeof(LmPublished) % 16 == 0, "copied as 16-byte words");
+    constexpr int kWords = int(offsetof(LmPublished, seq) / 16);
+    static_assert(offsetof(LmPublished, seq) % 16 == 0, "payload is a whole number of 16-byte words");
+    const uint4* src = reinterpret_cast<const uint4*>(stage);
+    uint4* dst = reinterpret_cast<uint4*>(pub);
+    uint4 w[kWords];
+#pragma unroll
+    for (int k = 0; k < kWords; ++k) w[k] = __ldcg(src + k);
+    const unsigned long long seq = __ldcg(&stage->seq);
+#pragma unroll
+    for (int k = 0; k < kWords; ++k) dst[k] = w[k];
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&pub->seq) = seq;
+  }
+}
+int launch_publish(const LmPublished* stage, LmPublished* pub, cudaStream_t s) {
+  publish_kernel<<<1, 32, 0, s>>>(stage, pub);
   return 1;
 }
 
