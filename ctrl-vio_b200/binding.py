@@ -113,16 +113,13 @@ DEVICE_ONLY_SYMBOLS = ("nccl_unique_id", "comm_init", "set_deterministic", "enab
                        "transfer_stats", "residual_summary")
 
 
-def _dp(a):
-    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+def _addr(a):
+    # (numpy's `.ctypes.data_as(...)` costs ~2.3 us per array; the raw address as a void pointer ~1.3 us: the host-buffer
+    #  path passes ~25 arrays per window)
+    return C.c_void_p(a.__array_interface__["data"][0]) if a is not None else None
 
 
-def _ip(a):
-    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
-
-
-def _lp(a):
-    return a.ctypes.data_as(C.POINTER(C.c_int64)) if a is not None else None
+_dp = _ip = _lp = _addr
 
 
 def _f64(a, shape=None):

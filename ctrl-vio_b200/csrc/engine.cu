@@ -1352,7 +1352,15 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
   // reading its radius from device memory and writing its candidate into a third state buffer.  When the host then
   // finds step i rejected / invalid / terminating, the speculated kernels' results are simply never used (they touch
   // only the step vectors, the free state buffer and per-step scalars that the next real step resets).
-  const bool pipelined = e->speculate && !sharded && !is_constrained && !e->deterministic;
+  // Measured (profiles/r2/README.md): -2.5 % at C2 / C5 sizes, but +8 % per LM step at 100 k observations and more, with
+  // identical kernels and a host that is provably ahead (CTVIO_LM_TRACE) - cause not found; the round trip it hides is
+  // 1 % of such a step anyway.  CTVIO_SPECULATION=always / never overrides the size test.
+  bool spec_size_ok = e->img.size() <= 20000;
+  if (const char* sp = std::getenv("CTVIO_SPECULATION")) {
+    if (std::strcmp(sp, "always") == 0) spec_size_ok = true;
+    if (std::strcmp(sp, "never") == 0) spec_size_ok = false;
+  }
+  const bool pipelined = e->speculate && spec_size_ok && !sharded && !is_constrained && !e->deterministic;
   int cur_ne = cur;  // normal-equation buffer of the current point (state and normal equations flip separately here)
   if (pipelined) {
     rc = alloc_state(e, e->xs);
@@ -1361,6 +1369,8 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     bool spec_in_flight = false; // speculated kernels that read ne_slab[cur_ne ^ 1] may still be running
     int spec_out = -1;
     unsigned spec_chol_seq0 = e->chol_seq;
+    double host_spec_us = 0, host_wait_us = 0;
+    static const bool lm_trace = std::getenv("CTVIO_LM_TRACE") != nullptr;  // host-side timing of the driver
     cudaEventRecord(e->ev_iter, st);
     while (true) {
       if (iter >= max_iterations) { term = CTVIO_TERM_NO_CONVERGENCE; break; }
@@ -1403,12 +1413,16 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
         while (spec_out == cur || spec_out == cand) ++spec_out;
         const ApplyLaunch spec_step = make_apply(cand, spec_out, 1.0);
         spec_chol_seq0 = e->chol_seq;
+        const auto th0 = std::chrono::steady_clock::now();
         rc = lm_step(e, cand_ne, 0.0, &spec_step, &e->d_dec.p->radius_next, &e->d_dec.p->go);
         if (rc) return rc;
         spec_ready = true;
         spec_in_flight = true;
+        host_spec_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - th0).count();
       }
+      const auto th1 = std::chrono::steady_clock::now();
       rc = read_scalars(e, true);
+      host_wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - th1).count();
       if (rc) return rc;
       const LmScalars sc = *e->h_scal;
       const LmDecision dec = const_cast<const LmPublished*>(e->h_pub)->dec;
@@ -1476,6 +1490,7 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
     CUDA_OK(cudaStreamSynchronize(e->stream2));
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev0, e->ev_iter);
+    if (lm_trace) std::fprintf(stderr, "[lm] iters %d device %.3f ms host: spec enqueue %.1f us/iter, wait %.1f us/iter\n", iter, ms, host_spec_us / std::max(iter, 1), host_wait_us / std::max(iter, 1));
     sum.iterations = iter;
     sum.termination = term;
     sum.final_cost = x_cost;
