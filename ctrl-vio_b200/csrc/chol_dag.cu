@@ -778,13 +778,12 @@ int launch_chol_dag(const LinearLaunch& l, cudaStream_t s) {
   a.epoch = int(epoch_src.fetch_add(1, std::memory_order_relaxed) % 0x7ffffffeu) + 1;
   // first choice: clusters of 8 consecutive CTAs (the chain's hops go through distributed shared memory), still a
   // cooperative launch (every CTA resident: the CTAs spin on each other's messages)
-  static std::atomic<int> cluster_state{-1};  // -1 untested, 0 unavailable / switched off, 1 in use
-  if (cluster_state.load(std::memory_order_relaxed) < 0) {
-    const char* v = std::getenv("CTVIO_CHOL_CLUSTER");
-    if (v && v[0] == '0') cluster_state.store(0);
-  }
+  static std::atomic<int> cluster_state{-1};  // -1 untested, 0 unavailable on this system, 1 in use
+  bool want_cluster = cluster_state.load(std::memory_order_relaxed) != 0;
+  if (const char* v = std::getenv("CTVIO_CHOL_CLUSTER"))  // re-read on every call (tests switch it)
+    if (v[0] == '0') want_cluster = false;
   const int total = dag_grid(l.npad / kCholNB);
-  if (cluster_state.load(std::memory_order_relaxed) != 0) {
+  if (want_cluster) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned((total + kDagCluster - 1) / kDagCluster * kDagCluster));
     cfg.blockDim = dim3(256);

@@ -454,3 +454,59 @@ def test_eigen_solvers_match_lapack(cuda_lib, n, rank_deficient, monkeypatch):
         assert np.max(np.abs(np.sort(ev) - ref)) <= 1e-13 * scale, mode
         assert np.max(np.abs(v.T @ v - np.eye(n))) <= 1e-12, mode
         assert np.max(np.abs((v * ev) @ v.T - a)) <= 1e-12 * scale, mode
+
+
+def _perturbed_c1(seed, scale):
+    """C1 started far from the optimum: the trust region rejects a good third of its steps, and one of the two cases ends on
+    the function tolerance (found with the oracle; the step counts are asserted below)."""
+    w = syn.config_c1()
+    rng = np.random.default_rng(seed)
+    w.p0 = w.p0 + scale * rng.standard_normal(w.p0.shape)
+    w.rho0 = w.rho0 * np.exp(np.clip(scale * rng.standard_normal(w.rho0.shape), -3, 3))
+    return w
+
+
+@pytest.mark.parametrize("seed,scale,expect_rejects", [(3, 2.0, 10), (5, 20.0, 5)])
+def test_lm_driver_with_rejected_steps_matches_oracle(oracle_lib, cuda_lib, monkeypatch, seed, scale, expect_rejects):
+    """The pipelined LM driver (device-side accept / radius decision, speculative linear solve of the next step, cancelled
+    on the device when the step is rejected or the solve terminates) and the plain one against the oracle on problems
+    with many rejected steps: the same step-by-step history (trust_region_minimizer.cc semantics: every accept / reject
+    decision and the termination test of 25 steps).  These runs start far from the optimum and stop unconverged, so the
+    end point itself is sensitive to rounding (measured: 3e-6 relative in the cost between the GPU and the oracle): the
+    states are compared with a correspondingly loose tolerance, the histories exactly."""
+    w = _perturbed_c1(seed, scale)
+    o = pkg.setup_estimator(oracle_lib, w)
+    so = o.Solve(25)
+    assert so.num_unsuccessful_steps == expect_rejects
+    so2 = o.Solve(5)
+    for mode in ("always", "never"):
+        monkeypatch.setenv("CTVIO_SPECULATION", mode)
+        g = pkg.setup_estimator(cuda_lib, w)
+        sg = g.Solve(25)
+        assert (sg.iterations, sg.num_successful_steps, sg.num_unsuccessful_steps, sg.termination) == \
+            (so.iterations, so.num_successful_steps, so.num_unsuccessful_steps, so.termination), mode
+        assert np.isclose(sg.final_cost, so.final_cost, rtol=1e-4), mode
+        # the engine is reusable after cancelled speculation (message-buffer parity of the tile-DAG solver, state buffers)
+        sg2 = g.Solve(5)
+        assert (sg2.iterations, sg2.termination) == (so2.iterations, so2.termination), mode
+        assert np.isclose(sg2.final_cost, so2.final_cost, rtol=1e-4), mode
+        assert_state_parity(g, o, tol_t=1e-3, tol_r=1e-3, aux_rtol=1e-2)
+
+
+def test_tile_dag_cluster_and_plain_launch_agree_bitwise(cuda_lib, monkeypatch):
+    """K5 with thread-block clusters (chain messages through distributed shared memory) and without (through L2): the
+    arithmetic is the same, only the transport differs - in deterministic mode the two solves are bit-identical."""
+    states = []
+    for cluster in ("1", "0"):
+        monkeypatch.setenv("CTVIO_CHOL_CLUSTER", cluster)
+        g = pkg.setup_estimator(cuda_lib, syn.config_c2())
+        g.SetDeterministic(True)
+        s = g.Solve(6)
+        states.append((s.final_cost,) + tuple(get_state(g)))
+    f = cuda_lib.lib.ctvio_debug_chol_cluster_launches
+    f.restype = __import__("ctypes").c_longlong
+    assert f() > 0, "the cluster launch path never ran"
+    a, b = states
+    assert a[0] == b[0]
+    for x, y in zip(a[1:], b[1:]):
+        assert np.array_equal(np.asarray(x), np.asarray(y))
