@@ -174,6 +174,18 @@ class StreamingRunner:
         if not first and self.predictor:
             init_sel = np.nonzero((w.imu_t >= max_bef_ns) & (w.imu_t < max_t))[0]
         h2d = 0
+        # the host buffers the front end hands over (factor order as the reference's containers would give it): built
+        # here, outside the timed region, like the rest of the slicing
+        img_args = tuple(np.ascontiguousarray(a[pi_]) for a in (w.ti, w.rowi, w.pi, w.tj, w.rowj, w.pj, w.lm, img_marg))
+        imu_args = tuple(np.ascontiguousarray(a[pm]) for a in (w.imu_t, w.imu_gyro, w.imu_accel, w.imu_node, imu_marg))
+        init_args = None
+        if init_sel is not None and len(init_sel) > 0:
+            init_args = (np.ascontiguousarray(w.imu_t[init_sel]), np.ascontiguousarray(w.imu_gyro[init_sel]),
+                         np.ascontiguousarray(w.imu_accel[init_sel]), np.full(len(init_sel), len(frames) - 1, np.int32))
+        opt_init = None if init_args is None else self._make_options(fixed_knot_index=max_bef_idx - ks, lock_wb=True, lock_ab=True,
+                                                                    fix_ld=True)
+        opt_main = self._make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER, is_marg_state=(marg_flag == MARGIN_OLD),
+                                      ctrl_to_be_opt_now=nowk, ctrl_to_be_opt_later=later)
 
         # ---- timed region: everything that crosses the C-ABI ----
         stats = e.lib.has("transfer_stats")
@@ -184,24 +196,20 @@ class StreamingRunner:
         e.SetKnots(q, p); e.SetBiases(b); e.SetInvDepths(rho); e.SetLineDelay(self.ld)
         h2d += q.nbytes + p.nbytes + b.nbytes + rho.nbytes + 8
         init_summary = None
-        if init_sel is not None and len(init_sel) > 0:
+        if init_args is not None:
             # InitTrajectory: IMU only, new control points only, biases locked at the newest keyframe's estimate
-            e.SetOptions(self._make_options(fixed_knot_index=max_bef_idx - ks, lock_wb=True, lock_ab=True, fix_ld=True))
+            e.SetOptions(opt_init)
             e.ClearFactors()
             e.AddMarginalizationFactor(None)
-            node = np.full(len(init_sel), len(frames) - 1, np.int32)
-            e.AddIMUMeasurementAnalytic(w.imu_t[init_sel], w.imu_gyro[init_sel], w.imu_accel[init_sel], node)
+            e.AddIMUMeasurementAnalytic(*init_args)
             h2d += len(init_sel) * 64
             init_summary = e.Solve(self.init_iters)
         # UpdateTrajectory
-        e.SetOptions(self._make_options(fix_ld=False, ld_lower=0.0, ld_upper=syn.LD_UPPER,
-                                        is_marg_state=(marg_flag == MARGIN_OLD), ctrl_to_be_opt_now=nowk,
-                                        ctrl_to_be_opt_later=later))
+        e.SetOptions(opt_main)
         e.ClearFactors()
         e.AddMarginalizationFactor(prior)
-        e.AddImageFeatureDelayAnalytic(w.ti[pi_], w.rowi[pi_], w.pi[pi_], w.tj[pi_], w.rowj[pi_], w.pj[pi_], w.lm[pi_],
-                                       img_marg[pi_])
-        e.AddIMUMeasurementAnalytic(w.imu_t[pm], w.imu_gyro[pm], w.imu_accel[pm], w.imu_node[pm], imu_marg[pm])
+        e.AddImageFeatureDelayAnalytic(*img_args)
+        e.AddIMUMeasurementAnalytic(*imu_args)
         e.AddBiasFactor(w.bf_i, w.bf_j, w.bf_sqrt_info, bias_marg)
         h2d += w.n_obs * 64 + len(w.imu_t) * 64 + len(w.bf_i) * 56 + (0 if prior is None else prior.n * prior.n * 8)
         # pre-solve pose of the window's first control point (R0, t0 of UpdateTrajectory:329-331) -- AFTER InitTrajectory
