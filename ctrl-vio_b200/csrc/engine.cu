@@ -2206,19 +2206,27 @@ int ctvio_marginalize(ctvio_handle e, int32_t* n_out, int32_t* nb_out) {
     a.st = e->x[e->cur].ptrs(); a.sp = e->sp; a.rig = e->rig; a.cauchy = e->cfg.cauchy_marg;
     a.pos_cam = d_pos_cam.p; a.pos_lm = d_pos_lm.p; a.idx_ld = d.idx_ld;
     a.Jrow = ws.Jrow.p; a.ldj = ldj; a.row0 = row_img; a.P = P; a.scal = e->d_scal.p;
+    // the three row kernels write disjoint row ranges of Jrow: one stream each, joined before the SYRK
+    cudaEventRecord(e->ev_fork, st);
     e->launches += ctvio::launch_marg_image(a, st);
     ctvio::MargImuArgs b;
     b.obs = ImuObsPtrs{e->d_imu_t.p, e->d_imu_ga.p, int32_t(e->imu.size())};
     b.marg_index = d_marg_imu.p; b.n_marg = int32_t(marg_imu.size());
     b.st = a.st; b.sp = e->sp; b.rig = e->rig; b.pos_cam = d_pos_cam.p; b.idx_bias0 = d.idx_bias0;
     b.Jrow = ws.Jrow.p; b.ldj = ldj; b.row0 = row_imu; b.P = P; b.scal = e->d_scal.p;
-    e->launches += ctvio::launch_marg_imu(b, st);
+    cudaStreamWaitEvent(e->stream2, e->ev_fork, 0);
+    e->launches += ctvio::launch_marg_imu(b, e->stream2);
+    cudaEventRecord(e->ev_join, e->stream2);
     ctvio::MargSmallArgs c;
     c.bf_ij = d_bij.p; c.bf_s = d_bs.p; c.n_bias = int32_t(bij.size());
     c.prior = prior_ptrs(e); c.use_prior = use_prior ? 1 : 0; c.prior_pos = d_prior_pos.p;
     c.st = a.st; c.pos_cam = d_pos_cam.p; c.idx_bias0 = d.idx_bias0;
     c.Jrow = ws.Jrow.p; c.ldj = ldj; c.row0_bias = row_bias; c.row0_prior = row_prior; c.P = P;
-    e->launches += ctvio::launch_marg_small(c, st);
+    cudaStreamWaitEvent(e->stream3, e->ev_fork, 0);
+    e->launches += ctvio::launch_marg_small(c, e->stream3);
+    cudaEventRecord(e->ev_join3, e->stream3);
+    cudaStreamWaitEvent(st, e->ev_join, 0);
+    cudaStreamWaitEvent(st, e->ev_join3, 0);
     e->launches += ctvio::launch_marg_syrk(ws.Jrow.p, R, ldj, P, d_A.p, d_b.p, st);
   }
   // ---- dense Schur complement through eigen-decompositions (marginalization_factor.cpp:240-263) ----
