@@ -1324,10 +1324,17 @@ int ctvio_solve(ctvio_handle e, int32_t max_iterations, ctvio_summary* out) {
   } else {
     e->launches += launch_jacobi_scale(lin, st);
   }
-  e->launches += launch_gradient_norm(lin, e->x[cur].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st);
-  rc = allreduce_scalars(e);
-  if (rc) return rc;
-  rc = read_scalars(e);
+  if (sharded) {
+    e->launches += launch_gradient_norm(lin, e->x[cur].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st);
+    rc = allreduce_scalars(e);
+    if (rc) return rc;
+    rc = read_scalars(e);
+  } else {
+    // (published through mapped memory like every later step: no copy + stream synchronisation)
+    e->launches += launch_gradient_norm(lin, e->x[cur].ptrs(), e->opt.fix_ld, e->opt.ld_lower, e->opt.ld_upper, st, true, e->h_pub,
+                                        ++e->pub_seq);
+    rc = read_scalars(e, true);
+  }
   if (rc) return rc;
   double x_cost = e->h_scal->cost_eval;
   double gmax = e->h_scal->gmax;  // sharded: the all-gathered maximum
